@@ -1,0 +1,103 @@
+/*
+ * ua3reo_b200.h - C ABI of libua3reo_b200.so: the UA3REO receive path (FPGA DDC + STM32 audio/FFT
+ * stage, TX DUC as mirror) batched over many channels that tap one shared 12-bit ADC stream, on
+ * one NVIDIA B200 (sm_100a).  Plain C: pointers, sizes and integers only.
+ *
+ * The reference has no FFI: its path sits behind void functions over global buffers
+ * (SURVEY.md 8b).  Each entry point below names the reference interface it stands in for
+ * (file:line under the reference tree).  Single-channel shims that keep the firmware's own
+ * names live in ua3reo_fw_shim.h.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative UA3_E_* code; ua3reo_last_error() gives
+ *     the message of the calling thread's last failure.  (The firmware's functions return void
+ *     and report through flags - FPGA_Buffer_underrun, fpga.c:16 - which has no batched analogue.)
+ *   - the library owns all device state; the caller owns every host buffer it passes in.
+ *   - one host thread per context; all work of a context is ordered on one CUDA stream.
+ *   - there is NO CPU fallback: without a usable CUDA device ua3reo_create() fails.
+ */
+#ifndef UA3REO_B200_H
+#define UA3REO_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UA3_OK 0
+#define UA3_E_INVAL (-1)      /* bad argument */
+#define UA3_E_CUDA (-2)       /* CUDA runtime error (see ua3reo_last_error) */
+#define UA3_E_NODEV (-3)      /* no CUDA device / not an sm_100 device */
+#define UA3_E_TOOBIG (-4)     /* push larger than the context's max_block_samples */
+#define UA3_E_STATE (-5)      /* call sequence error (e.g. reading frames before any push) */
+
+#define UA3_ADC_PER_FRAME 1024u   /* rx_cic R=512 (rx_cic.vhd:27) x rx_ciccomp /2 (rx_ciccomp.vhd:25) */
+#define UA3_FRAME_BYTES 8u        /* stm32_interface.v:228-271 */
+#define UA3_AUDIO_BLOCK 192u      /* audio_processor.h:10-12 FPGA_AUDIO_BUFFER_HALF_SIZE */
+#define UA3_FFT_SIZE 512u         /* fft.h:10 */
+#define UA3_FFT_BINS 256u         /* fft.h:12 FFT_PRINT_SIZE */
+
+typedef struct ua3reo_ctx ua3reo_ctx;
+
+/* Version / capability string, e.g. "ua3reo_b200 0.1 sm_100a". */
+const char *ua3reo_version(void);
+const char *ua3reo_last_error(void);
+
+/* Replaces the power-on reset of the FPGA fabric + FPGA_Init()/initAudioProcessor()/FFT_Init()
+ * (fpga.c:41-55, audio_processor.c:55-59, fft.c:185-210; init order main.c:188-193) for n_channels
+ * independent receivers.  max_block_samples: largest ADC block one push may carry (multiple of
+ * 1024; 0 selects 2^20).  All tuning words start at the FPGA's power-on value 620407
+ * (stm32_interface.v:56). */
+int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, ua3reo_ctx **out);
+int ua3reo_destroy(ua3reo_ctx *ctx);
+
+/* reset_n of the RX chain (UA3REO.bdf RX_N net): clears NCO phases and every filter state. */
+int ua3reo_reset(ua3reo_ctx *ctx);
+
+uint32_t ua3reo_n_channels(const ua3reo_ctx *ctx);
+uint32_t ua3reo_max_block_samples(const ua3reo_ctx *ctx);
+
+/* 22-bit NCO tuning words for channels [first, first+n).  Replaces the cmd-1 parameter frame
+ * (stm32_interface.v:142-171 <- fpga.c:173-220). Takes effect at the next push. */
+int ua3reo_set_fcw(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const uint32_t *fcw22);
+int ua3reo_get_fcw(ua3reo_ctx *ctx, uint32_t first, uint32_t n, uint32_t *fcw22);
+
+/* uint32_t getPhraseFromFrequency(uint32_t freq) (functions.c:206-226): Nyquist-zone folding and
+ * FCW = round(f / 49152000 * 2^22); *iq_swap receives TRX_IQ_swap.  Pure host function. */
+uint32_t ua3reo_phrase_from_frequency(uint32_t freq_hz, int *iq_swap);
+/* TRX_setFrequency for one channel: FCW from the above, and the channel's IQ-swap flag. */
+int ua3reo_set_frequency(ua3reo_ctx *ctx, uint32_t channel, uint32_t freq_hz);
+
+/* The FPGA receive chain for every channel over n new ADC samples (12-bit two's complement,
+ * sign-extended to int16; ADC_INPUT[11..0], UA3REO.bdf:26).  Samples are buffered until whole
+ * 1024-sample frames are available; *frames_out (optional) receives the number of 48 kHz frames
+ * produced per channel by this call.  n + carried remainder must not exceed max_block_samples.
+ *   ua3reo_ddc_push        : adc in host memory (copied to the device inside the call)
+ *   ua3reo_ddc_push_device : adc already in device memory of the context's device
+ * Both are asynchronous with respect to the host; ua3reo_sync() or a read waits. */
+int ua3reo_ddc_push(ua3reo_ctx *ctx, const int16_t *adc_host, size_t n, size_t *frames_out);
+int ua3reo_ddc_push_device(ua3reo_ctx *ctx, const int16_t *adc_dev, size_t n, size_t *frames_out);
+
+/* The I/Q words of the last push, in the byte order the FPGA puts on the bus on command 4
+ * (stm32_interface.v:228-271; consumer FPGA_fpgadata_getiq, fpga.c:286-401):
+ *   SPEC_Q hi, lo, SPEC_I hi, lo, VOICE_Q hi, lo, VOICE_I hi, lo.
+ * dst is [n_channels][n_frames][8] bytes; n_frames must equal the last push's frames_out. */
+int ua3reo_ddc_read_frames(ua3reo_ctx *ctx, uint8_t *dst_host, size_t n_frames);
+/* Device view of the same data: base pointer, frames of the last push, bytes between channels. */
+int ua3reo_ddc_frames_device(ua3reo_ctx *ctx, const uint8_t **base, size_t *n_frames, size_t *channel_stride_bytes);
+
+int ua3reo_sync(ua3reo_ctx *ctx);
+/* The context's CUDA stream (cudaStream_t), for callers that enqueue their own copies. */
+int ua3reo_stream(ua3reo_ctx *ctx, void **stream);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t ua3reo_launch_count(const ua3reo_ctx *ctx);
+
+/* Dependent-free INT32 issue-rate microbenchmark (IADD3 + IMAD interleaved) used as the roofline
+ * denominator: returns integer operations per second summed over the whole device. */
+int ua3reo_measure_int32_peak(int device, double *ops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,84 @@
+"""ctypes binding of the CPU checker (oracle/_build/libua3_oracle.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_build", "libua3_oracle.so")
+DDC_STATE_BYTES = 4096   # >= sizeof(ua3g_ddc)
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(LIB)
+            for f in os.listdir(_HERE) if f.endswith((".c", ".h"))):
+        subprocess.check_call(["make", "-s", "-C", _HERE])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(LIB)
+        L.ua3g_ddc_push.restype = ctypes.c_size_t
+        L.ua3g_ddc_push.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                    ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
+        L.ua3g_ddc_init.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+        L.ua3g_phrase_from_frequency.restype = ctypes.c_uint32
+        L.ua3g_phrase_from_frequency.argtypes = [ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
+        L.ua3g_nco.argtypes = [ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
+        L.ua3g_rx_mix.restype = ctypes.c_int32
+        L.ua3g_rx_mix.argtypes = [ctypes.c_int32, ctypes.c_int32]
+        _lib = L
+    return _lib
+
+
+class GoldenDDC:
+    """One channel of the register-transfer golden DDC (ddc_golden.c); state persists across push()."""
+
+    def __init__(self, fcw):
+        self._st = ctypes.create_string_buffer(DDC_STATE_BYTES)
+        lib().ua3g_ddc_init(self._st, int(fcw) & 0x3FFFFF)
+
+    def push(self, adc, want_cic=False):
+        adc = np.ascontiguousarray(adc, dtype=np.int16)
+        cap = adc.size // 1024 + 2
+        frames = np.zeros((cap, 8), np.uint8)
+        ncic = ctypes.c_size_t(0)
+        if want_cic:
+            ccap = adc.size // 512 + 2
+            ci = np.zeros(ccap, np.int16); cq = np.zeros(ccap, np.int16)
+            nf = lib().ua3g_ddc_push(self._st, adc.ctypes.data, adc.size, frames.ctypes.data, cap,
+                                     ci.ctypes.data, cq.ctypes.data, ccap, ctypes.byref(ncic))
+            return frames[:nf].copy(), ci[:ncic.value].copy(), cq[:ncic.value].copy()
+        nf = lib().ua3g_ddc_push(self._st, adc.ctypes.data, adc.size, frames.ctypes.data, cap, None, None, 0, None)
+        return frames[:nf].copy()
+
+
+def golden_frames(adc, fcws):
+    """uint8 [n_ch, n_frames, 8] for a list of tuning words over one ADC stream."""
+    out = []
+    for w in fcws:
+        out.append(GoldenDDC(w).push(adc))
+    return np.stack(out)
+
+
+def synth_adc(n, seed=20261018, tones=8, noise_lsb=8.0, level_dbfs=-6.0):
+    """Synthetic 12-bit ADC stream of SURVEY.md 8(d): K tones + white Gaussian noise, clipped to 12 bit."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64)
+    f = rng.uniform(0.02, 0.48, tones)
+    ph = rng.uniform(0, 2 * np.pi, tones)
+    amp = 2047.0 * 10 ** (level_dbfs / 20.0) / tones
+    x = np.zeros(n)
+    for k in range(tones):
+        x += amp * np.sin(2 * np.pi * f[k] * t + ph[k])
+    x += rng.normal(0.0, noise_lsb, n)
+    return np.clip(np.rint(x), -2048, 2047).astype(np.int16)

@@ -1,0 +1,42 @@
+#!/usr/bin/env python3
+"""DEVELOPMENT AID: runs the CUDA sources' host-emulation build (tools/emu) against the golden model."""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import ua3reo_loader
+from oracle import pyoracle
+
+pkg = ua3reo_loader.load()
+EMU = os.path.join(ROOT, "tools", "emu", "_build", "libua3reo_emu.so")
+
+def run(n_ch, pushes, max_block=1 << 14, seed=1):
+    rng = np.random.default_rng(seed)
+    fcw = rng.integers(1, 1 << 21, n_ch).astype(np.uint32)
+    total = sum(pushes)
+    adc = pyoracle.synth_adc(total, seed=seed)
+    adc[:5] = -2048   # exercise the (-2048)*(-2048) mixer wrap
+    rx = pkg.Receiver(n_ch, max_block, _lib_path=EMU)
+    rx.set_fcw(fcw)
+    got = []
+    off = 0
+    for n in pushes:
+        nf = rx.push(adc[off:off + n]); off += n
+        got.append(rx.read_frames())
+    got = np.concatenate(got, axis=1)
+    ref = pyoracle.golden_frames(adc, fcw)[:, :got.shape[1]]
+    ok = np.array_equal(got, ref)
+    print("n_ch=%d pushes=%s frames=%d match=%s" % (n_ch, pushes, got.shape[1], ok))
+    if not ok:
+        bad = np.argwhere(got != ref)
+        print(" first mismatches:", bad[:8].tolist())
+        print(" got", got[bad[0][0], bad[0][1]], "ref", ref[bad[0][0], bad[0][1]])
+    return ok
+
+if __name__ == "__main__":
+    t = time.time()
+    ok = run(3, [4096, 2048, 8192])
+    ok &= run(33, [16384], seed=2)
+    ok &= run(2, [1000, 24, 3000, 5192, 1024 * 3 + 5], seed=3)
+    print("ALL OK" if ok else "FAILED", "%.1fs" % (time.time() - t))
+    sys.exit(0 if ok else 1)

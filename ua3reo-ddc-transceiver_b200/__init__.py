@@ -1,0 +1,190 @@
+"""ua3reo-ddc-transceiver_b200 - host-side Python binding of libua3reo_b200.so.
+
+This is plumbing (ctypes over the C ABI in include/ua3reo_b200.h) used by tests/ and bench.py; the
+product is the shared library.  There is NO CPU fallback: if the CUDA library has not been built
+(`__graft_entry__.build()` / `ua3reo-ddc-transceiver_b200/build.sh`) importing this module raises.
+
+The directory name carries a hyphen (the repository layout asks for it), so import it through
+`ua3reo_loader.load()` at the repo root, which registers it as `ua3reo_ddc_transceiver_b200`.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libua3reo_b200.so")
+
+ADC_PER_FRAME = 1024
+FRAME_BYTES = 8
+AUDIO_BLOCK = 192
+FFT_SIZE = 512
+FFT_BINS = 256
+ADC_CLOCK_HZ = 49152000
+DEFAULT_FCW = 620407  # stm32_interface.v:56
+
+
+class UA3Error(RuntimeError):
+    pass
+
+
+def _bind(lib):
+    c = ctypes
+    vp, u32, sz = c.c_void_p, c.c_uint32, c.c_size_t
+    sigs = {
+        "ua3reo_version": (c.c_char_p, []),
+        "ua3reo_last_error": (c.c_char_p, []),
+        "ua3reo_create": (c.c_int, [c.c_int, u32, u32, c.POINTER(vp)]),
+        "ua3reo_destroy": (c.c_int, [vp]),
+        "ua3reo_reset": (c.c_int, [vp]),
+        "ua3reo_n_channels": (u32, [vp]),
+        "ua3reo_max_block_samples": (u32, [vp]),
+        "ua3reo_set_fcw": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_get_fcw": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_phrase_from_frequency": (u32, [u32, c.POINTER(c.c_int)]),
+        "ua3reo_set_frequency": (c.c_int, [vp, u32, u32]),
+        "ua3reo_ddc_push": (c.c_int, [vp, vp, sz, c.POINTER(sz)]),
+        "ua3reo_ddc_push_device": (c.c_int, [vp, vp, sz, c.POINTER(sz)]),
+        "ua3reo_ddc_read_frames": (c.c_int, [vp, vp, sz]),
+        "ua3reo_ddc_frames_device": (c.c_int, [vp, c.POINTER(vp), c.POINTER(sz), c.POINTER(sz)]),
+        "ua3reo_sync": (c.c_int, [vp]),
+        "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
+        "ua3reo_launch_count": (c.c_uint64, [vp]),
+        "ua3reo_measure_int32_peak": (c.c_int, [c.c_int, c.POINTER(c.c_double)]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+def load_library(path=None):
+    """Loads the CUDA library.  Raises UA3Error when it is missing: no fallback exists."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise UA3Error(
+            "%s not found: build it with ua3reo-ddc-transceiver_b200/build.sh (nvcc, sm_100a). "
+            "There is no CPU fallback." % path)
+    return _bind(ctypes.CDLL(path))
+
+
+def declared_symbols(header_path):
+    """Names of the functions include/*.h declares (used by the symbol-export test)."""
+    import re
+    txt = open(header_path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ua3reo_\w+|processRxAudio|processTxAudio|initAudioProcessor|FFT_Init|FFT_doFFT|"
+                                 r"FPGA_fpgadata_iqclock|getPhraseFromFrequency)\s*\(", txt)))
+
+
+def phrase_from_frequency(freq_hz, lib=None):
+    lib = lib or load_library()
+    swap = ctypes.c_int(0)
+    w = lib.ua3reo_phrase_from_frequency(int(freq_hz), ctypes.byref(swap))
+    return int(w), bool(swap.value)
+
+
+class Receiver:
+    """Batched receiver bank: n_channels DDCs over one shared ADC stream (one context = one GPU)."""
+
+    def __init__(self, n_channels, max_block_samples=1 << 20, device=0, _lib_path=None):
+        self.lib = load_library(_lib_path)
+        h = ctypes.c_void_p()
+        self._h = None
+        self._chk(self.lib.ua3reo_create(int(device), int(n_channels), int(max_block_samples), ctypes.byref(h)))
+        self._h = h
+        self.n_channels = int(n_channels)
+        self.max_block_samples = int(self.lib.ua3reo_max_block_samples(h))
+        self.device = int(device)
+        self.last_frames = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise UA3Error("ua3reo error %d: %s" % (rc, self.lib.ua3reo_last_error().decode()))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.ua3reo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        self._chk(self.lib.ua3reo_reset(self._h))
+
+    def set_fcw(self, fcw, first=0):
+        a = np.ascontiguousarray(fcw, dtype=np.uint32)
+        self._chk(self.lib.ua3reo_set_fcw(self._h, int(first), a.size, a.ctypes.data))
+
+    def get_fcw(self):
+        a = np.zeros(self.n_channels, np.uint32)
+        self._chk(self.lib.ua3reo_get_fcw(self._h, 0, a.size, a.ctypes.data))
+        return a
+
+    def set_frequency(self, channel, freq_hz):
+        self._chk(self.lib.ua3reo_set_frequency(self._h, int(channel), int(freq_hz)))
+
+    def push(self, adc):
+        """adc: 1-D int16 numpy array (host) or a CUDA torch tensor of dtype int16 on this device."""
+        n = ctypes.c_size_t(0)
+        if isinstance(adc, np.ndarray):
+            a = np.ascontiguousarray(adc, dtype=np.int16)
+            self._keep = a
+            self._chk(self.lib.ua3reo_ddc_push(self._h, a.ctypes.data, a.size, ctypes.byref(n)))
+        else:  # torch tensor
+            if adc.is_cuda:
+                assert adc.dtype.itemsize == 2 and adc.is_contiguous()
+                self._chk(self.lib.ua3reo_ddc_push_device(self._h, adc.data_ptr(), adc.numel(), ctypes.byref(n)))
+            else:
+                assert adc.dtype.itemsize == 2 and adc.is_contiguous()
+                self._keep = adc
+                self._chk(self.lib.ua3reo_ddc_push(self._h, adc.data_ptr(), adc.numel(), ctypes.byref(n)))
+        self.last_frames = int(n.value)
+        return self.last_frames
+
+    def read_frames(self, out=None):
+        """Returns uint8 [n_channels, frames_of_last_push, 8] in stm32_interface byte order."""
+        nf = self.last_frames
+        if out is None:
+            out = np.empty((self.n_channels, nf, FRAME_BYTES), np.uint8)
+        ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
+        self._chk(self.lib.ua3reo_ddc_read_frames(self._h, ptr, nf))
+        return out
+
+    def frames_device(self):
+        base, nf, stride = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_size_t()
+        self._chk(self.lib.ua3reo_ddc_frames_device(self._h, ctypes.byref(base), ctypes.byref(nf), ctypes.byref(stride)))
+        return base.value, int(nf.value), int(stride.value)
+
+    def sync(self):
+        self._chk(self.lib.ua3reo_sync(self._h))
+
+    def stream(self):
+        s = ctypes.c_void_p()
+        self._chk(self.lib.ua3reo_stream(self._h, ctypes.byref(s)))
+        return s.value or 0
+
+    def launch_count(self):
+        return int(self.lib.ua3reo_launch_count(self._h))
+
+
+def frames_to_iq(frames):
+    """uint8 [..., 8] frames -> dict of int16 arrays, as FPGA_fpgadata_getiq rebuilds them (fpga.c:286-385)."""
+    f = np.asarray(frames, dtype=np.uint8)
+    w = (f[..., 0::2].astype(np.uint16) << 8) | f[..., 1::2].astype(np.uint16)
+    w = w.astype(np.int16)
+    return {"spec_q": w[..., 0], "spec_i": w[..., 1], "voice_q": w[..., 2], "voice_i": w[..., 3]}
+
+
+def measure_int32_peak(device=0, lib=None):
+    lib = lib or load_library()
+    v = ctypes.c_double(0.0)
+    rc = lib.ua3reo_measure_int32_peak(int(device), ctypes.byref(v))
+    if rc != 0:
+        raise UA3Error("ua3reo error %d: %s" % (rc, lib.ua3reo_last_error().decode()))
+    return float(v.value)

@@ -1,0 +1,262 @@
+// api.cu - C ABI of libua3reo_b200.so (declared in include/ua3reo_b200.h).
+#include "../../include/ua3reo_b200.h"
+#include "ddc_launch.h"
+#include "ua3_common.cuh"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace ua3;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
+    g_err = what;
+    if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
+    return code;
+}
+#define UA3_CUDA(call)                                                  \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return fail(UA3_E_CUDA, #call, e__);    \
+    } while (0)
+
+struct ua3reo_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t n_ch = 0, n_ch_pad = 0, max_block = 0;
+    DdcBuffers b;
+    int16_t* adc_stage = nullptr;   // device [max_block + 1024]: carry + new samples
+    uint32_t carry = 0;
+    size_t last_frames = 0;
+    bool pushed = false;
+    std::vector<uint32_t> h_fcw;
+    std::vector<uint8_t> h_iq_swap;
+    uint64_t launches = 0;
+    std::vector<void*> allocs;
+};
+
+template <class T>
+static cudaError_t dev_alloc(ua3reo_ctx* c, T** p, size_t n) {
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    c->allocs.push_back(*p);
+    return cudaMemsetAsync(*p, 0, n * sizeof(T), c->stream);
+}
+
+extern "C" {
+
+const char* ua3reo_version(void) { return "ua3reo_b200 0.1 sm_100a"; }
+const char* ua3reo_last_error(void) { return g_err.c_str(); }
+
+uint32_t ua3reo_phrase_from_frequency(uint32_t freq, int* iq_swap) {
+    // functions.c:206-226, in double as the firmware does
+    const uint32_t clk = 49152000u;
+    bool inverted = false;
+    uint32_t f = freq;
+    if (f > clk / 2) {
+        while (f > clk / 2) { f -= clk / 2; inverted = !inverted; }
+        if (inverted) f = clk / 2 - f;
+    }
+    if (iq_swap) *iq_swap = inverted ? 1 : 0;
+    return (uint32_t)std::round(((double)f / (double)clk) * 4194304.0);
+}
+
+static int ctx_free(ua3reo_ctx* c) {
+    if (!c) return UA3_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return UA3_OK;
+}
+
+int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, ua3reo_ctx** out) {
+    if (!out || n_channels == 0) return fail(UA3_E_INVAL, "ua3reo_create: bad arguments");
+    *out = nullptr;
+    if (max_block_samples == 0) max_block_samples = 1u << 20;
+    if (max_block_samples % UA3_ADC_PER_FRAME) return fail(UA3_E_INVAL, "max_block_samples must be a multiple of 1024");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return fail(UA3_E_NODEV, "no CUDA device: libua3reo_b200 has no CPU fallback");
+    if (device < 0 || device >= n_dev) return fail(UA3_E_INVAL, "device index out of range");
+    cudaDeviceProp prop;
+    UA3_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(UA3_E_NODEV, "device is not sm_100: kernels are built for sm_100a only");
+    UA3_CUDA(cudaSetDevice(device));
+
+    ua3reo_ctx* c = new (std::nothrow) ua3reo_ctx;
+    if (!c) return fail(UA3_E_INVAL, "out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->n_ch = n_channels;
+    c->n_ch_pad = (n_channels + 31u) & ~31u;
+    c->max_block = max_block_samples;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return fail(UA3_E_CUDA, "cudaStreamCreate", e); }
+
+    DdcBuffers& b = c->b;
+    b.n_ch = c->n_ch; b.n_ch_pad = c->n_ch_pad;
+    b.max_chunks = max_block_samples / kCicR;
+    b.max_frames = max_block_samples / kFrameAdc;
+    b.l_ch_stride = (kLHalo + b.max_chunks) * kLRec;
+    b.u_rail_stride = (kUHalo + b.max_chunks + 7u) & ~7u;
+    b.yi_stride = (kYIHalo + b.max_frames + 7u) & ~7u;
+    b.yq_stride = (kYQHalo + b.max_frames + 7u) & ~7u;
+    b.frame_ch_stride = b.max_frames;
+#define UA3_TRY(call) do { e = (call); if (e != cudaSuccess) { ctx_free(c); return fail(UA3_E_CUDA, #call, e); } } while (0)
+    UA3_TRY(dev_alloc(c, &b.nco_tab, 2048));
+    UA3_TRY(dev_alloc(c, &b.fcw, c->n_ch_pad));
+    UA3_TRY(dev_alloc(c, &b.phase, c->n_ch_pad));
+    UA3_TRY(dev_alloc(c, &b.L, (size_t)c->n_ch_pad * b.l_ch_stride));
+    UA3_TRY(dev_alloc(c, &b.U, (size_t)c->n_ch_pad * 2 * b.u_rail_stride));
+    UA3_TRY(dev_alloc(c, &b.YI, (size_t)c->n_ch_pad * b.yi_stride));
+    UA3_TRY(dev_alloc(c, &b.YQ, (size_t)c->n_ch_pad * b.yq_stride));
+    UA3_TRY(dev_alloc(c, &b.frames, (size_t)c->n_ch * b.frame_ch_stride));
+    UA3_TRY(dev_alloc(c, &c->adc_stage, (size_t)max_block_samples + UA3_ADC_PER_FRAME));
+    uint32_t tab[2048];
+    build_nco_table(tab);
+    UA3_TRY(cudaMemcpyAsync(b.nco_tab, tab, sizeof tab, cudaMemcpyHostToDevice, c->stream));
+    UA3_TRY(ddc_upload_constants());
+    c->h_fcw.assign(c->n_ch_pad, 0u);
+    for (uint32_t i = 0; i < c->n_ch; ++i) c->h_fcw[i] = 620407u;   // stm32_interface.v:56 power-on freq_out
+    c->h_iq_swap.assign(c->n_ch, 0);
+    UA3_TRY(cudaMemcpyAsync(b.fcw, c->h_fcw.data(), sizeof(uint32_t) * c->n_ch_pad, cudaMemcpyHostToDevice, c->stream));
+    UA3_TRY(cudaStreamSynchronize(c->stream));
+#undef UA3_TRY
+    *out = c;
+    return UA3_OK;
+}
+
+int ua3reo_destroy(ua3reo_ctx* ctx) { return ctx_free(ctx); }
+
+int ua3reo_reset(ua3reo_ctx* c) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const DdcBuffers& b = c->b;
+    UA3_CUDA(cudaMemsetAsync(b.phase, 0, sizeof(uint32_t) * c->n_ch_pad, c->stream));
+    UA3_CUDA(cudaMemsetAsync(b.L, 0, sizeof(uint64_t) * (size_t)c->n_ch_pad * b.l_ch_stride, c->stream));
+    UA3_CUDA(cudaMemsetAsync(b.U, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * 2 * b.u_rail_stride, c->stream));
+    UA3_CUDA(cudaMemsetAsync(b.YI, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * b.yi_stride, c->stream));
+    UA3_CUDA(cudaMemsetAsync(b.YQ, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * b.yq_stride, c->stream));
+    c->carry = 0; c->last_frames = 0; c->pushed = false;
+    return UA3_OK;
+}
+
+uint32_t ua3reo_n_channels(const ua3reo_ctx* c) { return c ? c->n_ch : 0; }
+uint32_t ua3reo_max_block_samples(const ua3reo_ctx* c) { return c ? c->max_block : 0; }
+uint64_t ua3reo_launch_count(const ua3reo_ctx* c) { return c ? c->launches : 0; }
+
+int ua3reo_set_fcw(ua3reo_ctx* c, uint32_t first, uint32_t n, const uint32_t* fcw22) {
+    if (!c || !fcw22 || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_set_fcw: range");
+    UA3_CUDA(cudaSetDevice(c->device));
+    for (uint32_t i = 0; i < n; ++i) c->h_fcw[first + i] = fcw22[i] & 0x3FFFFFu;   // freq_out is 22 bits wide
+    UA3_CUDA(cudaMemcpyAsync(c->b.fcw + first, c->h_fcw.data() + first, sizeof(uint32_t) * n, cudaMemcpyHostToDevice,
+                             c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));   // h_fcw may be rewritten by the next call
+    return UA3_OK;
+}
+
+int ua3reo_get_fcw(ua3reo_ctx* c, uint32_t first, uint32_t n, uint32_t* fcw22) {
+    if (!c || !fcw22 || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_get_fcw: range");
+    std::memcpy(fcw22, c->h_fcw.data() + first, sizeof(uint32_t) * n);
+    return UA3_OK;
+}
+
+int ua3reo_set_frequency(ua3reo_ctx* c, uint32_t channel, uint32_t freq_hz) {
+    if (!c || channel >= c->n_ch) return fail(UA3_E_INVAL, "ua3reo_set_frequency: channel");
+    int swap = 0;
+    const uint32_t w = ua3reo_phrase_from_frequency(freq_hz, &swap);
+    c->h_iq_swap[channel] = (uint8_t)swap;
+    return ua3reo_set_fcw(c, channel, 1, &w);
+}
+
+static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* frames_out, cudaMemcpyKind kind) {
+    if (!c || (!src && n)) return fail(UA3_E_INVAL, "ua3reo_ddc_push: null argument");
+    if ((size_t)c->carry + n > (size_t)c->max_block + UA3_ADC_PER_FRAME - 1 ||
+        (((size_t)c->carry + n) / UA3_ADC_PER_FRAME) * UA3_ADC_PER_FRAME > c->max_block)
+        return fail(UA3_E_TOOBIG, "ua3reo_ddc_push: block exceeds max_block_samples");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t total = c->carry + n;
+    const uint32_t n_proc = (uint32_t)((total / UA3_ADC_PER_FRAME) * UA3_ADC_PER_FRAME);
+    const int16_t* proc_src = c->adc_stage;
+    const bool in_place = (kind == cudaMemcpyDeviceToDevice) && c->carry == 0 && n_proc == n &&
+                          ((uintptr_t)src % 16u) == 0;
+    if (in_place) {
+        proc_src = src;
+    } else if (n) {
+        UA3_CUDA(cudaMemcpyAsync(c->adc_stage + c->carry, src, n * sizeof(int16_t), kind, c->stream));
+    }
+    int launches = 0;
+    if (n_proc) UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, c->sm_count, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    const uint32_t left = (uint32_t)(total - n_proc);
+    if (!in_place && n_proc && left)
+        UA3_CUDA(cudaMemcpyAsync(c->adc_stage, c->adc_stage + n_proc, left * sizeof(int16_t), cudaMemcpyDeviceToDevice,
+                                 c->stream));
+    c->carry = left;
+    c->last_frames = n_proc / UA3_ADC_PER_FRAME;
+    c->pushed = true;
+    if (frames_out) *frames_out = c->last_frames;
+    return UA3_OK;
+}
+
+int ua3reo_ddc_push(ua3reo_ctx* c, const int16_t* adc_host, size_t n, size_t* frames_out) {
+    return push_common(c, adc_host, n, frames_out, cudaMemcpyHostToDevice);
+}
+
+int ua3reo_ddc_push_device(ua3reo_ctx* c, const int16_t* adc_dev, size_t n, size_t* frames_out) {
+    return push_common(c, adc_dev, n, frames_out, cudaMemcpyDeviceToDevice);
+}
+
+int ua3reo_ddc_read_frames(ua3reo_ctx* c, uint8_t* dst, size_t n_frames) {
+    if (!c || (!dst && n_frames)) return fail(UA3_E_INVAL, "ua3reo_ddc_read_frames: null argument");
+    if (!c->pushed) return fail(UA3_E_STATE, "ua3reo_ddc_read_frames: no push yet");
+    if (n_frames != c->last_frames) return fail(UA3_E_INVAL, "ua3reo_ddc_read_frames: n_frames != frames of last push");
+    UA3_CUDA(cudaSetDevice(c->device));
+    if (n_frames)
+        UA3_CUDA(cudaMemcpy2DAsync(dst, n_frames * UA3_FRAME_BYTES, c->b.frames,
+                                   (size_t)c->b.frame_ch_stride * UA3_FRAME_BYTES, n_frames * UA3_FRAME_BYTES, c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_ddc_frames_device(ua3reo_ctx* c, const uint8_t** base, size_t* n_frames, size_t* stride) {
+    if (!c || !base) return fail(UA3_E_INVAL, "ua3reo_ddc_frames_device: null argument");
+    *base = reinterpret_cast<const uint8_t*>(c->b.frames);
+    if (n_frames) *n_frames = c->last_frames;
+    if (stride) *stride = (size_t)c->b.frame_ch_stride * UA3_FRAME_BYTES;
+    return UA3_OK;
+}
+
+int ua3reo_sync(ua3reo_ctx* c) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    UA3_CUDA(cudaSetDevice(c->device));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_stream(ua3reo_ctx* c, void** stream) {
+    if (!c || !stream) return fail(UA3_E_INVAL, "null argument");
+    *stream = (void*)c->stream;
+    return UA3_OK;
+}
+
+int ua3reo_measure_int32_peak(int device, double* ops_per_s) {
+    if (!ops_per_s) return fail(UA3_E_INVAL, "null argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(UA3_E_NODEV, "no CUDA device");
+    if (device < 0 || device >= n_dev) return fail(UA3_E_INVAL, "device index out of range");
+    UA3_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    UA3_CUDA(cudaGetDeviceProperties(&prop, device));
+    UA3_CUDA(measure_int32_peak(prop.multiProcessorCount, nullptr, ops_per_s));
+    return UA3_OK;
+}
+
+}  // extern "C"

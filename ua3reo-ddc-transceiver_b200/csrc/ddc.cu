@@ -1,0 +1,215 @@
+// ddc.cu - sm_100a kernels for the batched UA3REO receive DDC (one shared ADC stream, many channels).
+//
+// Launch sequence per ADC block of n = 512*M samples (M even), all on one stream:
+//   ddc_front_kernel   : ADC tile -> shared memory once per CTA, 32 channels x 8 chunks per tile,
+//                        one warp per chunk, lane = channel; writes chunk partial states L
+//   ddc_cic_kernel     : L (5-chunk window) -> 96 kHz CIC outputs U (int16)
+//   ddc_comp_kernel    : U (65-tap window) -> 48 kHz compensator outputs YI/YQ (int16)
+//   ddc_hilb_kernel    : YI (256-tap window), YQ (130 delay) -> 8-byte frames
+//   ddc_rotate_kernel  : move the tails of L/U/YI/YQ into their halos, advance the NCO phases
+#include "ddc_launch.h"
+#include "ddc_front.cuh"
+#include "ddc_back.cuh"
+#include "tables_ddc.inc"
+
+namespace ua3 {
+
+__constant__ int16_t c_comp_h[kCompTaps];
+__constant__ int16_t c_hilb_c[kHilbTaps];
+__constant__ uint64_t c_cic_g[25];
+
+// ------------------------------------------------------------------------------------------------
+// front: grid-stride over tiles (channel tile of 32) x (time tile of kFrontWarps chunks)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFrontThreads, 3)
+ddc_front_kernel(const int16_t* __restrict__ adc, uint32_t n_chunks, const uint32_t* __restrict__ nco_tab,
+                 const uint32_t* __restrict__ fcw, const uint32_t* __restrict__ phase, uint32_t n_ch_pad,
+                 uint64_t* __restrict__ L, uint32_t l_ch_stride /* u64 per channel */) {
+    __shared__ uint32_t s_tab[2048];
+    __shared__ I4 s_adc[kFrontWarps * kCicR / 4];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 2048; i += kFrontThreads) s_tab[i] = nco_tab[i];
+
+    const uint32_t n_ttiles = (n_chunks + kFrontWarps - 1) / kFrontWarps;
+    const uint32_t n_ctiles = n_ch_pad >> 5;
+    const uint32_t n_tiles = n_ttiles * n_ctiles;
+
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // channel tile varies fastest so that concurrently running CTAs share the same ADC tile in L2
+        const uint32_t ct = tile % n_ctiles, tt = tile / n_ctiles;
+        const uint32_t chunk0 = tt * kFrontWarps;
+        __syncthreads();   // previous tile fully consumed (also orders the table fill on first pass)
+        // stage: 8 int16 per thread per step (16-byte coalesced loads), pre-shift by 9
+        {
+            const uint32_t n_valid = min((uint32_t)kFrontWarps, n_chunks - chunk0) * kCicR;  // samples
+            const uint4* src = reinterpret_cast<const uint4*>(adc + (size_t)chunk0 * kCicR);
+            for (uint32_t v = tid; v < n_valid / 8; v += kFrontThreads) {
+                const uint4 q = __ldg(src + v);
+                const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+                I4 lo, hi;
+                int32_t e[8];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    e[2 * k] = (int32_t)(int16_t)(ws[k] & 0xFFFFu) << 9;
+                    e[2 * k + 1] = ((int32_t)ws[k] >> 16) << 9;
+                }
+                lo.x = e[0]; lo.y = e[1]; lo.z = e[2]; lo.w = e[3];
+                hi.x = e[4]; hi.y = e[5]; hi.z = e[6]; hi.w = e[7];
+                s_adc[2 * v] = lo;
+                s_adc[2 * v + 1] = hi;
+            }
+        }
+        __syncthreads();
+        const uint32_t chunk = chunk0 + warp;
+        if (chunk < n_chunks) {
+            const uint32_t ch = (ct << 5) + lane;
+            const uint32_t F = fcw[ch] << 10;
+            const uint32_t P0 = (phase[ch] << 10) + F * (chunk * (uint32_t)kCicR);
+            uint64_t out[10];
+            front_chunk(s_tab, s_adc + warp * (kCicR / 4), P0, F, out);
+            uint64_t* dst = L + (size_t)ch * l_ch_stride + (size_t)(kLHalo + chunk) * kLRec;
+            ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) d2[k] = make_ulonglong2(out[2 * k], out[2 * k + 1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cic: one thread per (channel, chunk, rail)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ddc_cic_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_t n_chunks, uint32_t n_ch,
+               int16_t* __restrict__ U, uint32_t u_rail_stride /* int16 per (channel, rail) */) {
+    const uint32_t m = blockIdx.y * blockDim.x + threadIdx.x;
+    const uint32_t rail = blockIdx.x & 1, ch = blockIdx.x >> 1;
+    if (m >= n_chunks || ch >= n_ch) return;
+    const uint64_t* rec = L + (size_t)ch * l_ch_stride + (size_t)(kLHalo + m) * kLRec + rail * 5;
+    U[((size_t)ch * 2 + rail) * u_rail_stride + kUHalo + m] = cic_combine(rec, c_cic_g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// comp: CTA = (channel, rail, tile of 256 frames); window staged in shared memory
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ddc_comp_kernel(const int16_t* __restrict__ U, uint32_t u_rail_stride, uint32_t n_frames,
+                int16_t* __restrict__ YI, uint32_t yi_stride, int16_t* __restrict__ YQ, uint32_t yq_stride) {
+    __shared__ int16_t s_u[2 * 256 + kUHalo + 2];
+    const uint32_t rail = blockIdx.x & 1, ch = blockIdx.x >> 1;
+    const uint32_t k0 = blockIdx.y * 256;
+    const uint32_t nk = min(256u, n_frames - k0);
+    const int16_t* src = U + ((size_t)ch * 2 + rail) * u_rail_stride + 2 * k0;   // window start of frame k0
+    for (uint32_t i = threadIdx.x; i < 2 * nk + kUHalo; i += 256) s_u[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x < nk) {
+        const int16_t y = comp_fir(s_u, c_comp_h, (int)threadIdx.x);
+        if (rail == 0) YI[(size_t)ch * yi_stride + kYIHalo + k0 + threadIdx.x] = y;
+        else           YQ[(size_t)ch * yq_stride + kYQHalo + k0 + threadIdx.x] = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// hilb + delay + frame pack: CTA = (channel, tile of 256 frames)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_t* __restrict__ YQ, uint32_t yq_stride,
+                uint32_t n_frames, uint64_t* __restrict__ frames, uint32_t frame_ch_stride) {
+    __shared__ int16_t s_y[256 + kYIHalo + 1];
+    const uint32_t ch = blockIdx.x;
+    const uint32_t k0 = blockIdx.y * 256;
+    const uint32_t nk = min(256u, n_frames - k0);
+    const int16_t* src = YI + (size_t)ch * yi_stride + k0;
+    for (uint32_t i = threadIdx.x; i < nk + kYIHalo; i += 256) s_y[i] = src[i];
+    __syncthreads();
+    if (threadIdx.x < nk) {
+        const uint32_t k = k0 + threadIdx.x;
+        const int16_t vi = hilb_fir(s_y, c_hilb_c, (int)threadIdx.x);
+        const int16_t yi = s_y[kYIHalo + threadIdx.x];
+        const int16_t* q = YQ + (size_t)ch * yq_stride + k;   // q[kYQHalo] = yQ[k], q[0] = yQ[k-130]
+        frames[(size_t)ch * frame_ch_stride + k] = frame_pack(q[kYQHalo], yi, q[0], vi);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rotate: CTA per channel; tails -> halos (read everything, barrier, write), NCO phase advance
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ddc_rotate_kernel(uint64_t* __restrict__ L, uint32_t l_ch_stride, int16_t* __restrict__ U, uint32_t u_rail_stride,
+                  int16_t* __restrict__ YI, uint32_t yi_stride, int16_t* __restrict__ YQ, uint32_t yq_stride,
+                  uint32_t n_chunks, uint32_t n_frames, uint32_t* __restrict__ phase, const uint32_t* __restrict__ fcw,
+                  uint32_t n_ch) {
+    const uint32_t ch = blockIdx.x, t = threadIdx.x;
+    uint64_t* l = L + (size_t)ch * l_ch_stride;
+    int16_t* u0 = U + ((size_t)ch * 2) * u_rail_stride;
+    int16_t* u1 = u0 + u_rail_stride;
+    int16_t* yi = YI + (size_t)ch * yi_stride;
+    int16_t* yq = YQ + (size_t)ch * yq_stride;
+    uint64_t vl = 0; int16_t vu0 = 0, vu1 = 0, vyi = 0, vyq = 0;
+    if (t < kLHalo * kLRec) vl = l[(size_t)n_chunks * kLRec + t];
+    if (t < kUHalo) { vu0 = u0[n_chunks + t]; vu1 = u1[n_chunks + t]; }
+    if (t < kYIHalo) vyi = yi[n_frames + t];
+    if (t < kYQHalo) vyq = yq[n_frames + t];
+    __syncthreads();
+    if (t < kLHalo * kLRec) l[t] = vl;
+    if (t < kUHalo) { u0[t] = vu0; u1[t] = vu1; }
+    if (t < kYIHalo) yi[t] = vyi;
+    if (t < kYQHalo) yq[t] = vyq;
+    if (t == 0 && ch < n_ch) phase[ch] = (phase[ch] + fcw[ch] * (n_chunks * (uint32_t)kCicR)) & 0x3FFFFFu;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static uint64_t binom_u64(uint64_t n, int k) {
+    if (k < 0) return 0;
+    unsigned __int128 r = 1;
+    for (int i = 1; i <= k; ++i) r = r * (n - (uint64_t)(k - i)) / (unsigned)i;   // exact at every step
+    return (uint64_t)r;
+}
+
+void build_cic_weights(uint64_t G[25]) {
+    static const int64_t c5[6] = {1, -5, 10, -10, 5, -1};
+    for (int p = 0; p < 5; ++p)
+        for (int k = 1; k <= 5; ++k) {
+            uint64_t g = 0;
+            for (int i = 0; i <= p; ++i) g += (uint64_t)c5[i] * binom_u64((uint64_t)kCicR * (uint64_t)(p - i), 5 - k);
+            G[p * 5 + (k - 1)] = g;
+        }
+}
+
+void build_nco_table(uint32_t tab[2048]) {
+    for (int k = 0; k < 2048; ++k) tab[k] = nco_pack(UA3_NCO_SIN_C[k], UA3_NCO_COS_C[k]);
+}
+
+cudaError_t ddc_upload_constants() {
+    uint64_t G[25];
+    build_cic_weights(G);
+    cudaError_t e = cudaMemcpyToSymbol(c_cic_g, G, sizeof G);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_comp_h, UA3_RXCOMP_H, sizeof(int16_t) * kCompTaps);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_hilb_c, UA3_RXHILB_C, sizeof(int16_t) * kHilbTaps);
+}
+
+cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, int sm_count,
+                             cudaStream_t st, int* launches) {
+    const uint32_t n_chunks = n_samples / kCicR, n_frames = n_samples / kFrameAdc;
+    if (n_chunks == 0) return cudaSuccess;
+    const uint32_t n_tiles = ((n_chunks + kFrontWarps - 1) / kFrontWarps) * (b.n_ch_pad >> 5);
+    const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count * 3);
+    UA3_LAUNCH(ddc_front_kernel, grid, kFrontThreads, 0, st, adc_dev, n_chunks, b.nco_tab, b.fcw, b.phase, b.n_ch_pad,
+               b.L, b.l_ch_stride);
+    UA3_LAUNCH(ddc_cic_kernel, dim3(b.n_ch * 2, (n_chunks + 255) / 256), 256, 0, st, b.L, b.l_ch_stride, n_chunks,
+               b.n_ch, b.U, b.u_rail_stride);
+    UA3_LAUNCH(ddc_comp_kernel, dim3(b.n_ch * 2, (n_frames + 255) / 256), 256, 0, st, b.U, b.u_rail_stride, n_frames,
+               b.YI, b.yi_stride, b.YQ, b.yq_stride);
+    UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + 255) / 256), 256, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
+               n_frames, b.frames, b.frame_ch_stride);
+    UA3_LAUNCH(ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.U, b.u_rail_stride, b.YI, b.yi_stride,
+               b.YQ, b.yq_stride, n_chunks, n_frames, b.phase, b.fcw, b.n_ch_pad);
+    if (launches) *launches += 5;
+    return cudaGetLastError();
+}
+
+}  // namespace ua3

@@ -1,0 +1,87 @@
+// ddc_front.cuh - NCO + quadrature mixer + CIC integrators for one (channel, 512-sample chunk).
+//
+// Replaces, per ADC clock: nco_nco_ii_0.v:299-420 (NCO), nco_shift.v:9, mixer.v:64-71,
+// rx_mixer_shift.v:9 and the five integrators of rx_cic.vhd:178-289.
+//
+// B200 formulation (not the HDL's): the integrator cascade is linear over Z/2^64, so the state
+// after a chunk is  S' = A512 * S + L  where L is the state reached from ZERO over the chunk's 512
+// samples.  Every (channel, chunk) pair can therefore compute its L independently - no sequential
+// carry along time - and ddc_back.cuh combines five consecutive L records with constant weights
+// into the comb output.  Inside a chunk the cascade runs in 32-bit registers over 16-sample
+// sub-blocks (|x| <= 2^14, so stage 5 stays below 2^14 * C(16,5) < 2^27) and is folded into the
+// 64-bit chunk state with the binomial matrix A16 once per sub-block.
+#pragma once
+#include "ua3_common.cuh"
+
+namespace ua3 {
+
+// NCO fine-sine ROM in closed form: UA3_NCO_SIN_F[j] == (j * 6433 + 2^18) >> 19 for all j < 2048
+// (checked exhaustively in tests/test_tables.py); cos_f ROM is the constant 8191.
+constexpr int32_t kSinFMul = 6433;
+constexpr int32_t kCosF = 8191;
+
+// Packed coarse ROM word: sin_c in the high half, cos_c in the low half (both s14, sign-extended to 16).
+UA3_HD uint32_t nco_pack(int32_t sin_c, int32_t cos_c) {
+    return ((uint32_t)sin_c << 16) | ((uint32_t)cos_c & 0xFFFFu);
+}
+
+// One ADC sample for one channel: returns the two 15-bit CIC inputs.
+//   P   : 22-bit phase, left-aligned in 32 bits (P = phase << 10) so the accumulator wraps for free
+//   a9  : ADC sample pre-shifted left by 9, so that (a9 * nco12) >> 17 == s23(adc * nco12) >> 8
+UA3_HD void nco_mix(const uint32_t* __restrict__ tab, uint32_t P, int32_t a9, int32_t& xi, int32_t& xq) {
+    const uint32_t w = tab[P >> 21];                        // coarse address = phase[21:11]
+    const int32_t sc = (int32_t)w >> 16;
+    const int32_t cc = (int32_t)(int16_t)(w & 0xFFFFu);
+    const int32_t j = (int32_t)((P >> 10) & 0x7FFu);        // fine address = phase[10:0]
+    const int32_t sf = (j * kSinFMul + (1 << 18)) >> 19;
+    // 28-bit angle-sum products + round-half-up to 14 bits + nco_shift's [13:2]  ==  (x + 2^12) >> 15
+    const int32_t s12 = (sc * kCosF + sf * cc + 4096) >> 15;
+    const int32_t c12 = (cc * kCosF - sc * sf + 4096) >> 15;
+    xi = (int32_t)((uint32_t)a9 * (uint32_t)s12) >> 17;     // mixer I = ADC * sin (UA3REO.bdf netlist)
+    xq = (int32_t)((uint32_t)a9 * (uint32_t)c12) >> 17;     // mixer Q = ADC * cos
+}
+
+// Fold a 16-sample partial state (32-bit, from zero) into the 64-bit chunk state: S = A16*S + l.
+// A16[r][c] = C(16, r-c): the cascade's own response to its state over 16 clocks.
+UA3_HD void fold16(uint64_t S[5], int32_t l1, int32_t l2, int32_t l3, int32_t l4, int32_t l5) {
+    S[4] += 16u * S[3] + 120u * S[2] + 560u * S[1] + 1820u * S[0] + (uint64_t)(int64_t)l5;
+    S[3] += 16u * S[2] + 120u * S[1] + 560u * S[0] + (uint64_t)(int64_t)l4;
+    S[2] += 16u * S[1] + 120u * S[0] + (uint64_t)(int64_t)l3;
+    S[1] += 16u * S[0] + (uint64_t)(int64_t)l2;
+    S[0] += (uint64_t)(int64_t)l1;
+}
+
+// Whole chunk for one channel.  adc9: 512 pre-shifted samples (shared memory on the device, read
+// as 16-byte vectors, every lane of the warp reads the same address -> broadcast).
+// P0: left-aligned phase of the chunk's first sample; F: left-aligned tuning word.
+// out[0..4] = I-rail partial states, out[5..9] = Q-rail.
+UA3_HD void front_chunk(const uint32_t* __restrict__ tab, const I4* __restrict__ adc9, uint32_t P0, uint32_t F,
+                        uint64_t out[10]) {
+    uint64_t SI[5] = {0, 0, 0, 0, 0}, SQ[5] = {0, 0, 0, 0, 0};
+    uint32_t P = P0;
+#pragma unroll 1
+    for (int sb = 0; sb < kCicR / kSub; ++sb) {
+        int32_t i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
+        int32_t q1 = 0, q2 = 0, q3 = 0, q4 = 0, q5 = 0;
+#pragma unroll
+        for (int v = 0; v < kSub / 4; ++v) {
+            const I4 a = adc9[sb * (kSub / 4) + v];
+            const int32_t as[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                int32_t xi, xq;
+                nco_mix(tab, P, as[t], xi, xq);
+                P += F;
+                // registered cascade (rx_cic.vhd:197-289): every stage adds the PREVIOUS value of the stage before it
+                i5 += i4; i4 += i3; i3 += i2; i2 += i1; i1 += xi;
+                q5 += q4; q4 += q3; q3 += q2; q2 += q1; q1 += xq;
+            }
+        }
+        fold16(SI, i1, i2, i3, i4, i5);
+        fold16(SQ, q1, q2, q3, q4, q5);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { out[k] = SI[k]; out[5 + k] = SQ[k]; }
+}
+
+}  // namespace ua3

@@ -1,0 +1,33 @@
+// ddc_launch.h - host-visible launch interface of ddc.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ua3 {
+
+struct DdcBuffers {
+    uint32_t n_ch = 0, n_ch_pad = 0;
+    uint32_t max_chunks = 0, max_frames = 0;
+    uint32_t* nco_tab = nullptr;   // [2048] packed coarse ROM
+    uint32_t* fcw = nullptr;       // [n_ch_pad] 22-bit tuning words
+    uint32_t* phase = nullptr;     // [n_ch_pad] 22-bit phase at the start of the next block
+    uint64_t* L = nullptr;         // [n_ch_pad][kLHalo + max_chunks][2][5]
+    uint32_t l_ch_stride = 0;
+    int16_t* U = nullptr;          // [n_ch_pad][2][kUHalo + max_chunks]
+    uint32_t u_rail_stride = 0;
+    int16_t* YI = nullptr;         // [n_ch_pad][kYIHalo + max_frames]
+    uint32_t yi_stride = 0;
+    int16_t* YQ = nullptr;         // [n_ch_pad][kYQHalo + max_frames]
+    uint32_t yq_stride = 0;
+    uint64_t* frames = nullptr;    // [n_ch][max_frames] 8-byte frames
+    uint32_t frame_ch_stride = 0;  // frames per channel
+};
+
+void build_cic_weights(uint64_t G[25]);
+void build_nco_table(uint32_t tab[2048]);
+cudaError_t ddc_upload_constants();
+cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, int sm_count,
+                             cudaStream_t st, int* launches);
+cudaError_t measure_int32_peak(int sm_count, cudaStream_t st, double* ops_per_s);
+
+}  // namespace ua3

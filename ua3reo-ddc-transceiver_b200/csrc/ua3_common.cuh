@@ -1,0 +1,48 @@
+// ua3_common.cuh - shared definitions for the UA3REO B200 receive-path kernels.
+//
+// The per-thread bodies of the integer kernels are written as UA3_HD functions that take their
+// thread/block coordinates as arguments.  The __global__ wrappers in *.cu pass threadIdx/blockIdx;
+// tools/emu/ compiles the same bodies with g++ (UA3_HOST_EMU) as a development aid to debug index
+// logic without a GPU.  The emulation build is never loaded by the product.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#if defined(__CUDACC__) && !defined(UA3_HOST_EMU)
+#define UA3_HD __host__ __device__ __forceinline__
+#define UA3_D __device__ __forceinline__
+#else
+#define UA3_HD inline
+#define UA3_D inline
+#endif
+
+#if !defined(UA3_HOST_EMU)
+#define UA3_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+namespace ua3 {
+
+// ---- geometry of the FPGA chain (SURVEY.md 0 / rx_cic.vhd:27-29, rx_ciccomp.vhd:25-47) ----
+constexpr int kCicR = 512;          // ADC samples per CIC output (rx_cic.vhd:27)
+constexpr int kFrameAdc = 1024;     // ADC samples per 48 kHz frame (CIC 512 x compensator 2)
+constexpr int kCompTaps = 65;       // rx_ciccomp.vhd:47
+constexpr int kHilbTaps = 256;      // rx_hilb.vhd
+constexpr int kQDelay = 130;        // UA3REO.bdf:1693-1694
+constexpr int kFrameBytes = 8;      // stm32_interface.v:228-271
+
+// ---- layout of the per-chunk CIC partial-state records in HBM ----
+// One record per (channel, 512-sample chunk): 2 rails x 5 integrator partial states (u64).
+constexpr int kLHalo = 4;           // chunks of history needed by the 5-chunk comb window
+constexpr int kLRec = 10;           // u64 per record: [rail][stage]
+constexpr int kUHalo = 64;          // 96 kHz samples of history for the 65-tap compensator
+constexpr int kYIHalo = 255;        // 48 kHz samples of history for the 256-tap Hilbert FIR
+constexpr int kYQHalo = 130;        // data_delay depth
+
+// ---- front kernel tiling ----
+constexpr int kFrontWarps = 8;                     // warps per CTA, one 512-sample chunk each
+constexpr int kFrontThreads = kFrontWarps * 32;
+constexpr int kSub = 16;                           // 32-bit sub-block length (see ddc_front.cuh)
+
+struct alignas(16) I4 { int32_t x, y, z, w; };
+
+}  // namespace ua3
