@@ -1,0 +1,307 @@
+#!/usr/bin/env python3
+"""bench.py - DDC channel x ADC-samples / s on N B200 (BASELINE.json metric), one JSON line on rank 0.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # the CPU golden model on the host cores
+
+Workload (config.workload): BASELINE.json configs[2] at N=1 - 1024 independent DDC channels with random
+tuning words over one shared synthetic 12-bit ADC stream, blocks of 2^20 samples - and configs[3] at N=8
+(8192 channels sharded by channel, 1024 per GPU, the ADC block broadcast from rank 0 with NCCL): weak scaling.
+A step is one ADC block through the whole FPGA receive chain (NCO, mixer, CIC, compensator FIR, Hilbert FIR,
+Q delay, 8-byte frames) for every channel of the rank.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CH_PER_GPU = 1024
+BLOCK = 1 << 20
+A_INT_OPS = 41          # literal HDL-faithful INT32 ops per channel x ADC-sample
+SEED = 20261018
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels-per-gpu", type=int, default=CH_PER_GPU)
+    ap.add_argument("--block", type=int, default=BLOCK)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_ddc_rate(n_ch, n_samples, blocks, threads, seed=SEED, warm=0):
+    """Golden model (oracle/, C, scalar per channel) on `threads` host threads -> channel*samples/s."""
+    from oracle import pyoracle
+    import ua3reo_loader
+    synth = ua3reo_loader.load().synth
+    adc = synth.synth_adc(n_samples, seed=seed)
+    bank = pyoracle.GoldenBank(synth.random_fcw(n_ch, seed))
+    for _ in range(warm):
+        bank.push(adc, threads)
+    t = 0.0
+    for _ in range(blocks):
+        t += bank.push(adc, threads)
+    return n_ch * n_samples * blocks / t, t
+
+
+def run_reference(args):
+    """--impl reference: the reference algorithm's CPU implementation (the golden restatement of the HDL;
+    the FPGA design cannot be compiled or simulated here) on all host cores.  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    n_ch = 2 * cores
+    n_samples = 1 << 18            # bounded sample: 2*cores channels x 2^18 ADC samples per step
+    rate, t = cpu_ddc_rate(n_ch, n_samples, args.steps, cores, warm=args.warmup)
+    sample = "%d channels x 2^18 ADC samples per step, %d threads, golden C model (oracle/ddc_golden.c)" % (n_ch, cores)
+    line = {
+        "impl": "reference", "metric": "ddc_channel_adc_samples_per_s", "value": rate, "unit": "channel*samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": "full FPGA RX DDC, random tuning words, one shared 12-bit ADC stream (CPU sample: %s)" % sample,
+                   "channels_per_gpu": args.channels_per_gpu, "block_samples": args.block},
+        "cpu_baseline": {"value": rate, "unit": "channel*samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "channel*samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ua3reo_loader
+    pkg = ua3reo_loader.load()
+    synth = pkg.synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - this repo has no CPU fallback (use --impl reference for the CPU model)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_ch, block, K, W = args.channels_per_gpu, args.block, args.steps, args.warmup
+
+    rx = pkg.Receiver(n_ch, block, device=local)
+    fcw_all = synth.random_fcw(n_ch * world, SEED)
+    rx.set_fcw(fcw_all[rank * n_ch:(rank + 1) * n_ch])          # channels sharded by rank, contiguous slabs
+    ext = torch.cuda.ExternalStream(rx.stream(), device=local)
+
+    # synthetic ADC: NB distinct blocks generated once on the host (pinned); rank 0 is the ingest rank
+    NB = 4
+    host_blocks = torch.from_numpy(synth.synth_adc(NB * block, SEED).reshape(NB, block)).pin_memory()
+    dev_blocks = host_blocks.cuda(non_blocking=False) if rank == 0 else None
+    bcast = [torch.empty(block, dtype=torch.int16, device="cuda") for _ in range(2)]
+    frames_host = torch.empty((n_ch, block // 1024, 8), dtype=torch.uint8).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        """One ADC block, input resident in HBM.  N>1: rank 0 broadcasts the block over NVLink first."""
+        with torch.cuda.stream(ext):
+            if world > 1:
+                buf = bcast[i & 1]
+                if rank == 0:
+                    buf.copy_(dev_blocks[i % NB], non_blocking=True)
+                dist.broadcast(buf, src=0)
+                rx.push(buf)
+            else:
+                rx.push(dev_blocks[i % NB])
+
+    def step_e2e(i):
+        """Same step through the host-facing C ABI: H2D of the ADC block (rank 0 ingests, others receive the
+        broadcast), kernels, D2H of every frame."""
+        with torch.cuda.stream(ext):
+            if world > 1:
+                buf = bcast[i & 1]
+                if rank == 0:
+                    buf.copy_(host_blocks[i % NB], non_blocking=True)
+                dist.broadcast(buf, src=0)
+                rx.push(buf)
+            else:
+                rx.push(host_blocks[i % NB])
+        rx.read_frames(frames_host)
+
+    for i in range(W):
+        step_device(i)
+    barrier()
+    int32_peak = pkg.measure_int32_peak(local)
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    rx.profile_begin(K)
+    launches0 = rx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(ext):
+        e0.record()
+    for i in range(K):
+        step_device(i)
+    with torch.cuda.stream(ext):
+        e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = rx.launch_count() - launches0
+    kms, nblocks = rx.profile_end()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end through the C ABI with host buffers
+    for i in range(max(2, W // 2)):
+        step_e2e(i)
+    barrier()
+    with torch.cuda.stream(ext):
+        e0.record()
+    for i in range(K):
+        step_e2e(i)
+    with torch.cuda.stream(ext):
+        e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+
+    units = float(n_ch) * world * block * K
+    value = units / (ms * 1e-3)
+    e2e = units / (ms_e2e * 1e-3)
+    front_s = kms["front"] * 1e-3 / max(nblocks, 1)
+    achieved = A_INT_OPS * float(n_ch) * block / front_s if front_s > 0 else 0.0
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = host_cores()
+            c_ch, c_n = 4 * cores, 1 << 19
+            blocks = 1
+            rate, t = cpu_ddc_rate(c_ch, c_n, 1, cores)
+            while t < 10.0 and blocks < 64:                       # bounded: about 10-20 s of CPU work
+                r2, t2 = cpu_ddc_rate(c_ch, c_n, min(blocks * 2, 64), cores)
+                rate, t, blocks = r2, t + t2, min(blocks * 2, 64)
+            cpu = {"value": rate, "unit": "channel*samples/s", "cores": cores, "kind": "port",
+                   "sample": "%d channels x 2^19 ADC samples x %d blocks, %d threads, golden C model "
+                             "(oracle/ddc_golden.c; the FPGA HDL itself cannot be built here)" % (c_ch, blocks, cores)}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        step_bytes = 2.0 * block * (n_ch // 32) + 2 * 80.0 * n_ch * (block // 512) + 8.0 * n_ch * (block // 1024)
+        line = {
+            "metric": "ddc_channel_adc_samples_per_s", "value": value, "unit": "channel*samples/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]/[3]: %d independent DDC channels per GPU (random tuning words, seed %d) "
+                                   "over one shared synthetic 12-bit ADC stream, blocks of %d samples; full FPGA RX chain "
+                                   "(NCO+mixer+CIC/512+compensator FIR+Hilbert FIR+Q delay+8-byte frames); "
+                                   "N>1: channels sharded by rank, ADC block NCCL-broadcast from rank 0" % (n_ch, SEED, block),
+                       "channels_total": n_ch * world, "channels_per_gpu": n_ch, "block_samples": block,
+                       "real_time_channels": value / 49152000.0,
+                       "l2": "per-step working set ~%.0f MB (chunk records + frames) exceeds the 126 MB L2; no flush needed"
+                             % (step_bytes / 1e6)},
+            "e2e": {"value": e2e, "unit": "channel*samples/s", "h2d_bytes_per_step": 2 * block,
+                    "d2h_bytes_per_step": n_ch * (block // 1024) * 8, "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "int32_alu", "kernel": "ddc_front_kernel", "achieved": achieved / 1e12, "peak": int32_peak / 1e12,
+                         "unit": "TOP/s (INT32)", "frac": (achieved / int32_peak) if int32_peak else None,
+                         "traffic": None,
+                         "ops_per_unit": A_INT_OPS, "units_per_launch": float(n_ch) * block,
+                         "kernel_ms": front_s * 1e3,
+                         "kernel_share_of_step": kms["front"] / max(sum(kms.values()), 1e-9),
+                         "all_kernels_ms_per_step": {k: v / max(nblocks, 1) for k, v in kms.items()},
+                         "peak_source": "ua3reo_measure_int32_peak (IMAD+LOP3+IADD3 chains), measured live on this GPU; "
+                                        "MEASURED_PEAKS.json has no integer peak",
+                         "hbm": {"algorithmic_gbs": step_bytes / (ms / K * 1e-3) / 1e9,
+                                 "peak_gbs": peaks.get("hbm_gbs"), "note": "HBM is not the bound (SURVEY.md 8d)"}},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    rx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

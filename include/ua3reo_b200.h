@@ -93,6 +93,15 @@ int ua3reo_stream(ua3reo_ctx *ctx, void **stream);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t ua3reo_launch_count(const ua3reo_ctx *ctx);
 
+/* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline):
+ * after ua3reo_profile_begin(ctx, max_blocks) each processed ADC block records an event before and
+ * after every kernel; ua3reo_profile_end() waits for the stream and sums the elapsed times per
+ * kernel over the recorded blocks.  kernel_ms[0..4] = front (NCO+mixer+CIC integrators), cic combs,
+ * compensator FIR, Hilbert+delay+frame pack, state rotate. */
+#define UA3_DDC_KERNELS 5u
+int ua3reo_profile_begin(ua3reo_ctx *ctx, uint32_t max_blocks);
+int ua3reo_profile_end(ua3reo_ctx *ctx, double *kernel_ms, uint32_t n_kernels, uint32_t *blocks);
+
 /* Dependent-free INT32 issue-rate microbenchmark (IADD3 + IMAD interleaved) used as the roofline
  * denominator: returns integer operations per second summed over the whole device. */
 int ua3reo_measure_int32_peak(int device, double *ops_per_s);

@@ -36,6 +36,12 @@ def lib():
         L.ua3g_nco.argtypes = [ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
         L.ua3g_rx_mix.restype = ctypes.c_int32
         L.ua3g_rx_mix.argtypes = [ctypes.c_int32, ctypes.c_int32]
+        L.ua3g_bank_create.restype = ctypes.c_void_p
+        L.ua3g_bank_create.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        L.ua3g_bank_destroy.argtypes = [ctypes.c_void_p]
+        L.ua3g_bank_push.restype = ctypes.c_double
+        L.ua3g_bank_push.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                     ctypes.c_int]
         _lib = L
     return _lib
 
@@ -82,3 +88,25 @@ def synth_adc(n, seed=20261018, tones=8, noise_lsb=8.0, level_dbfs=-6.0):
         x += amp * np.sin(2 * np.pi * f[k] * t + ph[k])
     x += rng.normal(0.0, noise_lsb, n)
     return np.clip(np.rint(x), -2048, 2047).astype(np.int16)
+
+
+class GoldenBank:
+    """n_ch golden DDC channels driven by n_threads host threads (bench baseline only)."""
+
+    def __init__(self, fcws):
+        self.fcw = np.ascontiguousarray(fcws, dtype=np.uint32)
+        self.n_ch = self.fcw.size
+        self._b = lib().ua3g_bank_create(self.n_ch, self.fcw.ctypes.data)
+
+    def push(self, adc, n_threads, want_frames=False):
+        adc = np.ascontiguousarray(adc, dtype=np.int16)
+        frames = np.zeros((self.n_ch, adc.size // 1024, 8), np.uint8) if want_frames else None
+        dt = lib().ua3g_bank_push(self._b, self.n_ch, adc.ctypes.data, adc.size,
+                                  frames.ctypes.data if want_frames else None, int(n_threads))
+        return (dt, frames) if want_frames else dt
+
+    def __del__(self):
+        try:
+            lib().ua3g_bank_destroy(self._b)
+        except Exception:
+            pass

@@ -12,6 +12,9 @@ import os
 
 import numpy as np
 
+from . import synth  # noqa: F401  (synthetic ADC stream / tuning words of SURVEY.md 8d)
+from .synth import random_fcw, synth_adc  # noqa: F401
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libua3reo_b200.so")
 
@@ -50,6 +53,8 @@ def _bind(lib):
         "ua3reo_sync": (c.c_int, [vp]),
         "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_launch_count": (c.c_uint64, [vp]),
+        "ua3reo_profile_begin": (c.c_int, [vp, u32]),
+        "ua3reo_profile_end": (c.c_int, [vp, c.POINTER(c.c_double), u32, c.POINTER(u32)]),
         "ua3reo_measure_int32_peak": (c.c_int, [c.c_int, c.POINTER(c.c_double)]),
     }
     for name, (res, args) in sigs.items():
@@ -168,6 +173,16 @@ class Receiver:
         s = ctypes.c_void_p()
         self._chk(self.lib.ua3reo_stream(self._h, ctypes.byref(s)))
         return s.value or 0
+
+    def profile_begin(self, max_blocks):
+        self._chk(self.lib.ua3reo_profile_begin(self._h, int(max_blocks)))
+
+    def profile_end(self):
+        ms = (ctypes.c_double * 5)()
+        nb = ctypes.c_uint32(0)
+        self._chk(self.lib.ua3reo_profile_end(self._h, ms, 5, ctypes.byref(nb)))
+        names = ["front", "cic", "comp", "hilb", "rotate"]
+        return {k: float(v) for k, v in zip(names, ms)}, int(nb.value)
 
     def launch_count(self):
         return int(self.lib.ua3reo_launch_count(self._h))

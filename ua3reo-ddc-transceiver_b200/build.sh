@@ -8,7 +8,7 @@ mkdir -p "$OUT"
 SRCS=("$HERE"/csrc/*.cu)
 # --fmad=false: the float audio/FFT stages must match the firmware's unfused arithmetic
 "$NVCC" -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -std=c++17 \
-    -Xcompiler -fPIC,-O2,-Wall,-Wno-unknown-pragmas -Xptxas -v --shared -o "$OUT/libua3reo_b200.so" "${SRCS[@]}" -lcudart 2> "$OUT/ptxas.log" \
+    -Xcompiler -fPIC,-O2,-Wall,-Wno-unknown-pragmas -Xptxas -v --shared -o "$OUT/libua3reo_b200.so" "${SRCS[@]}" 2> "$OUT/ptxas.log" \
     || { cat "$OUT/ptxas.log"; exit 1; }
 grep -E "error|warning" "$OUT/ptxas.log" || true
 echo "built $OUT/libua3reo_b200.so"

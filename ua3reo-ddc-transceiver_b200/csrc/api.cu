@@ -37,6 +37,8 @@ struct ua3reo_ctx {
     std::vector<uint8_t> h_iq_swap;
     uint64_t launches = 0;
     std::vector<void*> allocs;
+    std::vector<cudaEvent_t> prof_ev;   // (kDdcKernels + 1) events per profiled block
+    uint32_t prof_cap = 0, prof_used = 0;
 };
 
 template <class T>
@@ -70,6 +72,7 @@ static int ctx_free(ua3reo_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void* p : c->allocs) cudaFree(p);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return UA3_OK;
@@ -192,7 +195,9 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
         UA3_CUDA(cudaMemcpyAsync(c->adc_stage + c->carry, src, n * sizeof(int16_t), kind, c->stream));
     }
     int launches = 0;
-    if (n_proc) UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, c->sm_count, c->stream, &launches));
+    cudaEvent_t* ev = nullptr;
+    if (n_proc && c->prof_used < c->prof_cap) ev = c->prof_ev.data() + (size_t)(c->prof_used++) * (kDdcKernels + 1);
+    if (n_proc) UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, c->sm_count, c->stream, &launches, ev));
     c->launches += (uint64_t)launches;
     const uint32_t left = (uint32_t)(total - n_proc);
     if (!in_place && n_proc && left)
@@ -244,6 +249,37 @@ int ua3reo_sync(ua3reo_ctx* c) {
 int ua3reo_stream(ua3reo_ctx* c, void** stream) {
     if (!c || !stream) return fail(UA3_E_INVAL, "null argument");
     *stream = (void*)c->stream;
+    return UA3_OK;
+}
+
+int ua3reo_profile_begin(ua3reo_ctx* c, uint32_t max_blocks) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    UA3_CUDA(cudaSetDevice(c->device));
+    while (c->prof_ev.size() < (size_t)max_blocks * (kDdcKernels + 1)) {
+        cudaEvent_t e;
+        UA3_CUDA(cudaEventCreate(&e));
+        c->prof_ev.push_back(e);
+    }
+    c->prof_cap = max_blocks;
+    c->prof_used = 0;
+    return UA3_OK;
+}
+
+int ua3reo_profile_end(ua3reo_ctx* c, double* kernel_ms, uint32_t n_kernels, uint32_t* blocks) {
+    if (!c || !kernel_ms) return fail(UA3_E_INVAL, "null argument");
+    UA3_CUDA(cudaSetDevice(c->device));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint32_t k = 0; k < n_kernels; ++k) kernel_ms[k] = 0.0;
+    for (uint32_t b = 0; b < c->prof_used; ++b)
+        for (uint32_t k = 0; k < (uint32_t)kDdcKernels && k < n_kernels; ++k) {
+            float ms = 0.f;
+            const cudaEvent_t* ev = c->prof_ev.data() + (size_t)b * (kDdcKernels + 1);
+            UA3_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
+            kernel_ms[k] += (double)ms;
+        }
+    if (blocks) *blocks = c->prof_used;
+    c->prof_cap = 0;
+    c->prof_used = 0;
     return UA3_OK;
 }
 

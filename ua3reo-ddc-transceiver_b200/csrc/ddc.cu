@@ -193,22 +193,28 @@ cudaError_t ddc_upload_constants() {
 }
 
 cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, int sm_count,
-                             cudaStream_t st, int* launches) {
+                             cudaStream_t st, int* launches, cudaEvent_t* ev) {
     const uint32_t n_chunks = n_samples / kCicR, n_frames = n_samples / kFrameAdc;
     if (n_chunks == 0) return cudaSuccess;
     const uint32_t n_tiles = ((n_chunks + kFrontWarps - 1) / kFrontWarps) * (b.n_ch_pad >> 5);
     const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count * 3);
+    if (ev) cudaEventRecord(ev[0], st);
     UA3_LAUNCH(ddc_front_kernel, grid, kFrontThreads, 0, st, adc_dev, n_chunks, b.nco_tab, b.fcw, b.phase, b.n_ch_pad,
                b.L, b.l_ch_stride);
+    if (ev) cudaEventRecord(ev[1], st);
     UA3_LAUNCH(ddc_cic_kernel, dim3(b.n_ch * 2, (n_chunks + 255) / 256), 256, 0, st, b.L, b.l_ch_stride, n_chunks,
                b.n_ch, b.U, b.u_rail_stride);
+    if (ev) cudaEventRecord(ev[2], st);
     UA3_LAUNCH(ddc_comp_kernel, dim3(b.n_ch * 2, (n_frames + 255) / 256), 256, 0, st, b.U, b.u_rail_stride, n_frames,
                b.YI, b.yi_stride, b.YQ, b.yq_stride);
+    if (ev) cudaEventRecord(ev[3], st);
     UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + 255) / 256), 256, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
                n_frames, b.frames, b.frame_ch_stride);
+    if (ev) cudaEventRecord(ev[4], st);
     UA3_LAUNCH(ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.U, b.u_rail_stride, b.YI, b.yi_stride,
                b.YQ, b.yq_stride, n_chunks, n_frames, b.phase, b.fcw, b.n_ch_pad);
-    if (launches) *launches += 5;
+    if (ev) cudaEventRecord(ev[5], st);
+    if (launches) *launches += kDdcKernels;
     return cudaGetLastError();
 }
 

@@ -26,8 +26,10 @@ struct DdcBuffers {
 void build_cic_weights(uint64_t G[25]);
 void build_nco_table(uint32_t tab[2048]);
 cudaError_t ddc_upload_constants();
+constexpr int kDdcKernels = 5;   // front, cic, comp, hilb, rotate
+// ev: optional array of kDdcKernels + 1 events recorded before/after each kernel (profiling mode)
 cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, int sm_count,
-                             cudaStream_t st, int* launches);
+                             cudaStream_t st, int* launches, cudaEvent_t* ev);
 cudaError_t measure_int32_peak(int sm_count, cudaStream_t st, double* ops_per_s);
 
 }  // namespace ua3
