@@ -84,14 +84,68 @@ int ua3reo_ddc_push_device(ua3reo_ctx *ctx, const int16_t *adc_dev, size_t n, si
  *   SPEC_Q hi, lo, SPEC_I hi, lo, VOICE_Q hi, lo, VOICE_I hi, lo.
  * dst is [n_channels][n_frames][8] bytes; n_frames must equal the last push's frames_out. */
 int ua3reo_ddc_read_frames(ua3reo_ctx *ctx, uint8_t *dst_host, size_t n_frames);
-/* Device view of the same data: base pointer, frames of the last push, bytes between channels. */
-int ua3reo_ddc_frames_device(ua3reo_ctx *ctx, const uint8_t **base, size_t *n_frames, size_t *channel_stride_bytes);
+/* Device view of the same data.  Each channel owns a ring of *ring_frames 8-byte frames (a power of two),
+ * *channel_stride_bytes apart; the last push wrote *n_frames frames starting at ring index *first_frame. */
+int ua3reo_ddc_frames_device(ua3reo_ctx *ctx, const uint8_t **base, size_t *first_frame, size_t *n_frames,
+                             size_t *ring_frames, size_t *channel_stride_bytes);
 
 int ua3reo_sync(ua3reo_ctx *ctx);
 /* The context's CUDA stream (cudaStream_t), for callers that enqueue their own copies. */
 int ua3reo_stream(ua3reo_ctx *ctx, void **stream);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t ua3reo_launch_count(const ua3reo_ctx *ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * STM32 stage: processRxAudio() and FFT_doFFT() for every channel.
+ * ------------------------------------------------------------------------------------------- */
+
+/* The subset of `struct TRX_SETTINGS TRX` / `VFO` (settings.h:57-123) and of the TRX manager globals
+ * (trx_manager.h:60-61) that processRxAudio()/FFT_doFFT() read, per channel.  Defaults (ua3reo_rx_defaults)
+ * are the firmware's LoadSettings() values (settings.c:33-94). */
+typedef struct ua3reo_rx_settings {
+    uint8_t mode;              /* TRX_MODE_* (trx_manager.h:11-24): 0 LSB 1 USB 2 IQ 3 CW_L 4 CW_U 5 DIGI_L 6 DIGI_U 8 NFM 9 WFM 10 AM */
+    uint8_t agc;               /* TRX.AGC */
+    uint8_t agc_speed;         /* TRX.Agc_speed (agc.c:17) */
+    uint8_t dnr;               /* TRX.DNR */
+    uint8_t notch;             /* TRX.NotchFilter */
+    uint8_t mute;              /* TRX.Mute */
+    uint8_t volume;            /* TRX.Volume, percent */
+    uint8_t rf_gain;           /* TRX.RF_Gain */
+    uint8_t fm_sql_threshold;  /* TRX.FM_SQL_threshold */
+    uint8_t fft_enabled;       /* TRX.FFT_Enabled */
+    uint8_t fft_averaging;     /* TRX.FFT_Averaging */
+    uint8_t fft_zoom;          /* TRX.FFT_Zoom: only 1 is implemented (ZoomFFT is a later row) */
+    uint8_t iq_swap;           /* TRX_IQ_swap (functions.c:211-223) */
+    uint8_t reserved[3];
+    uint16_t filter_width;     /* CurrentVFO()->Filter_Width: 0 (LPF off) or one of the 32 table widths (audio_filters.c:59-122) */
+    uint16_t ssb_hpf_pass;     /* TRX.SSB_HPF_pass: 60/100/200/300/400/500 */
+    uint16_t notch_fc;         /* TRX.NotchFC, Hz */
+    uint16_t reserved2;
+} ua3reo_rx_settings;
+
+void ua3reo_rx_defaults(ua3reo_rx_settings *s);
+
+/* initAudioProcessor() + FFT_Init() (audio_processor.c:55-59, fft.c:185-210) for every channel, and from
+ * then on every ua3reo_ddc_push*() also runs the STM32 stage over the whole 192-sample audio blocks and
+ * 512-sample FFT frames that have become available (frames are buffered across pushes).  */
+int ua3reo_rx_enable(ua3reo_ctx *ctx, int enable);
+
+/* TRX_setMode()/ReinitAudioFilters()/InitNotchFilter()/InitAGC() for channels [first, first+n)
+ * (trx_manager.c:193-220, audio_filters.c:141-346, agc.c:14-19).  As in the firmware, selecting filters
+ * clears the lattice filter states of the channel.  Fails with UA3_E_INVAL for a filter width, HPF
+ * corner or mode the firmware has no table/branch for. */
+int ua3reo_rx_set(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const ua3reo_rx_settings *settings);
+
+/* Results of the last push.  Audio: what processRxAudio() leaves in Processor_AudioBuffer_A/B
+ * (audio_processor.c:377-394): per channel and block 384 int32, L/R interleaved.  dst is
+ * [n_channels][n_blocks][384]; n_blocks must equal *audio_blocks of ua3reo_rx_counts(). */
+int ua3reo_rx_counts(ua3reo_ctx *ctx, size_t *audio_blocks, size_t *fft_frames);
+int ua3reo_rx_read_audio(ua3reo_ctx *ctx, int32_t *dst_host, size_t n_blocks);
+/* Spectra: FFTOutput_mean (fft.c:27,324-328) after each FFT_doFFT(): dst is [n_channels][n_frames][256] float. */
+int ua3reo_rx_read_spectra(ua3reo_ctx *ctx, float *dst_host, size_t n_frames);
+/* S-meter accumulators Processor_RX_Audio_Samples_MAX/MIN_value (audio_processor.c:491-501): dst [n_channels][2];
+ * reset != 0 clears them afterwards, as the 1 s housekeeping tick does (stm32f4xx_it.c:398-409). */
+int ua3reo_rx_read_smeter(ua3reo_ctx *ctx, float *dst_host, int reset);
 
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline):
  * after ua3reo_profile_begin(ctx, max_blocks) each processed ADC block records an event before and

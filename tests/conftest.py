@@ -15,7 +15,13 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def pkg():
     import ua3reo_loader
-    return ua3reo_loader.load()
+    mod = ua3reo_loader.load()
+    # DEVELOPMENT AID: UA3REO_DEV_EMU=1 points the tests at the host-emulation build of the CUDA sources
+    # (tools/emu) so that `-m gpu` test logic can be debugged in the GPU-less build container.
+    emu = os.path.join(ROOT, "tools", "emu", "_build", "libua3reo_emu.so")
+    if os.environ.get("UA3REO_DEV_EMU") == "1" and os.path.exists(emu):
+        mod.LIB_PATH = emu
+    return mod
 
 
 @pytest.fixture(scope="session")

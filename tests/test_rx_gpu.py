@@ -1,0 +1,157 @@
+"""processRxAudio()/FFT_doFFT() on the GPU against the reference firmware's own C code:
+(a) the committed golden fixtures (tests/golden/rx_cases.npz, produced by oracle/_ref/fw_rx from the
+    reference sources; generator tools/gen_golden_rx.py), every mode the firmware demodulates;
+(b) when the host-built firmware binary travelled with the snapshot, live runs on fresh random input.
+Tolerance (BASELINE.json north_star): max |delta| / peak <= 1e-5 and SNR >= 120 dB per channel."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+TOL_REL, TOL_SNR = 1e-5, 120.0
+
+
+def stats(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    peak = max(np.abs(ref).max(), 1e-30)
+    den = ((got - ref) ** 2).sum()
+    snr = 10 * np.log10(max((ref ** 2).sum(), 1e-300) / den) if den > 0 else np.inf
+    return np.abs(got - ref).max() / peak, snr
+
+
+def check(got, ref, what):
+    if not np.any(ref):
+        assert not np.any(got), what + ": reference is all zero"
+        return
+    err, snr = stats(got, ref)
+    # int32 audio: one LSB of truncation noise is allowed on top of the relative tolerance
+    lsb = 1.0 / max(np.abs(np.asarray(ref, np.float64)).max(), 1.0) if np.issubdtype(np.asarray(ref).dtype, np.integer) else 0.0
+    assert err <= TOL_REL + lsb, "%s: max|d|/peak = %.3e" % (what, err)
+    assert snr >= TOL_SNR or err <= lsb, "%s: SNR = %.1f dB" % (what, snr)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "rx_cases.npz"))
+    return z, json.loads(bytes(z["meta"]).decode())
+
+
+def _run_frames_through_gpu(pkg, oracle, cases, n_adc, pushes, seed):
+    """Frames come from the GPU DDC itself (all channels share tuning word and ADC stream)."""
+    fs = 49152000.0
+    t = np.arange(n_adc, dtype=np.float64)
+    f0 = 605867 * fs / 2 ** 22
+    rng = np.random.default_rng(seed)
+    x = 600 * np.cos(2 * np.pi * (f0 + 1000.0) / fs * t) + 250 * np.cos(2 * np.pi * (f0 - 1900.0) / fs * t)
+    x += 200 * (1 + 0.5 * np.cos(2 * np.pi * 400.0 / fs * t)) * np.cos(2 * np.pi * (f0 + 6000.0) / fs * t)
+    x += rng.normal(0, 8.0, n_adc)
+    adc = np.clip(np.rint(x), -2048, 2047).astype(np.int16)
+    rx = pkg.Receiver(len(cases), 1 << 21)
+    rx.set_fcw([605867] * len(cases))
+    rx.rx_enable(True)
+    rx.rx_set([rx.rx_defaults(**c) for c in cases])
+    frames, audio, spec, off = [], [], [], 0
+    for p in pushes:
+        rx.push(adc[off:off + p]); off += p
+        frames.append(rx.read_frames()); audio.append(rx.read_audio()); spec.append(rx.read_spectra())
+    sm = rx.read_smeter()
+    rx.close()
+    return np.concatenate(frames, 1), np.concatenate(audio, 1), np.concatenate(spec, 1), sm
+
+
+def test_against_reference_firmware_fixtures(pkg, oracle, golden):
+    z, meta = golden
+    cases = meta["cases"]
+    n_frames = meta["n_frames"]
+    # same ADC recipe as tools/gen_golden_rx.py -> the GPU DDC must reproduce the fixture's frames bit-exactly
+    keys = ("mode", "agc", "agc_speed", "dnr", "notch", "mute", "volume", "rf_gain", "fm_sql_threshold", "fft_enabled",
+            "fft_averaging", "fft_zoom", "iq_swap", "filter_width", "ssb_hpf_pass", "notch_fc")
+    frames, audio, spec, sm = _run_frames_through_gpu(
+        pkg, oracle, [{k: c["settings"][k] for k in keys} for c in cases], 1024 * n_frames, [1024 * n_frames], 20261018)
+    assert np.array_equal(frames[0], z["frames"]), "GPU DDC frames differ from the fixture's golden frames"
+    exact = 0
+    for i, c in enumerate(cases):
+        ra, rs = z[c["name"] + "/audio"], z[c["name"] + "/spectra"]
+        assert audio.shape[1] == ra.shape[0] == 7
+        check(audio[i], ra, c["name"] + " audio")
+        exact += int(np.array_equal(audio[i], ra))
+        if c["settings"]["fft_enabled"]:
+            assert spec.shape[1] == rs.shape[0] == 2
+            check(spec[i], rs, c["name"] + " spectrum")
+        rsm = z[c["name"] + "/smeter"][-1]
+        assert np.allclose(sm[i], rsm, rtol=1e-5, atol=1e-3), c["name"] + " s-meter"
+    # SSB/CW/DIGI/IQ/AM use only IEEE +,-,*,/,sqrt: those channels are expected to be bit-identical
+    assert exact >= len(cases) - 3, "only %d of %d cases bit-exact" % (exact, len(cases))
+
+
+def test_state_carry_across_pushes(pkg, oracle, golden):
+    """Splitting the ADC stream into ragged pushes changes nothing (ring buffer + per-channel state)."""
+    z, meta = golden
+    cases = [dict(mode=1, dnr=1, notch=1, notch_fc=1500), dict(mode=0), dict(mode=8, filter_width=15000), dict(mode=10, filter_width=6000)]
+    n = 1024 * (192 * 9 + 5)
+    _, a1, s1, _ = _run_frames_through_gpu(pkg, oracle, cases, n, [n], 7)
+    _, a2, s2, _ = _run_frames_through_gpu(pkg, oracle, cases, n, [1024 * 700 + 3, 1024 * 11, 1021, n - (1024 * 711 + 3 + 1021)], 7)
+    assert a1.shape[1] == 9 and s1.shape[1] == 3
+    assert np.array_equal(a1, a2) and np.array_equal(s1, s2)
+
+
+def test_live_against_host_built_firmware(pkg, oracle):
+    if not oracle.have_fw_rx():
+        pytest.skip("oracle/_ref/fw_rx did not travel with this snapshot")
+    cases = [dict(mode=m, filter_width=w, dnr=d, notch=nt, notch_fc=fc, agc_speed=sp, rf_gain=g, iq_swap=sw)
+             for m, w, d, nt, fc, sp, g, sw in [
+                 (0, 2700, 0, 0, 1000, 3, 50, 0), (1, 3400, 1, 1, 700, 5, 30, 0), (3, 500, 1, 0, 1000, 3, 50, 1),
+                 (4, 300, 0, 1, 600, 1, 80, 0), (5, 2900, 0, 0, 1000, 3, 50, 0), (6, 1800, 1, 0, 1000, 7, 10, 1),
+                 (10, 10000, 0, 1, 2000, 3, 50, 0), (8, 9000, 0, 0, 1000, 3, 50, 0), (9, 15000, 1, 0, 1000, 3, 50, 0),
+                 (2, 2700, 0, 0, 1000, 3, 50, 1), (1, 0, 0, 0, 1000, 3, 50, 0), (0, 5000, 0, 0, 1000, 9, 100, 0)]]
+    n = 1024 * (192 * 12 + 1)
+    frames, audio, spec, sm = _run_frames_through_gpu(pkg, oracle, cases, n, [n // 2 + 17, n - (n // 2 + 17)], 99)
+    rx0 = pkg.Receiver(1, 1024)
+    for i, c in enumerate(cases):
+        s = rx0.rx_defaults(**c).as_dict()
+        ref = oracle.run_fw_rx(frames[i], s)
+        nb = min(audio.shape[1], ref["audio"].shape[0])
+        assert nb == 12
+        check(audio[i, :nb], ref["audio"][:nb], "live %s audio" % c)
+        nf = min(spec.shape[1], ref["spectra"].shape[0])
+        assert nf >= 4
+        check(spec[i, :nf], ref["spectra"][:nf], "live %s spectrum" % c)
+    rx0.close()
+
+
+def test_rejects_settings_without_firmware_table(pkg):
+    rx = pkg.Receiver(2, 1024)
+    rx.rx_enable(True)
+    for bad in (dict(filter_width=2750), dict(mode=12), dict(agc_speed=0), dict(fft_zoom=2), dict(fft_averaging=0)):
+        with pytest.raises(pkg.UA3Error):
+            rx.rx_set(rx.rx_defaults(**bad))
+    rx.rx_set(rx.rx_defaults(mode=1, ssb_hpf_pass=60))     # no branch in ReinitAudioFilters: keeps the previous HPF
+    rx.close()
+
+
+def test_full_chain_many_channels_consistency(pkg, oracle):
+    """BASELINE config 5 shape at reduced length: 512 channels, modes round-robin; channels that share
+    tuning word and settings must agree bit for bit, whatever lane pair / warp they land in."""
+    n_ch = 512
+    modes = [0, 1, 4, 10, 8]
+    widths = {0: 2700, 1: 2700, 4: 500, 10: 6000, 8: 15000}
+    rx = pkg.Receiver(n_ch, 1 << 19)
+    fcw = np.where(np.arange(n_ch) % 2 == 0, 605867, 620407).astype(np.uint32)
+    rx.set_fcw(fcw)
+    rx.rx_enable(True)
+    sets = []
+    for c in range(n_ch):
+        m = modes[(c // 2) % 5]
+        sets.append(rx.rx_defaults(mode=m, filter_width=widths[m], dnr=(c // 10) % 2, notch=(c // 10) % 2))
+    rx.rx_set(sets)
+    adc = oracle.synth_adc(1 << 19, seed=5)
+    rx.push(adc)
+    a, s = rx.read_audio(), rx.read_spectra()
+    rx.close()
+    assert a.shape == (n_ch, 2, 384) and s.shape == (n_ch, 1, 256)
+    for c in range(20, n_ch):
+        assert np.array_equal(a[c], a[c - 20]) and np.array_equal(s[c], s[c - 20])   # period lcm(10,20)=20 in settings, 2 in fcw

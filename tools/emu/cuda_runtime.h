@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <math.h>
 #include <barrier>
 #include <thread>
 #include <vector>
@@ -86,3 +87,23 @@ static void ua3_emu_launch(K kernel, dim3 grid, dim3 block, A... args) {
     }
 }
 #define UA3_LAUNCH(kernel, grid, block, smem, stream, ...) ua3_emu_launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
+
+// ---- warp primitives for single-warp CTAs (every lane of the CTA takes part; no divergence around them) ----
+extern float ua3_emu_shfl_slots[1024];
+static inline float ua3_emu_shfl(float v, int src_lane) {
+    ua3_emu_shfl_slots[threadIdx.x] = v;
+    ua3_emu_barrier->arrive_and_wait();
+    const float r = ua3_emu_shfl_slots[(threadIdx.x & ~31u) | (unsigned)(src_lane & 31)];
+    ua3_emu_barrier->arrive_and_wait();
+    return r;
+}
+static inline float __shfl_xor_sync(unsigned, float v, int m) { return ua3_emu_shfl(v, (int)(threadIdx.x & 31) ^ m); }
+static inline float __shfl_sync(unsigned, float v, int l) { return ua3_emu_shfl(v, l); }
+static inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, int m) {
+    float f; memcpy(&f, &v, 4); f = ua3_emu_shfl(f, (int)(threadIdx.x & 31) ^ m); memcpy(&v, &f, 4); return v;
+}
+static inline void __syncwarp() { ua3_emu_barrier->arrive_and_wait(); }
+static inline cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t w, size_t h, cudaStream_t) {
+    for (size_t i = 0; i < h; ++i) memset((char*)p + i * pitch, v, w);
+    return 0;
+}

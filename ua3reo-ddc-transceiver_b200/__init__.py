@@ -31,6 +31,27 @@ class UA3Error(RuntimeError):
     pass
 
 
+# trx_manager.h:11-24
+MODE_LSB, MODE_USB, MODE_IQ, MODE_CW_L, MODE_CW_U, MODE_DIGI_L, MODE_DIGI_U, MODE_NO_TX, MODE_NFM, MODE_WFM, MODE_AM, \
+    MODE_LOOPBACK = range(12)
+
+
+class RxSettings(ctypes.Structure):
+    """struct ua3reo_rx_settings (include/ua3reo_b200.h): the TRX fields processRxAudio()/FFT_doFFT() read."""
+    _fields_ = [("mode", ctypes.c_uint8), ("agc", ctypes.c_uint8), ("agc_speed", ctypes.c_uint8), ("dnr", ctypes.c_uint8),
+                ("notch", ctypes.c_uint8), ("mute", ctypes.c_uint8), ("volume", ctypes.c_uint8), ("rf_gain", ctypes.c_uint8),
+                ("fm_sql_threshold", ctypes.c_uint8), ("fft_enabled", ctypes.c_uint8), ("fft_averaging", ctypes.c_uint8),
+                ("fft_zoom", ctypes.c_uint8), ("iq_swap", ctypes.c_uint8), ("reserved", ctypes.c_uint8 * 3),
+                ("filter_width", ctypes.c_uint16), ("ssb_hpf_pass", ctypes.c_uint16), ("notch_fc", ctypes.c_uint16),
+                ("reserved2", ctypes.c_uint16)]
+
+    FIELDS = ("mode", "agc", "agc_speed", "dnr", "notch", "mute", "volume", "rf_gain", "fm_sql_threshold", "fft_enabled",
+              "fft_averaging", "fft_zoom", "iq_swap", "filter_width", "ssb_hpf_pass", "notch_fc")
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k in self.FIELDS}
+
+
 def _bind(lib):
     c = ctypes
     vp, u32, sz = c.c_void_p, c.c_uint32, c.c_size_t
@@ -49,7 +70,14 @@ def _bind(lib):
         "ua3reo_ddc_push": (c.c_int, [vp, vp, sz, c.POINTER(sz)]),
         "ua3reo_ddc_push_device": (c.c_int, [vp, vp, sz, c.POINTER(sz)]),
         "ua3reo_ddc_read_frames": (c.c_int, [vp, vp, sz]),
-        "ua3reo_ddc_frames_device": (c.c_int, [vp, c.POINTER(vp), c.POINTER(sz), c.POINTER(sz)]),
+        "ua3reo_ddc_frames_device": (c.c_int, [vp, c.POINTER(vp), c.POINTER(sz), c.POINTER(sz), c.POINTER(sz), c.POINTER(sz)]),
+        "ua3reo_rx_defaults": (None, [c.POINTER(RxSettings)]),
+        "ua3reo_rx_enable": (c.c_int, [vp, c.c_int]),
+        "ua3reo_rx_set": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_rx_counts": (c.c_int, [vp, c.POINTER(sz), c.POINTER(sz)]),
+        "ua3reo_rx_read_audio": (c.c_int, [vp, vp, sz]),
+        "ua3reo_rx_read_spectra": (c.c_int, [vp, vp, sz]),
+        "ua3reo_rx_read_smeter": (c.c_int, [vp, vp, c.c_int]),
         "ua3reo_sync": (c.c_int, [vp]),
         "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_launch_count": (c.c_uint64, [vp]),
@@ -66,7 +94,7 @@ def _bind(lib):
 
 def load_library(path=None):
     """Loads the CUDA library.  Raises UA3Error when it is missing: no fallback exists."""
-    path = path or LIB_PATH
+    path = path or LIB_PATH   # module global, read at call time
     if not os.path.exists(path):
         raise UA3Error(
             "%s not found: build it with ua3reo-ddc-transceiver_b200/build.sh (nvcc, sm_100a). "
@@ -162,9 +190,58 @@ class Receiver:
         return out
 
     def frames_device(self):
-        base, nf, stride = ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_size_t()
-        self._chk(self.lib.ua3reo_ddc_frames_device(self._h, ctypes.byref(base), ctypes.byref(nf), ctypes.byref(stride)))
-        return base.value, int(nf.value), int(stride.value)
+        """(base pointer, first ring index, frames of last push, ring size in frames, bytes between channels)"""
+        base, first, nf, ring, stride = (ctypes.c_void_p(), ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t(),
+                                         ctypes.c_size_t())
+        self._chk(self.lib.ua3reo_ddc_frames_device(self._h, ctypes.byref(base), ctypes.byref(first), ctypes.byref(nf),
+                                                    ctypes.byref(ring), ctypes.byref(stride)))
+        return base.value, int(first.value), int(nf.value), int(ring.value), int(stride.value)
+
+    # ---- STM32 stage: processRxAudio / FFT_doFFT ----
+    def rx_defaults(self, **overrides):
+        s = RxSettings()
+        self.lib.ua3reo_rx_defaults(ctypes.byref(s))
+        for k, v in overrides.items():
+            setattr(s, k, v)
+        return s
+
+    def rx_enable(self, on=True):
+        self._chk(self.lib.ua3reo_rx_enable(self._h, 1 if on else 0))
+
+    def rx_set(self, settings, first=0):
+        """settings: one RxSettings (applied to every channel from `first`) or a list, one per channel."""
+        if isinstance(settings, RxSettings):
+            settings = [settings] * (self.n_channels - first)
+        arr = (RxSettings * len(settings))(*settings)
+        self._chk(self.lib.ua3reo_rx_set(self._h, int(first), len(settings), ctypes.cast(arr, ctypes.c_void_p)))
+
+    def rx_counts(self):
+        a, f = ctypes.c_size_t(), ctypes.c_size_t()
+        self._chk(self.lib.ua3reo_rx_counts(self._h, ctypes.byref(a), ctypes.byref(f)))
+        return int(a.value), int(f.value)
+
+    def read_audio(self, out=None):
+        """int32 [n_channels, blocks_of_last_push, 384] (L/R interleaved, Processor_AudioBuffer layout)."""
+        nb, _ = self.rx_counts()
+        if out is None:
+            out = np.empty((self.n_channels, nb, 2 * AUDIO_BLOCK), np.int32)
+        ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
+        self._chk(self.lib.ua3reo_rx_read_audio(self._h, ptr, nb))
+        return out
+
+    def read_spectra(self, out=None):
+        """float32 [n_channels, fft_frames_of_last_push, 256] (FFTOutput_mean after each FFT_doFFT)."""
+        _, nf = self.rx_counts()
+        if out is None:
+            out = np.empty((self.n_channels, nf, FFT_BINS), np.float32)
+        ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
+        self._chk(self.lib.ua3reo_rx_read_spectra(self._h, ptr, nf))
+        return out
+
+    def read_smeter(self, reset=False):
+        out = np.empty((self.n_channels, 2), np.float32)
+        self._chk(self.lib.ua3reo_rx_read_smeter(self._h, out.ctypes.data, 1 if reset else 0))
+        return out
 
     def sync(self):
         self._chk(self.lib.ua3reo_sync(self._h))

@@ -1,6 +1,7 @@
 // api.cu - C ABI of libua3reo_b200.so (declared in include/ua3reo_b200.h).
 #include "../../include/ua3reo_b200.h"
 #include "ddc_launch.h"
+#include "rx_launch.h"
 #include "ua3_common.cuh"
 #include <cmath>
 #include <cstdio>
@@ -10,6 +11,7 @@
 #include <vector>
 
 using namespace ua3;
+#include "rx_host.cpp.inc"
 
 static thread_local std::string g_err;
 
@@ -39,6 +41,16 @@ struct ua3reo_ctx {
     std::vector<void*> allocs;
     std::vector<cudaEvent_t> prof_ev;   // (kDdcKernels + 1) events per profiled block
     uint32_t prof_cap = 0, prof_used = 0;
+    // frame ring bookkeeping (monotonic frame counters; ring index = counter & ring_mask)
+    uint64_t w_pos = 0;                 // frames written so far
+    uint64_t a_pos = 0, f_pos = 0;      // frames consumed by the audio / FFT stage
+    // STM32 stage
+    bool rx_on = false, rx_alloc = false;
+    RxBuffers rx;
+    std::vector<ua3reo_rx_settings> h_set;
+    std::vector<RxParams> h_par;
+    uint8_t* rx_flags = nullptr;        // device scratch for rx_set's state-clear flags
+    size_t last_audio_blocks = 0, last_fft_frames = 0;
 };
 
 template <class T>
@@ -110,7 +122,10 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     b.u_rail_stride = (kUHalo + b.max_chunks + 7u) & ~7u;
     b.yi_stride = (kYIHalo + b.max_frames + 7u) & ~7u;
     b.yq_stride = (kYQHalo + b.max_frames + 7u) & ~7u;
-    b.frame_ch_stride = b.max_frames;
+    uint32_t ring = 1024;
+    while (ring < b.max_frames + 1024u) ring <<= 1;      // holds one push plus the <= 511 frames the STM32 stage has not consumed
+    b.frame_ch_stride = ring;
+    b.ring_mask = ring - 1u;
 #define UA3_TRY(call) do { e = (call); if (e != cudaSuccess) { ctx_free(c); return fail(UA3_E_CUDA, #call, e); } } while (0)
     UA3_TRY(dev_alloc(c, &b.nco_tab, 2048));
     UA3_TRY(dev_alloc(c, &b.fcw, c->n_ch_pad));
@@ -147,6 +162,13 @@ int ua3reo_reset(ua3reo_ctx* c) {
     UA3_CUDA(cudaMemsetAsync(b.YI, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * b.yi_stride, c->stream));
     UA3_CUDA(cudaMemsetAsync(b.YQ, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * b.yq_stride, c->stream));
     c->carry = 0; c->last_frames = 0; c->pushed = false;
+    c->w_pos = c->a_pos = c->f_pos = 0;
+    c->last_audio_blocks = c->last_fft_frames = 0;
+    if (c->rx_alloc) {
+        int launches = 0;
+        UA3_CUDA(rx_launch_init_state(c->rx, c->stream, &launches));
+        c->launches += (uint64_t)launches;
+    }
     return UA3_OK;
 }
 
@@ -197,7 +219,23 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
     int launches = 0;
     cudaEvent_t* ev = nullptr;
     if (n_proc && c->prof_used < c->prof_cap) ev = c->prof_ev.data() + (size_t)(c->prof_used++) * (kDdcKernels + 1);
-    if (n_proc) UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, c->sm_count, c->stream, &launches, ev));
+    if (n_proc)
+        UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, (uint32_t)(c->w_pos & c->b.ring_mask), c->sm_count, c->stream,
+                                  &launches, ev));
+    c->w_pos += n_proc / UA3_ADC_PER_FRAME;
+    c->last_audio_blocks = c->last_fft_frames = 0;
+    if (c->rx_on) {
+        const uint32_t nb = (uint32_t)((c->w_pos - c->a_pos) / UA3_AUDIO_BLOCK);
+        const uint32_t nf = (uint32_t)((c->w_pos - c->f_pos) / UA3_FFT_SIZE);
+        UA3_CUDA(rx_launch_audio(c->rx, (uint32_t)(c->a_pos & c->b.ring_mask), nb, c->stream, &launches));
+        UA3_CUDA(rx_launch_fft(c->rx, (uint32_t)(c->f_pos & c->b.ring_mask), nf, c->stream, &launches));
+        c->a_pos += (uint64_t)nb * UA3_AUDIO_BLOCK;
+        c->f_pos += (uint64_t)nf * UA3_FFT_SIZE;
+        c->last_audio_blocks = nb;
+        c->last_fft_frames = nf;
+    } else {
+        c->a_pos = c->f_pos = c->w_pos;
+    }
     c->launches += (uint64_t)launches;
     const uint32_t left = (uint32_t)(total - n_proc);
     if (!in_place && n_proc && left)
@@ -223,19 +261,163 @@ int ua3reo_ddc_read_frames(ua3reo_ctx* c, uint8_t* dst, size_t n_frames) {
     if (!c->pushed) return fail(UA3_E_STATE, "ua3reo_ddc_read_frames: no push yet");
     if (n_frames != c->last_frames) return fail(UA3_E_INVAL, "ua3reo_ddc_read_frames: n_frames != frames of last push");
     UA3_CUDA(cudaSetDevice(c->device));
-    if (n_frames)
-        UA3_CUDA(cudaMemcpy2DAsync(dst, n_frames * UA3_FRAME_BYTES, c->b.frames,
-                                   (size_t)c->b.frame_ch_stride * UA3_FRAME_BYTES, n_frames * UA3_FRAME_BYTES, c->n_ch,
+    if (n_frames) {
+        const uint32_t ring = c->b.frame_ch_stride;
+        const uint32_t first = (uint32_t)((c->w_pos - n_frames) & c->b.ring_mask);
+        const size_t n1 = (first + n_frames <= ring) ? n_frames : (size_t)(ring - first);   // up to the wrap
+        const size_t pitch = (size_t)ring * UA3_FRAME_BYTES;
+        UA3_CUDA(cudaMemcpy2DAsync(dst, n_frames * UA3_FRAME_BYTES, c->b.frames + first, pitch, n1 * UA3_FRAME_BYTES,
+                                   c->n_ch, cudaMemcpyDeviceToHost, c->stream));
+        if (n1 < n_frames)
+            UA3_CUDA(cudaMemcpy2DAsync(dst + n1 * UA3_FRAME_BYTES, n_frames * UA3_FRAME_BYTES, c->b.frames, pitch,
+                                       (n_frames - n1) * UA3_FRAME_BYTES, c->n_ch, cudaMemcpyDeviceToHost, c->stream));
+    }
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_ddc_frames_device(ua3reo_ctx* c, const uint8_t** base, size_t* first_frame, size_t* n_frames,
+                             size_t* ring_frames, size_t* stride) {
+    if (!c || !base) return fail(UA3_E_INVAL, "ua3reo_ddc_frames_device: null argument");
+    *base = reinterpret_cast<const uint8_t*>(c->b.frames);
+    if (first_frame) *first_frame = (size_t)((c->w_pos - c->last_frames) & c->b.ring_mask);
+    if (n_frames) *n_frames = c->last_frames;
+    if (ring_frames) *ring_frames = c->b.frame_ch_stride;
+    if (stride) *stride = (size_t)c->b.frame_ch_stride * UA3_FRAME_BYTES;
+    return UA3_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// STM32 stage
+// ------------------------------------------------------------------------------------------------
+void ua3reo_rx_defaults(ua3reo_rx_settings* s) {
+    if (!s) return;
+    std::memset(s, 0, sizeof *s);                 // settings.c:33-94
+    s->mode = kModeLSB; s->agc = 1; s->agc_speed = 3; s->dnr = 0; s->notch = 0; s->mute = 0; s->volume = 20;
+    s->rf_gain = 50; s->fm_sql_threshold = 1; s->fft_enabled = 1; s->fft_averaging = 4; s->fft_zoom = 1; s->iq_swap = 0;
+    s->filter_width = 2700; s->ssb_hpf_pass = 300; s->notch_fc = 1000;
+}
+
+static int rx_allocate(ua3reo_ctx* c) {
+    if (c->rx_alloc) return UA3_OK;
+    RxBuffers& r = c->rx;
+    r.n_ch = c->n_ch;
+    r.frames = c->b.frames; r.ring_mask = c->b.ring_mask; r.frame_ch_stride = c->b.frame_ch_stride;
+    r.max_audio_blocks = (c->b.max_frames + UA3_AUDIO_BLOCK - 1) / UA3_AUDIO_BLOCK + 1;
+    r.max_fft_frames = c->b.max_frames / UA3_FFT_SIZE + 1;
+    r.audio_ch_stride = r.max_audio_blocks * 2 * UA3_AUDIO_BLOCK;
+    r.spec_ch_stride = r.max_fft_frames * UA3_FFT_BINS;
+    UA3_CUDA(dev_alloc(c, &r.params, (size_t)c->n_ch));
+    UA3_CUDA(dev_alloc(c, &r.state, (size_t)c->n_ch));
+    UA3_CUDA(dev_alloc(c, &r.audio_out, (size_t)c->n_ch * r.audio_ch_stride));
+    UA3_CUDA(dev_alloc(c, &r.spectra, (size_t)c->n_ch * r.spec_ch_stride));
+    UA3_CUDA(dev_alloc(c, &c->rx_flags, (size_t)c->n_ch));
+    std::vector<float> win(kFftSize), tw(2 * kFftSize);
+    rx_build_window(win.data());
+    rx_build_twiddles(tw.data());
+    UA3_CUDA(rx_upload_constants(win.data(), tw.data()));
+    int launches = 0;
+    UA3_CUDA(rx_launch_init_state(r, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    // every channel starts with the firmware's default settings
+    ua3reo_rx_settings d;
+    ua3reo_rx_defaults(&d);
+    c->h_set.assign(c->n_ch, d);
+    c->h_par.assign(c->n_ch, RxParams());
+    for (uint32_t i = 0; i < c->n_ch; ++i) {
+        std::memset(&c->h_par[i], 0, sizeof(RxParams));
+        bool cl, ch;
+        if (!rx_derive(d, c->h_par[i], cl, ch)) return fail(UA3_E_INVAL, "internal: default settings rejected");
+    }
+    UA3_CUDA(cudaMemcpyAsync(r.params, c->h_par.data(), sizeof(RxParams) * c->n_ch, cudaMemcpyHostToDevice, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    c->rx_alloc = true;
+    return UA3_OK;
+}
+
+int ua3reo_rx_enable(ua3reo_ctx* c, int enable) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    UA3_CUDA(cudaSetDevice(c->device));
+    if (enable) {
+        const int rc = rx_allocate(c);
+        if (rc != UA3_OK) return rc;
+        if (!c->rx_on) c->a_pos = c->f_pos = c->w_pos;     // start consuming from "now"
+    }
+    c->rx_on = enable != 0;
+    return UA3_OK;
+}
+
+int ua3reo_rx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_rx_settings* settings) {
+    if (!c || !settings || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_rx_set: range");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const int rc = rx_allocate(c);
+    if (rc != UA3_OK) return rc;
+    std::vector<RxParams> np(c->h_par.begin() + first, c->h_par.begin() + first + n);
+    std::vector<uint8_t> flags(n, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        bool cl = false, chp = false;
+        if (!rx_derive(settings[i], np[i], cl, chp)) {
+            char msg[128];
+            std::snprintf(msg, sizeof msg, "ua3reo_rx_set: channel %u: settings outside the firmware's tables", first + i);
+            return fail(UA3_E_INVAL, msg);
+        }
+        flags[i] = (uint8_t)((cl ? 1 : 0) | (chp ? 2 : 0));
+    }
+    for (uint32_t i = 0; i < n; ++i) { c->h_par[first + i] = np[i]; c->h_set[first + i] = settings[i]; }
+    UA3_CUDA(cudaMemcpyAsync(c->rx.params + first, c->h_par.data() + first, sizeof(RxParams) * n, cudaMemcpyHostToDevice,
+                             c->stream));
+    UA3_CUDA(cudaMemcpyAsync(c->rx_flags, flags.data(), n, cudaMemcpyHostToDevice, c->stream));
+    int launches = 0;
+    UA3_CUDA(rx_launch_clear(c->rx, c->rx_flags, first, n, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_rx_counts(ua3reo_ctx* c, size_t* audio_blocks, size_t* fft_frames) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    if (audio_blocks) *audio_blocks = c->last_audio_blocks;
+    if (fft_frames) *fft_frames = c->last_fft_frames;
+    return UA3_OK;
+}
+
+int ua3reo_rx_read_audio(ua3reo_ctx* c, int32_t* dst, size_t n_blocks) {
+    if (!c || (!dst && n_blocks)) return fail(UA3_E_INVAL, "ua3reo_rx_read_audio: null argument");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_audio: STM32 stage not enabled");
+    if (n_blocks != c->last_audio_blocks) return fail(UA3_E_INVAL, "ua3reo_rx_read_audio: n_blocks != blocks of last push");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t row = n_blocks * 2 * UA3_AUDIO_BLOCK * sizeof(int32_t);
+    if (n_blocks)
+        UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.audio_out, (size_t)c->rx.audio_ch_stride * sizeof(int32_t), row, c->n_ch,
                                    cudaMemcpyDeviceToHost, c->stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
     return UA3_OK;
 }
 
-int ua3reo_ddc_frames_device(ua3reo_ctx* c, const uint8_t** base, size_t* n_frames, size_t* stride) {
-    if (!c || !base) return fail(UA3_E_INVAL, "ua3reo_ddc_frames_device: null argument");
-    *base = reinterpret_cast<const uint8_t*>(c->b.frames);
-    if (n_frames) *n_frames = c->last_frames;
-    if (stride) *stride = (size_t)c->b.frame_ch_stride * UA3_FRAME_BYTES;
+int ua3reo_rx_read_spectra(ua3reo_ctx* c, float* dst, size_t n_frames) {
+    if (!c || (!dst && n_frames)) return fail(UA3_E_INVAL, "ua3reo_rx_read_spectra: null argument");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_spectra: STM32 stage not enabled");
+    if (n_frames != c->last_fft_frames) return fail(UA3_E_INVAL, "ua3reo_rx_read_spectra: n_frames != FFT frames of last push");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t row = n_frames * UA3_FFT_BINS * sizeof(float);
+    if (n_frames)
+        UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.spectra, (size_t)c->rx.spec_ch_stride * sizeof(float), row, c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_rx_read_smeter(ua3reo_ctx* c, float* dst, int reset) {
+    if (!c || !dst) return fail(UA3_E_INVAL, "ua3reo_rx_read_smeter: null argument");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_smeter: STM32 stage not enabled");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t off = offsetof(RxState, smeter_max);
+    UA3_CUDA(cudaMemcpy2DAsync(dst, 2 * sizeof(float), reinterpret_cast<const uint8_t*>(c->rx.state) + off, sizeof(RxState),
+                               2 * sizeof(float), c->n_ch, cudaMemcpyDeviceToHost, c->stream));
+    if (reset)
+        UA3_CUDA(cudaMemset2DAsync(reinterpret_cast<uint8_t*>(c->rx.state) + off, sizeof(RxState), 0, 2 * sizeof(float),
+                                   c->n_ch, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
     return UA3_OK;
 }
 

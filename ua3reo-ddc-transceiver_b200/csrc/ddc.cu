@@ -114,7 +114,8 @@ ddc_comp_kernel(const int16_t* __restrict__ U, uint32_t u_rail_stride, uint32_t 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_t* __restrict__ YQ, uint32_t yq_stride,
-                uint32_t n_frames, uint64_t* __restrict__ frames, uint32_t frame_ch_stride) {
+                uint32_t n_frames, uint64_t* __restrict__ frames, uint32_t frame_ch_stride, uint32_t ring_start,
+                uint32_t ring_mask) {
     __shared__ int16_t s_y[256 + kYIHalo + 1];
     const uint32_t ch = blockIdx.x;
     const uint32_t k0 = blockIdx.y * 256;
@@ -127,7 +128,7 @@ ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_
         const int16_t vi = hilb_fir(s_y, c_hilb_c, (int)threadIdx.x);
         const int16_t yi = s_y[kYIHalo + threadIdx.x];
         const int16_t* q = YQ + (size_t)ch * yq_stride + k;   // q[kYQHalo] = yQ[k], q[0] = yQ[k-130]
-        frames[(size_t)ch * frame_ch_stride + k] = frame_pack(q[kYQHalo], yi, q[0], vi);
+        frames[(size_t)ch * frame_ch_stride + ((ring_start + k) & ring_mask)] = frame_pack(q[kYQHalo], yi, q[0], vi);
     }
 }
 
@@ -192,8 +193,8 @@ cudaError_t ddc_upload_constants() {
     return cudaMemcpyToSymbol(c_hilb_c, UA3_RXHILB_C, sizeof(int16_t) * kHilbTaps);
 }
 
-cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, int sm_count,
-                             cudaStream_t st, int* launches, cudaEvent_t* ev) {
+cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, uint32_t ring_start,
+                             int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev) {
     const uint32_t n_chunks = n_samples / kCicR, n_frames = n_samples / kFrameAdc;
     if (n_chunks == 0) return cudaSuccess;
     const uint32_t n_tiles = ((n_chunks + kFrontWarps - 1) / kFrontWarps) * (b.n_ch_pad >> 5);
@@ -209,7 +210,7 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
                b.YI, b.yi_stride, b.YQ, b.yq_stride);
     if (ev) cudaEventRecord(ev[3], st);
     UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + 255) / 256), 256, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
-               n_frames, b.frames, b.frame_ch_stride);
+               n_frames, b.frames, b.frame_ch_stride, ring_start, b.ring_mask);
     if (ev) cudaEventRecord(ev[4], st);
     UA3_LAUNCH(ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.U, b.u_rail_stride, b.YI, b.yi_stride,
                b.YQ, b.yq_stride, n_chunks, n_frames, b.phase, b.fcw, b.n_ch_pad);

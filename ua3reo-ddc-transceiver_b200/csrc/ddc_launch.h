@@ -19,8 +19,9 @@ struct DdcBuffers {
     uint32_t yi_stride = 0;
     int16_t* YQ = nullptr;         // [n_ch_pad][kYQHalo + max_frames]
     uint32_t yq_stride = 0;
-    uint64_t* frames = nullptr;    // [n_ch][max_frames] 8-byte frames
-    uint32_t frame_ch_stride = 0;  // frames per channel
+    uint64_t* frames = nullptr;    // [n_ch][ring] 8-byte frames, a ring per channel (ring is a power of two)
+    uint32_t frame_ch_stride = 0;  // ring size in frames
+    uint32_t ring_mask = 0;
 };
 
 void build_cic_weights(uint64_t G[25]);
@@ -28,8 +29,9 @@ void build_nco_table(uint32_t tab[2048]);
 cudaError_t ddc_upload_constants();
 constexpr int kDdcKernels = 5;   // front, cic, comp, hilb, rotate
 // ev: optional array of kDdcKernels + 1 events recorded before/after each kernel (profiling mode)
-cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, int sm_count,
-                             cudaStream_t st, int* launches, cudaEvent_t* ev);
+// ring_start: ring index that receives the block's first frame
+cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, uint32_t ring_start,
+                             int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev);
 cudaError_t measure_int32_peak(int sm_count, cudaStream_t st, double* ops_per_s);
 
 }  // namespace ua3

@@ -1,0 +1,28 @@
+// rx_launch.h - host-visible launch interface of rx.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "rx_types.h"
+
+namespace ua3 {
+
+struct RxBuffers {
+    uint32_t n_ch = 0;
+    const uint64_t* frames = nullptr;   // the DDC's frame ring: [n_ch][ring] 8-byte frames
+    uint32_t ring_mask = 0, frame_ch_stride = 0;
+    RxParams* params = nullptr;         // [n_ch]
+    RxState* state = nullptr;           // [n_ch]
+    int32_t* audio_out = nullptr;       // [n_ch][max_audio_blocks][384]
+    uint32_t audio_ch_stride = 0, max_audio_blocks = 0;
+    float* spectra = nullptr;           // [n_ch][max_fft_frames][256]
+    uint32_t spec_ch_stride = 0, max_fft_frames = 0;
+};
+
+cudaError_t rx_upload_constants(const float* window, const float* twiddle);
+cudaError_t rx_launch_audio(const RxBuffers& b, uint32_t start, uint32_t n_blocks, cudaStream_t st, int* launches);
+cudaError_t rx_launch_fft(const RxBuffers& b, uint32_t start, uint32_t n_frames, cudaStream_t st, int* launches);
+cudaError_t rx_launch_clear(const RxBuffers& b, const uint8_t* flags_dev, uint32_t first, uint32_t n, cudaStream_t st,
+                            int* launches);
+cudaError_t rx_launch_init_state(const RxBuffers& b, cudaStream_t st, int* launches);
+
+}  // namespace ua3
