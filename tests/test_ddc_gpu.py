@@ -98,8 +98,8 @@ def test_device_resident_input_and_frames_view(pkg, oracle):
     d = torch.from_numpy(adc).cuda()
     assert rx.push(d) == 64
     got = rx.read_frames()
-    base, nf, stride = rx.frames_device()
-    assert nf == 64 and stride == 64 * 8 and base
+    base, first, nf, ring, stride = rx.frames_device()
+    assert nf == 64 and first == 0 and ring >= 64 + 1024 and ring & (ring - 1) == 0 and stride == ring * 8 and base
     rx.close()
     assert np.array_equal(got, oracle.golden_frames(adc, fcw))
 

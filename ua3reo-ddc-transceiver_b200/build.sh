@@ -11,4 +11,7 @@ SRCS=("$HERE"/csrc/*.cu)
     -Xcompiler -fPIC,-O2,-Wall,-Wno-unknown-pragmas -Xptxas -v --shared -o "$OUT/libua3reo_b200.so" "${SRCS[@]}" 2> "$OUT/ptxas.log" \
     || { cat "$OUT/ptxas.log"; exit 1; }
 grep -E "error|warning" "$OUT/ptxas.log" || true
-echo "built $OUT/libua3reo_b200.so"
+# the C host driver (the reference's host language) on top of the C ABI
+gcc -O2 -std=gnu11 -Wall -I"$HERE/../include" "$HERE/host/ua3reo_rx_host.c" -o "$OUT/ua3reo_rx_host" \
+    -L"$OUT" -lua3reo_b200 -lm -Wl,-rpath,'$ORIGIN'
+echo "built $OUT/libua3reo_b200.so and $OUT/ua3reo_rx_host"
