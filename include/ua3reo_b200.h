@@ -147,6 +147,22 @@ int ua3reo_rx_read_spectra(ua3reo_ctx *ctx, float *dst_host, size_t n_frames);
  * reset != 0 clears them afterwards, as the 1 s housekeeping tick does (stm32f4xx_it.c:398-409). */
 int ua3reo_rx_read_smeter(ua3reo_ctx *ctx, float *dst_host, int reset);
 
+/* ---------------------------------------------------------------------------------------------
+ * Transmit DUC (mirror of the DDC): tx_ciccomp (x2) -> tx_cic (x512) -> tx_mixer (I*sin14, Q*cos14) ->
+ * tx_summator -> DAC_corrector  (FPGA/tx_ciccomp.vhd, tx_cic.vhd, tx_mixer.v:64-71, tx_summator.v:74-80,
+ * DAC_corrector.v:15-21).  Every channel uses its DDC tuning word (the FPGA has one NCO for RX and TX).
+ * ------------------------------------------------------------------------------------------- */
+/* Allocates the DUC for pushes of up to max_tx_samples 48 kHz I/Q samples (each makes 1024 DAC words). */
+int ua3reo_duc_enable(ua3reo_ctx *ctx, uint32_t max_tx_samples);
+/* The TX I/Q words the MCU sends on command 3 (stm32_interface.v:206-227 <- FPGA_fpgadata_sendiq, fpga.c:403-436):
+ * iq_host is [n_channels][n][2] int16 (I, Q).  Produces n*1024 DAC words per channel. */
+int ua3reo_duc_push(ua3reo_ctx *ctx, const int16_t *iq_host, size_t n);
+/* The 14-bit offset-binary words DAC_corrector.v:15-21 drives onto the DAC pins: dst [n_channels][n*1024] uint16. */
+int ua3reo_duc_read_dac(ua3reo_ctx *ctx, uint16_t *dst_host, size_t n);
+int ua3reo_duc_dac_device(ua3reo_ctx *ctx, const uint16_t **base, size_t *n_words, size_t *channel_stride_words);
+/* tx_summator overflow count per channel since reset (the DAC_OTR flag, stm32_interface.v:172-205): dst [n_channels]. */
+int ua3reo_duc_read_otr(ua3reo_ctx *ctx, uint32_t *dst_host);
+
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline):
  * after ua3reo_profile_begin(ctx, max_blocks) each processed ADC block records an event before and
  * after every kernel; ua3reo_profile_end() waits for the stream and sums the elapsed times per

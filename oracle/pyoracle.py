@@ -42,6 +42,9 @@ def lib():
         L.ua3g_bank_push.restype = ctypes.c_double
         L.ua3g_bank_push.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                      ctypes.c_int]
+        L.ua3g_duc_init.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+        L.ua3g_duc_push.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                    ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -151,3 +154,20 @@ def run_fw_rx(frames, settings, workdir=None):
             "waterfall": np.ascontiguousarray(raw[:, 1024:1536]).view(np.uint16).reshape(-1, 256),
             "fft_max": np.ascontiguousarray(raw[:, 1536:1540]).view(np.float32).reshape(-1),
         }
+
+
+class GoldenDUC:
+    """One channel of the register-transfer golden transmit DUC (duc_golden.c)."""
+
+    def __init__(self, fcw):
+        self._st = ctypes.create_string_buffer(DDC_STATE_BYTES)
+        lib().ua3g_duc_init(self._st, int(fcw) & 0x3FFFFF)
+
+    def push(self, tx_i, tx_q):
+        tx_i = np.ascontiguousarray(tx_i, dtype=np.int16)
+        tx_q = np.ascontiguousarray(tx_q, dtype=np.int16)
+        n = tx_i.size
+        dac = np.zeros(n * 1024, np.uint16)
+        otr = np.zeros(n * 1024, np.uint8)
+        lib().ua3g_duc_push(self._st, tx_i.ctypes.data, tx_q.ctypes.data, n, dac.ctypes.data, otr.ctypes.data)
+        return dac, otr

@@ -78,6 +78,11 @@ def _bind(lib):
         "ua3reo_rx_read_audio": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_spectra": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_smeter": (c.c_int, [vp, vp, c.c_int]),
+        "ua3reo_duc_enable": (c.c_int, [vp, u32]),
+        "ua3reo_duc_push": (c.c_int, [vp, vp, sz]),
+        "ua3reo_duc_read_dac": (c.c_int, [vp, vp, sz]),
+        "ua3reo_duc_dac_device": (c.c_int, [vp, c.POINTER(vp), c.POINTER(sz), c.POINTER(sz)]),
+        "ua3reo_duc_read_otr": (c.c_int, [vp, vp]),
         "ua3reo_sync": (c.c_int, [vp]),
         "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_launch_count": (c.c_uint64, [vp]),
@@ -241,6 +246,29 @@ class Receiver:
     def read_smeter(self, reset=False):
         out = np.empty((self.n_channels, 2), np.float32)
         self._chk(self.lib.ua3reo_rx_read_smeter(self._h, out.ctypes.data, 1 if reset else 0))
+        return out
+
+    # ---- transmit DUC ----
+    def duc_enable(self, max_tx_samples=64):
+        self._chk(self.lib.ua3reo_duc_enable(self._h, int(max_tx_samples)))
+
+    def duc_push(self, iq):
+        """iq: int16 [n_channels, n, 2] (I, Q) 48 kHz TX samples; returns n."""
+        a = np.ascontiguousarray(iq, dtype=np.int16)
+        assert a.ndim == 3 and a.shape[0] == self.n_channels and a.shape[2] == 2
+        self._keep_tx = a
+        self._chk(self.lib.ua3reo_duc_push(self._h, a.ctypes.data, a.shape[1]))
+        self._last_tx = a.shape[1]
+        return a.shape[1]
+
+    def duc_read_dac(self):
+        out = np.empty((self.n_channels, self._last_tx * 1024), np.uint16)
+        self._chk(self.lib.ua3reo_duc_read_dac(self._h, out.ctypes.data, self._last_tx))
+        return out
+
+    def duc_read_otr(self):
+        out = np.empty(self.n_channels, np.uint32)
+        self._chk(self.lib.ua3reo_duc_read_otr(self._h, out.ctypes.data))
         return out
 
     def sync(self):

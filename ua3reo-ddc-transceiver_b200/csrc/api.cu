@@ -2,6 +2,7 @@
 #include "../../include/ua3reo_b200.h"
 #include "ddc_launch.h"
 #include "rx_launch.h"
+#include "duc_launch.h"
 #include "ua3_common.cuh"
 #include <cmath>
 #include <cstdio>
@@ -51,6 +52,10 @@ struct ua3reo_ctx {
     std::vector<RxParams> h_par;
     uint8_t* rx_flags = nullptr;        // device scratch for rx_set's state-clear flags
     size_t last_audio_blocks = 0, last_fft_frames = 0;
+    // transmit DUC
+    bool duc_alloc = false;
+    DucBuffers duc;
+    size_t last_tx = 0;
 };
 
 template <class T>
@@ -169,6 +174,8 @@ int ua3reo_reset(ua3reo_ctx* c) {
         UA3_CUDA(rx_launch_init_state(c->rx, c->stream, &launches));
         c->launches += (uint64_t)launches;
     }
+    if (c->duc_alloc) UA3_CUDA(cudaMemsetAsync(c->duc.state, 0, sizeof(DucState) * (size_t)c->n_ch, c->stream));
+    c->last_tx = 0;
     return UA3_OK;
 }
 
@@ -431,6 +438,71 @@ int ua3reo_sync(ua3reo_ctx* c) {
 int ua3reo_stream(ua3reo_ctx* c, void** stream) {
     if (!c || !stream) return fail(UA3_E_INVAL, "null argument");
     *stream = (void*)c->stream;
+    return UA3_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// transmit DUC
+// ------------------------------------------------------------------------------------------------
+int ua3reo_duc_enable(ua3reo_ctx* c, uint32_t max_tx_samples) {
+    if (!c || max_tx_samples == 0) return fail(UA3_E_INVAL, "ua3reo_duc_enable: bad arguments");
+    if (c->duc_alloc) return (max_tx_samples <= c->duc.max_in) ? UA3_OK : fail(UA3_E_STATE, "ua3reo_duc_enable: already enabled with a smaller block");
+    UA3_CUDA(cudaSetDevice(c->device));
+    DucBuffers& d = c->duc;
+    d.n_ch = c->n_ch; d.max_in = max_tx_samples; d.nco_tab = c->b.nco_tab; d.fcw = c->b.fcw;
+    UA3_CUDA(dev_alloc(c, &d.state, (size_t)c->n_ch));
+    UA3_CUDA(dev_alloc(c, &d.iq_in, (size_t)c->n_ch * max_tx_samples * 2));
+    UA3_CUDA(dev_alloc(c, &d.dac, (size_t)c->n_ch * max_tx_samples * 1024));
+    UA3_CUDA(duc_upload_constants());
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    c->duc_alloc = true;
+    return UA3_OK;
+}
+
+int ua3reo_duc_push(ua3reo_ctx* c, const int16_t* iq_host, size_t n) {
+    if (!c || (!iq_host && n)) return fail(UA3_E_INVAL, "ua3reo_duc_push: null argument");
+    if (!c->duc_alloc) return fail(UA3_E_STATE, "ua3reo_duc_push: call ua3reo_duc_enable first");
+    if (n > c->duc.max_in) return fail(UA3_E_TOOBIG, "ua3reo_duc_push: more samples than max_tx_samples");
+    UA3_CUDA(cudaSetDevice(c->device));
+    if (n)
+        UA3_CUDA(cudaMemcpy2DAsync(c->duc.iq_in, (size_t)c->duc.max_in * 2 * sizeof(int16_t), iq_host, n * 2 * sizeof(int16_t),
+                                   n * 2 * sizeof(int16_t), c->n_ch, cudaMemcpyHostToDevice, c->stream));
+    int launches = 0;
+    UA3_CUDA(duc_launch(c->duc, (uint32_t)n, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    c->last_tx = n;
+    return UA3_OK;
+}
+
+int ua3reo_duc_read_dac(ua3reo_ctx* c, uint16_t* dst, size_t n) {
+    if (!c || (!dst && n)) return fail(UA3_E_INVAL, "ua3reo_duc_read_dac: null argument");
+    if (!c->duc_alloc) return fail(UA3_E_STATE, "ua3reo_duc_read_dac: DUC not enabled");
+    if (n != c->last_tx) return fail(UA3_E_INVAL, "ua3reo_duc_read_dac: n != samples of last push");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t row = n * 1024 * sizeof(uint16_t);
+    if (n)
+        UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->duc.dac, (size_t)c->duc.max_in * 1024 * sizeof(uint16_t), row, c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_duc_dac_device(ua3reo_ctx* c, const uint16_t** base, size_t* n_words, size_t* channel_stride_words) {
+    if (!c || !base) return fail(UA3_E_INVAL, "ua3reo_duc_dac_device: null argument");
+    if (!c->duc_alloc) return fail(UA3_E_STATE, "ua3reo_duc_dac_device: DUC not enabled");
+    *base = c->duc.dac;
+    if (n_words) *n_words = c->last_tx * 1024;
+    if (channel_stride_words) *channel_stride_words = (size_t)c->duc.max_in * 1024;
+    return UA3_OK;
+}
+
+int ua3reo_duc_read_otr(ua3reo_ctx* c, uint32_t* dst) {
+    if (!c || !dst) return fail(UA3_E_INVAL, "ua3reo_duc_read_otr: null argument");
+    if (!c->duc_alloc) return fail(UA3_E_STATE, "ua3reo_duc_read_otr: DUC not enabled");
+    UA3_CUDA(cudaSetDevice(c->device));
+    UA3_CUDA(cudaMemcpy2DAsync(dst, sizeof(uint32_t), reinterpret_cast<const uint8_t*>(c->duc.state) + offsetof(DucState, otr),
+                               sizeof(DucState), sizeof(uint32_t), c->n_ch, cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
     return UA3_OK;
 }
 
