@@ -12,6 +12,7 @@ import os
 
 import numpy as np
 
+from . import sharding  # noqa: F401
 from . import synth  # noqa: F401  (synthetic ADC stream / tuning words of SURVEY.md 8d)
 from .synth import random_fcw, synth_adc  # noqa: F401
 
