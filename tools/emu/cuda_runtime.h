@@ -106,6 +106,8 @@ static inline int32_t __shfl_xor_sync(unsigned, int32_t v, int m) {
     float f; memcpy(&f, &v, 4); f = ua3_emu_shfl(f, (int)(threadIdx.x & 31) ^ m); memcpy(&v, &f, 4); return v;
 }
 static inline void __syncwarp() { ua3_emu_barrier->arrive_and_wait(); }
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 static inline cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t w, size_t h, cudaStream_t) {
     for (size_t i = 0; i < h; ++i) memset((char*)p + i * pitch, v, w);
     return 0;

@@ -6,6 +6,7 @@
 #include "ua3_common.cuh"
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -133,6 +134,15 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     b.ring_mask = ring - 1u;
 #define UA3_TRY(call) do { e = (call); if (e != cudaSuccess) { ctx_free(c); return fail(UA3_E_CUDA, #call, e); } } while (0)
     UA3_TRY(dev_alloc(c, &b.nco_tab, 2048));
+    UA3_TRY(dev_alloc(c, &b.big_tab, (size_t)kNcoBigTabWords));
+    UA3_TRY(ddc_prepare_kernels());
+    {
+        std::vector<uint32_t> bt((size_t)kNcoBigTabWords);
+        build_nco_big_table(bt.data());
+        UA3_TRY(cudaMemcpyAsync(b.big_tab, bt.data(), bt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        UA3_TRY(cudaStreamSynchronize(c->stream));
+    }
+    if (const char* v = std::getenv("UA3REO_FRONT_VARIANT")) b.front_variant = std::atoi(v);   // 1 small table, 2 big table
     UA3_TRY(dev_alloc(c, &b.fcw, c->n_ch_pad));
     UA3_TRY(dev_alloc(c, &b.phase, c->n_ch_pad));
     UA3_TRY(dev_alloc(c, &b.L, (size_t)c->n_ch_pad * b.l_ch_stride));

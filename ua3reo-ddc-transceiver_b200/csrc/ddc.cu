@@ -77,6 +77,126 @@ ddc_front_kernel(const int16_t* __restrict__ adc, uint32_t n_chunks, const uint3
 }
 
 // ------------------------------------------------------------------------------------------------
+// front, big-table variant: one persistent CTA per SM (208 KB NCO table in shared memory, loaded once per
+// launch with TMA bulk copies), 32 warps = 8 channel tiles x 4 chunks; the next tile's raw ADC samples are
+// fetched by a TMA bulk copy while the current tile computes.
+// ------------------------------------------------------------------------------------------------
+// big table + pre-shifted int32 tile + raw int16 tile + 2 mbarriers
+constexpr size_t kBtSmemBytes = (size_t)kBigTabWords * 4 + (size_t)kBtTG * kCicR * 6 + 64;
+
+#if !defined(UA3_HOST_EMU)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}"
+        ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+#endif
+
+__global__ void __launch_bounds__(kBtThreads, 1)
+ddc_front_bt_kernel(const int16_t* __restrict__ adc, uint32_t n_chunks, const uint32_t* __restrict__ big_tab,
+                    const uint32_t* __restrict__ fcw, const uint32_t* __restrict__ phase, uint32_t n_ch_pad,
+                    uint64_t* __restrict__ L, uint32_t l_ch_stride) {
+#if defined(UA3_HOST_EMU)
+    static uint8_t s_dyn[kBtSmemBytes] __attribute__((aligned(128)));
+#else
+    extern __shared__ __align__(128) uint8_t s_dyn[];
+#endif
+    uint32_t* s_bt = reinterpret_cast<uint32_t*>(s_dyn);                                    // 53248 words
+    I4* s_adc = reinterpret_cast<I4*>(s_dyn + (size_t)kBigTabWords * 4);                    // kBtTG * 512 int32
+    int16_t* s_raw = reinterpret_cast<int16_t*>(s_dyn + (size_t)kBigTabWords * 4 + (size_t)kBtTG * kCicR * 4);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dyn + (size_t)kBigTabWords * 4 + (size_t)kBtTG * kCicR * 6);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t n_ctiles = n_ch_pad >> 5;
+    const uint32_t n_cg = (n_ctiles + kBtCG - 1) / kBtCG, n_tg = (n_chunks + kBtTG - 1) / kBtTG;
+    const uint32_t n_tiles = n_cg * n_tg;
+
+#if !defined(UA3_HOST_EMU)
+    // bar[0]: table; bar[1]: raw ADC tile
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue_raw = [&](uint32_t tile) {       // thread 0: fetch the tile's raw int16 samples
+        const uint32_t tg = tile / n_cg;
+        const uint32_t chunk0 = tg * kBtTG;
+        const uint32_t bytes = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR * 2u;
+        mbar_expect_tx(&s_bar[1], bytes);
+        tma_bulk_g2s(s_raw, adc + (size_t)chunk0 * kCicR, bytes, &s_bar[1]);
+    };
+    if (tid == 0) {
+        mbar_expect_tx(&s_bar[0], (uint32_t)kBigTabWords * 4u);
+        for (uint32_t off = 0; off < (uint32_t)kBigTabWords * 4u; off += 16384u)
+            tma_bulk_g2s(s_dyn + off, reinterpret_cast<const uint8_t*>(big_tab) + off, 16384u, &s_bar[0]);
+        if (blockIdx.x < n_tiles) issue_raw(blockIdx.x);
+    }
+    mbar_wait(&s_bar[0], 0);
+#else
+    for (int i = tid; i < kBigTabWords; i += kBtThreads) s_bt[i] = big_tab[i];
+    __syncthreads();
+#endif
+
+    uint32_t raw_parity = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t cg = tile % n_cg, tg = tile / n_cg;     // channel group fastest: neighbours share the ADC tile in L2
+        const uint32_t chunk0 = tg * kBtTG;
+        const uint32_t n_valid = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR;
+        __syncthreads();                                       // previous tile's compute is done with s_adc
+#if !defined(UA3_HOST_EMU)
+        mbar_wait(&s_bar[1], raw_parity);
+        raw_parity ^= 1u;
+#else
+        for (uint32_t v = tid; v < n_valid; v += kBtThreads) s_raw[v] = adc[(size_t)chunk0 * kCicR + v];
+        __syncthreads();
+#endif
+        {   // int16 -> int32 << 9, 8 samples per thread step
+            const uint4* src = reinterpret_cast<const uint4*>(s_raw);
+            for (uint32_t v = tid; v < n_valid / 8; v += kBtThreads) {
+                const uint4 q = src[v];
+                const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+                I4 lo, hi;
+                lo.x = (int32_t)(int16_t)(ws[0] & 0xFFFFu) << 9; lo.y = ((int32_t)ws[0] >> 16) << 9;
+                lo.z = (int32_t)(int16_t)(ws[1] & 0xFFFFu) << 9; lo.w = ((int32_t)ws[1] >> 16) << 9;
+                hi.x = (int32_t)(int16_t)(ws[2] & 0xFFFFu) << 9; hi.y = ((int32_t)ws[2] >> 16) << 9;
+                hi.z = (int32_t)(int16_t)(ws[3] & 0xFFFFu) << 9; hi.w = ((int32_t)ws[3] >> 16) << 9;
+                s_adc[2 * v] = lo;
+                s_adc[2 * v + 1] = hi;
+            }
+        }
+        __syncthreads();                                       // s_adc complete, s_raw free again
+#if !defined(UA3_HOST_EMU)
+        if (tid == 0 && tile + gridDim.x < n_tiles) issue_raw(tile + gridDim.x);   // overlaps with the compute below
+#endif
+        const uint32_t wc = (uint32_t)warp % kBtCG, wt = (uint32_t)warp / kBtCG;
+        const uint32_t ctile = cg * kBtCG + wc, chunk = chunk0 + wt;
+        if (ctile < n_ctiles && chunk < n_chunks) {
+            const uint32_t ch = (ctile << 5) + lane;
+            const uint32_t F = fcw[ch] << 10;
+            const uint32_t P0 = (phase[ch] << 10) + F * (chunk * (uint32_t)kCicR);
+            uint64_t out[10];
+            front_chunk_bt(s_bt, s_adc + wt * (kCicR / 4), P0, F, out);
+            uint64_t* dst = L + (size_t)ch * l_ch_stride + (size_t)(kLHalo + chunk) * kLRec;
+            ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) d2[k] = make_ulonglong2(out[2 * k], out[2 * k + 1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // cic: one thread per (channel, chunk, rail)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -179,6 +299,20 @@ void build_cic_weights(uint64_t G[25]) {
         }
 }
 
+void build_nco_big_table(uint32_t* tab /* kBigTabWords */) {
+    for (int k = 0; k < 2048; ++k)
+        for (int sf = 0; sf < kSfLevels; ++sf)
+            tab[k * kSfLevels + sf] = nco_bigtab_entry(UA3_NCO_SIN_C[k], UA3_NCO_COS_C[k], sf);
+}
+
+cudaError_t ddc_prepare_kernels() {
+#if !defined(UA3_HOST_EMU)
+    return cudaFuncSetAttribute(ddc_front_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmemBytes);
+#else
+    return cudaSuccess;
+#endif
+}
+
 void build_nco_table(uint32_t tab[2048]) {
     for (int k = 0; k < 2048; ++k) tab[k] = nco_pack(UA3_NCO_SIN_C[k], UA3_NCO_COS_C[k]);
 }
@@ -197,11 +331,20 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
                              int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev) {
     const uint32_t n_chunks = n_samples / kCicR, n_frames = n_samples / kFrameAdc;
     if (n_chunks == 0) return cudaSuccess;
-    const uint32_t n_tiles = ((n_chunks + kFrontWarps - 1) / kFrontWarps) * (b.n_ch_pad >> 5);
-    const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count * 3);
     if (ev) cudaEventRecord(ev[0], st);
-    UA3_LAUNCH(ddc_front_kernel, grid, kFrontThreads, 0, st, adc_dev, n_chunks, b.nco_tab, b.fcw, b.phase, b.n_ch_pad,
-               b.L, b.l_ch_stride);
+    // big-table kernel when a CTA tile (256 channels x 4 chunks) can be filled; the 8 KB-table kernel otherwise
+    const bool big = b.front_variant != 1 && b.big_tab && (b.front_variant == 2 || ((b.n_ch_pad >> 5) >= (uint32_t)kBtCG && n_chunks >= (uint32_t)kBtTG));
+    if (big) {
+        const uint32_t n_tiles = (((b.n_ch_pad >> 5) + kBtCG - 1) / kBtCG) * ((n_chunks + kBtTG - 1) / kBtTG);
+        const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count);
+        UA3_LAUNCH(ddc_front_bt_kernel, grid, kBtThreads, kBtSmemBytes, st, adc_dev, n_chunks, b.big_tab, b.fcw, b.phase,
+                   b.n_ch_pad, b.L, b.l_ch_stride);
+    } else {
+        const uint32_t n_tiles = ((n_chunks + kFrontWarps - 1) / kFrontWarps) * (b.n_ch_pad >> 5);
+        const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count * 3);
+        UA3_LAUNCH(ddc_front_kernel, grid, kFrontThreads, 0, st, adc_dev, n_chunks, b.nco_tab, b.fcw, b.phase, b.n_ch_pad,
+                   b.L, b.l_ch_stride);
+    }
     if (ev) cudaEventRecord(ev[1], st);
     UA3_LAUNCH(ddc_cic_kernel, dim3(b.n_ch * 2, (n_chunks + 255) / 256), 256, 0, st, b.L, b.l_ch_stride, n_chunks,
                b.n_ch, b.U, b.u_rail_stride);

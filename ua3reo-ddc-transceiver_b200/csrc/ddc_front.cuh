@@ -84,4 +84,59 @@ UA3_HD void front_chunk(const uint32_t* __restrict__ tab, const I4* __restrict__
     for (int k = 0; k < 5; ++k) { out[k] = SI[k]; out[5 + k] = SQ[k]; }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// "Big table" variant: the fine-sine ROM takes only 26 distinct values (0..25), so the whole NCO output
+// stage - angle-sum products, round-half-up to 14 bits and nco_shift's [13:2] - is a function of
+// (coarse address k, sf) with 2048 x 26 = 53248 entries.  One packed word (sin12 << 16 | cos12 & 0xFFFF)
+// per entry is 208 KB: it fits the 227 KB of shared memory of one persistent CTA per SM and removes the
+// four angle-sum IMADs, the rounding add and the two shifts from every channel-sample.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSfLevels = 26;
+constexpr int kBigTabWords = 2048 * kSfLevels;
+
+UA3_HD uint32_t nco_bigtab_entry(int32_t sc, int32_t cc, int32_t sf) {
+    const int32_t s12 = (sc * kCosF + sf * cc + 4096) >> 15;
+    const int32_t c12 = (cc * kCosF - sc * sf + 4096) >> 15;
+    return ((uint32_t)s12 << 16) | ((uint32_t)c12 & 0xFFFFu);
+}
+
+UA3_HD void nco_mix_bt(const uint32_t* __restrict__ bt, uint32_t P, int32_t a9, int32_t& xi, int32_t& xq) {
+    const uint32_t k = P >> 21;
+    const int32_t j = (int32_t)((P >> 10) & 0x7FFu);
+    const uint32_t sf = (uint32_t)((j * kSinFMul + (1 << 18)) >> 19);
+    const uint32_t w = bt[k * kSfLevels + sf];
+    const int32_t s12 = (int32_t)w >> 16;
+    const int32_t c12 = (int32_t)(int16_t)(w & 0xFFFFu);
+    xi = (int32_t)((uint32_t)a9 * (uint32_t)s12) >> 17;
+    xq = (int32_t)((uint32_t)a9 * (uint32_t)c12) >> 17;
+}
+
+UA3_HD void front_chunk_bt(const uint32_t* __restrict__ bt, const I4* __restrict__ adc9, uint32_t P0, uint32_t F,
+                           uint64_t out[10]) {
+    uint64_t SI[5] = {0, 0, 0, 0, 0}, SQ[5] = {0, 0, 0, 0, 0};
+    uint32_t P = P0;
+#pragma unroll 1
+    for (int sb = 0; sb < kCicR / kSub; ++sb) {
+        int32_t i1 = 0, i2 = 0, i3 = 0, i4 = 0, i5 = 0;
+        int32_t q1 = 0, q2 = 0, q3 = 0, q4 = 0, q5 = 0;
+#pragma unroll
+        for (int v = 0; v < kSub / 4; ++v) {
+            const I4 a = adc9[sb * (kSub / 4) + v];
+            const int32_t as[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                int32_t xi, xq;
+                nco_mix_bt(bt, P, as[t], xi, xq);
+                P += F;
+                i5 += i4; i4 += i3; i3 += i2; i2 += i1; i1 += xi;
+                q5 += q4; q4 += q3; q3 += q2; q2 += q1; q1 += xq;
+            }
+        }
+        fold16(SI, i1, i2, i3, i4, i5);
+        fold16(SQ, q1, q2, q3, q4, q5);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { out[k] = SI[k]; out[5 + k] = SQ[k]; }
+}
+
 }  // namespace ua3

@@ -9,6 +9,8 @@ struct DdcBuffers {
     uint32_t n_ch = 0, n_ch_pad = 0;
     uint32_t max_chunks = 0, max_frames = 0;
     uint32_t* nco_tab = nullptr;   // [2048] packed coarse ROM
+    uint32_t* big_tab = nullptr;   // [2048 * 26] packed (sin12, cos12) by (coarse address, fine-sine value)
+    int front_variant = 0;         // 0 auto, 1 force the 8 KB-table kernel, 2 force the big-table kernel
     uint32_t* fcw = nullptr;       // [n_ch_pad] 22-bit tuning words
     uint32_t* phase = nullptr;     // [n_ch_pad] 22-bit phase at the start of the next block
     uint64_t* L = nullptr;         // [n_ch_pad][kLHalo + max_chunks][2][5]
@@ -26,6 +28,9 @@ struct DdcBuffers {
 
 void build_cic_weights(uint64_t G[25]);
 void build_nco_table(uint32_t tab[2048]);
+void build_nco_big_table(uint32_t* tab);
+cudaError_t ddc_prepare_kernels();
+constexpr int kNcoBigTabWords = 2048 * 26;
 cudaError_t ddc_upload_constants();
 constexpr int kDdcKernels = 5;   // front, cic, comp, hilb, rotate
 // ev: optional array of kDdcKernels + 1 events recorded before/after each kernel (profiling mode)

@@ -42,6 +42,11 @@ constexpr int kYQHalo = 130;        // data_delay depth
 constexpr int kFrontWarps = 8;                     // warps per CTA, one 512-sample chunk each
 constexpr int kFrontThreads = kFrontWarps * 32;
 constexpr int kSub = 16;                           // 32-bit sub-block length (see ddc_front.cuh)
+// big-table front kernel: one persistent CTA per SM, 32 warps = 8 channel tiles x 4 chunks per tile
+constexpr int kBtCG = 8;                           // channel tiles (of 32 channels) per CTA tile
+constexpr int kBtTG = 4;                           // 512-sample chunks per CTA tile
+constexpr int kBtWarps = kBtCG * kBtTG;
+constexpr int kBtThreads = kBtWarps * 32;
 
 struct alignas(16) I4 { int32_t x, y, z, w; };
 
