@@ -75,7 +75,9 @@ int ua3reo_set_frequency(ua3reo_ctx *ctx, uint32_t channel, uint32_t freq_hz);
  * produced per channel by this call.  n + carried remainder must not exceed max_block_samples.
  *   ua3reo_ddc_push        : adc in host memory (copied to the device inside the call)
  *   ua3reo_ddc_push_device : adc already in device memory of the context's device
- * Both are asynchronous with respect to the host; ua3reo_sync() or a read waits. */
+ * Both are asynchronous with respect to the host; ua3reo_sync() or a read waits.  A host buffer in pinned
+ * memory must stay unchanged until then (whole-block host pushes are copied on a separate stream so that
+ * the copy of block k+1 overlaps the kernels of block k). */
 int ua3reo_ddc_push(ua3reo_ctx *ctx, const int16_t *adc_host, size_t n, size_t *frames_out);
 int ua3reo_ddc_push_device(ua3reo_ctx *ctx, const int16_t *adc_dev, size_t n, size_t *frames_out);
 
@@ -84,6 +86,11 @@ int ua3reo_ddc_push_device(ua3reo_ctx *ctx, const int16_t *adc_dev, size_t n, si
  *   SPEC_Q hi, lo, SPEC_I hi, lo, VOICE_Q hi, lo, VOICE_I hi, lo.
  * dst is [n_channels][n_frames][8] bytes; n_frames must equal the last push's frames_out. */
 int ua3reo_ddc_read_frames(ua3reo_ctx *ctx, uint8_t *dst_host, size_t n_frames);
+/* Same copy, enqueued on a second stream that waits for the last push only: returns immediately so that
+ * the caller can issue the NEXT push while the frames travel to the host.  dst (pinned memory for a true
+ * overlap) is valid after ua3reo_sync().  At most two reads may be outstanding; the push after next waits
+ * for the older one because it overwrites those ring slots. */
+int ua3reo_ddc_read_frames_async(ua3reo_ctx *ctx, uint8_t *dst_host, size_t n_frames);
 /* Device view of the same data.  Each channel owns a ring of *ring_frames 8-byte frames (a power of two),
  * *channel_stride_bytes apart; the last push wrote *n_frames frames starting at ring index *first_frame. */
 int ua3reo_ddc_frames_device(ua3reo_ctx *ctx, const uint8_t **base, size_t *first_frame, size_t *n_frames,

@@ -150,3 +150,22 @@ def test_front_kernel_variants_agree(pkg, oracle, monkeypatch):
     assert np.array_equal(outs["1"], outs["2"])
     pick = [0, 1, 31, 32, 255, 256, 299]
     assert np.array_equal(outs["2"][pick], oracle.golden_frames(adc, fcw[pick])[:, :outs["2"].shape[1]])
+
+
+def test_async_frame_reads_overlap_pushes(pkg, oracle):
+    """ua3reo_ddc_read_frames_async: results of push k are copied while push k+1 runs; pinned host buffers."""
+    import torch
+    n_ch, block, n_blocks = 64, 1 << 15, 7
+    adc = oracle.synth_adc(block * n_blocks, seed=123)
+    fcw = _fcws(n_ch, 123)
+    rx = pkg.Receiver(n_ch, block)
+    rx.set_fcw(fcw)
+    host_adc = torch.from_numpy(adc.reshape(n_blocks, block)).pin_memory()
+    outs = [torch.empty((n_ch, block // 1024, 8), dtype=torch.uint8).pin_memory() for _ in range(n_blocks)]
+    for b in range(n_blocks):
+        rx.push(host_adc[b])
+        rx.read_frames_async(outs[b])
+    rx.sync()
+    got = np.concatenate([o.numpy() for o in outs], axis=1)
+    rx.close()
+    assert np.array_equal(got, oracle.golden_frames(adc, fcw))

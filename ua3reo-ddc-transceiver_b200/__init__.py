@@ -71,6 +71,7 @@ def _bind(lib):
         "ua3reo_ddc_push": (c.c_int, [vp, vp, sz, c.POINTER(sz)]),
         "ua3reo_ddc_push_device": (c.c_int, [vp, vp, sz, c.POINTER(sz)]),
         "ua3reo_ddc_read_frames": (c.c_int, [vp, vp, sz]),
+        "ua3reo_ddc_read_frames_async": (c.c_int, [vp, vp, sz]),
         "ua3reo_ddc_frames_device": (c.c_int, [vp, c.POINTER(vp), c.POINTER(sz), c.POINTER(sz), c.POINTER(sz), c.POINTER(sz)]),
         "ua3reo_rx_defaults": (None, [c.POINTER(RxSettings)]),
         "ua3reo_rx_enable": (c.c_int, [vp, c.c_int]),
@@ -193,6 +194,13 @@ class Receiver:
             out = np.empty((self.n_channels, nf, FRAME_BYTES), np.uint8)
         ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
         self._chk(self.lib.ua3reo_ddc_read_frames(self._h, ptr, nf))
+        return out
+
+    def read_frames_async(self, out):
+        """Enqueue the copy of the last push's frames into `out` (pinned torch tensor or numpy array) and return;
+        `out` is valid after sync().  Lets the next push overlap the device-to-host copy."""
+        ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
+        self._chk(self.lib.ua3reo_ddc_read_frames_async(self._h, ptr, self.last_frames))
         return out
 
     def frames_device(self):

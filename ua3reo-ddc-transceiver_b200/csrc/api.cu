@@ -31,6 +31,19 @@ static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
 struct ua3reo_ctx {
     int device = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // device->host result copies that overlap the next push
+    cudaEvent_t ev_push = nullptr;        // end of the last push on `stream`
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};   // end of the async frame read issued after push k (k & 1)
+    bool copy_pending[2] = {false, false};
+    uint64_t n_push = 0;
+    // host pushes of whole blocks go through two staging buffers on their own stream, so that the
+    // host->device copy of block k+1 overlaps the kernels of block k
+    cudaStream_t h2d_stream = nullptr;
+    int16_t* adc_stage2[2] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d = nullptr;                  // staging buffer filled
+    cudaEvent_t ev_stage_free[2] = {nullptr, nullptr};   // kernels that read staging buffer i have finished
+    bool stage_busy[2] = {false, false};
+    uint64_t n_host_push = 0;
     uint32_t n_ch = 0, n_ch_pad = 0, max_block = 0;
     DdcBuffers b;
     int16_t* adc_stage = nullptr;   // device [max_block + 1024]: carry + new samples
@@ -91,6 +104,12 @@ static int ctx_free(ua3reo_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (void* p : c->allocs) cudaFree(p);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamDestroy(c->h2d_stream); }
+    if (c->ev_h2d) cudaEventDestroy(c->ev_h2d);
+    for (int i = 0; i < 2; ++i) if (c->ev_stage_free[i]) cudaEventDestroy(c->ev_stage_free[i]);
+    if (c->ev_push) cudaEventDestroy(c->ev_push);
+    for (int i = 0; i < 2; ++i) if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return UA3_OK;
@@ -119,6 +138,13 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     c->max_block = max_block_samples;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete c; return fail(UA3_E_CUDA, "cudaStreamCreate", e); }
+    e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_stage_free[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) { ctx_free(c); return fail(UA3_E_CUDA, "stream/event creation", e); }
 
     DdcBuffers& b = c->b;
     b.n_ch = c->n_ch; b.n_ch_pad = c->n_ch_pad;
@@ -129,7 +155,7 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     b.yi_stride = (kYIHalo + b.max_frames + 7u) & ~7u;
     b.yq_stride = (kYQHalo + b.max_frames + 7u) & ~7u;
     uint32_t ring = 1024;
-    while (ring < b.max_frames + 1024u) ring <<= 1;      // holds one push plus the <= 511 frames the STM32 stage has not consumed
+    while (ring < 2u * b.max_frames + 1024u) ring <<= 1;  // two pushes (async reads overlap the next push) + the <= 511 frames the STM32 stage has not consumed
     b.frame_ch_stride = ring;
     b.ring_mask = ring - 1u;
 #define UA3_TRY(call) do { e = (call); if (e != cudaSuccess) { ctx_free(c); return fail(UA3_E_CUDA, #call, e); } } while (0)
@@ -151,6 +177,8 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     UA3_TRY(dev_alloc(c, &b.YQ, (size_t)c->n_ch_pad * b.yq_stride));
     UA3_TRY(dev_alloc(c, &b.frames, (size_t)c->n_ch * b.frame_ch_stride));
     UA3_TRY(dev_alloc(c, &c->adc_stage, (size_t)max_block_samples + UA3_ADC_PER_FRAME));
+    UA3_TRY(dev_alloc(c, &c->adc_stage2[0], (size_t)max_block_samples));
+    UA3_TRY(dev_alloc(c, &c->adc_stage2[1], (size_t)max_block_samples));
     uint32_t tab[2048];
     build_nco_table(tab);
     UA3_TRY(cudaMemcpyAsync(b.nco_tab, tab, sizeof tab, cudaMemcpyHostToDevice, c->stream));
@@ -228,10 +256,25 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
     const int16_t* proc_src = c->adc_stage;
     const bool in_place = (kind == cudaMemcpyDeviceToDevice) && c->carry == 0 && n_proc == n &&
                           ((uintptr_t)src % 16u) == 0;
+    const bool staged = (kind == cudaMemcpyHostToDevice) && c->carry == 0 && n_proc == n && n > 0;
+    int stage_slot = -1;
     if (in_place) {
         proc_src = src;
+    } else if (staged) {
+        // whole-block host push: copy on the H2D stream into the free staging buffer, kernels wait for the copy
+        stage_slot = (int)(c->n_host_push++ & 1);
+        if (c->stage_busy[stage_slot]) UA3_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_stage_free[stage_slot], 0));
+        UA3_CUDA(cudaMemcpyAsync(c->adc_stage2[stage_slot], src, n * sizeof(int16_t), kind, c->h2d_stream));
+        UA3_CUDA(cudaEventRecord(c->ev_h2d, c->h2d_stream));
+        UA3_CUDA(cudaStreamWaitEvent(c->stream, c->ev_h2d, 0));
+        proc_src = c->adc_stage2[stage_slot];
     } else if (n) {
         UA3_CUDA(cudaMemcpyAsync(c->adc_stage + c->carry, src, n * sizeof(int16_t), kind, c->stream));
+    }
+    // an asynchronous frame read issued after push k-2 still owns the ring slots this push overwrites
+    if (c->copy_pending[c->n_push & 1]) {
+        UA3_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[c->n_push & 1], 0));
+        c->copy_pending[c->n_push & 1] = false;
     }
     int launches = 0;
     cudaEvent_t* ev = nullptr;
@@ -254,6 +297,12 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
         c->a_pos = c->f_pos = c->w_pos;
     }
     c->launches += (uint64_t)launches;
+    UA3_CUDA(cudaEventRecord(c->ev_push, c->stream));
+    if (stage_slot >= 0) {
+        UA3_CUDA(cudaEventRecord(c->ev_stage_free[stage_slot], c->stream));
+        c->stage_busy[stage_slot] = true;
+    }
+    c->n_push++;
     const uint32_t left = (uint32_t)(total - n_proc);
     if (!in_place && n_proc && left)
         UA3_CUDA(cudaMemcpyAsync(c->adc_stage, c->adc_stage + n_proc, left * sizeof(int16_t), cudaMemcpyDeviceToDevice,
@@ -273,8 +322,8 @@ int ua3reo_ddc_push_device(ua3reo_ctx* c, const int16_t* adc_dev, size_t n, size
     return push_common(c, adc_dev, n, frames_out, cudaMemcpyDeviceToDevice);
 }
 
-int ua3reo_ddc_read_frames(ua3reo_ctx* c, uint8_t* dst, size_t n_frames) {
-    if (!c || (!dst && n_frames)) return fail(UA3_E_INVAL, "ua3reo_ddc_read_frames: null argument");
+static int read_frames_on(ua3reo_ctx* c, uint8_t* dst, size_t n_frames, cudaStream_t st, const char* who) {
+    if (!c || (!dst && n_frames)) return fail(UA3_E_INVAL, who);
     if (!c->pushed) return fail(UA3_E_STATE, "ua3reo_ddc_read_frames: no push yet");
     if (n_frames != c->last_frames) return fail(UA3_E_INVAL, "ua3reo_ddc_read_frames: n_frames != frames of last push");
     UA3_CUDA(cudaSetDevice(c->device));
@@ -284,12 +333,32 @@ int ua3reo_ddc_read_frames(ua3reo_ctx* c, uint8_t* dst, size_t n_frames) {
         const size_t n1 = (first + n_frames <= ring) ? n_frames : (size_t)(ring - first);   // up to the wrap
         const size_t pitch = (size_t)ring * UA3_FRAME_BYTES;
         UA3_CUDA(cudaMemcpy2DAsync(dst, n_frames * UA3_FRAME_BYTES, c->b.frames + first, pitch, n1 * UA3_FRAME_BYTES,
-                                   c->n_ch, cudaMemcpyDeviceToHost, c->stream));
+                                   c->n_ch, cudaMemcpyDeviceToHost, st));
         if (n1 < n_frames)
             UA3_CUDA(cudaMemcpy2DAsync(dst + n1 * UA3_FRAME_BYTES, n_frames * UA3_FRAME_BYTES, c->b.frames, pitch,
-                                       (n_frames - n1) * UA3_FRAME_BYTES, c->n_ch, cudaMemcpyDeviceToHost, c->stream));
+                                       (n_frames - n1) * UA3_FRAME_BYTES, c->n_ch, cudaMemcpyDeviceToHost, st));
     }
+    return UA3_OK;
+}
+
+int ua3reo_ddc_read_frames(ua3reo_ctx* c, uint8_t* dst, size_t n_frames) {
+    const int rc = read_frames_on(c, dst, n_frames, c ? c->stream : nullptr, "ua3reo_ddc_read_frames: null argument");
+    if (rc != UA3_OK) return rc;
     UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_ddc_read_frames_async(ua3reo_ctx* c, uint8_t* dst, size_t n_frames) {
+    if (!c) return fail(UA3_E_INVAL, "ua3reo_ddc_read_frames_async: null argument");
+    if (c->b.frame_ch_stride < 2u * c->b.max_frames)
+        return fail(UA3_E_STATE, "ua3reo_ddc_read_frames_async: frame ring cannot hold two pushes");
+    UA3_CUDA(cudaSetDevice(c->device));
+    UA3_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_push, 0));
+    const int rc = read_frames_on(c, dst, n_frames, c->copy_stream, "ua3reo_ddc_read_frames_async: null argument");
+    if (rc != UA3_OK) return rc;
+    const unsigned slot = (unsigned)((c->n_push + 1) & 1);      // n_push was already advanced by the push being read
+    UA3_CUDA(cudaEventRecord(c->ev_copy[slot], c->copy_stream));
+    c->copy_pending[slot] = true;
     return UA3_OK;
 }
 
@@ -441,7 +510,9 @@ int ua3reo_rx_read_smeter(ua3reo_ctx* c, float* dst, int reset) {
 int ua3reo_sync(ua3reo_ctx* c) {
     if (!c) return fail(UA3_E_INVAL, "null context");
     UA3_CUDA(cudaSetDevice(c->device));
+    UA3_CUDA(cudaStreamSynchronize(c->h2d_stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->copy_stream));
     return UA3_OK;
 }
 
