@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -278,6 +278,13 @@ def run_ours(args):
             cpu = {"value": rate, "unit": "channel*samples/s", "cores": cores, "kind": "port",
                    "sample": "%d channels x 2^19 ADC samples x %d blocks, %d threads, golden C model "
                              "(oracle/ddc_golden.c; the FPGA HDL itself cannot be built here)" % (c_ch, blocks, cores)}
+        variant = os.environ.get("UA3REO_FRONT_VARIANT", "0")
+        front_name = "ddc_front_kernel" if (variant == "1" or n_ch < 256) else "ddc_front_bt_kernel"
+        static = {}
+        try:
+            static = json.load(open(os.path.join(ROOT, "profiles", "r01_front_kernel_static.json"))).get(front_name, {})
+        except Exception:
+            pass
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -299,9 +306,12 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "channel*samples/s", "h2d_bytes_per_step": 2 * block,
                     "d2h_bytes_per_step": n_ch * (block // 1024) * 8, "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "int32_alu", "kernel": "ddc_front_kernel", "achieved": achieved / 1e12, "peak": int32_peak / 1e12,
+            "roofline": {"bound": "int32_alu", "kernel": front_name, "achieved": achieved / 1e12, "peak": int32_peak / 1e12,
                          "unit": "TOP/s (INT32)", "frac": (achieved / int32_peak) if int32_peak else None,
-                         "traffic": None,
+                         "traffic": static.get("traffic_bytes_per_launch") if (n_ch, block) == (1024, 1 << 20) else None,
+                         "executed_ops_per_unit": static.get("sass_instructions_per_unit"),
+                         "issue_frac": (static["sass_instructions_per_unit"] * float(n_ch) * block / front_s / int32_peak)
+                                       if static.get("sass_instructions_per_unit") and front_s > 0 and int32_peak else None,
                          "ops_per_unit": A_INT_OPS, "units_per_launch": float(n_ch) * block,
                          "kernel_ms": front_s * 1e3,
                          "kernel_share_of_step": kms["front"] / max(sum(kms.values()), 1e-9),
