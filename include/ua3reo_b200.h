@@ -170,6 +170,34 @@ int ua3reo_duc_dac_device(ua3reo_ctx *ctx, const uint16_t **base, size_t *n_word
 /* tx_summator overflow count per channel since reset (the DAC_OTR flag, stm32_interface.v:172-205): dst [n_channels]. */
 int ua3reo_duc_read_otr(ua3reo_ctx *ctx, uint32_t *dst_host);
 
+/* ---------------------------------------------------------------------------------------------
+ * STM32 transmit audio: processTxAudio() (audio_processor.c:61-273) for every channel - DC filter, lattice
+ * HPF/LPF, ALC compressor, SSB (+/-45 degree Hilbert FIR pair), AM, FM and CW modulators.  Its I/Q output is
+ * what FPGA_fpgadata_sendiq() (fpga.c:403-436) puts on the bus and the DUC above consumes.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ua3reo_tx_settings {
+    uint8_t mode;            /* TRX_MODE_*: LSB USB IQ CW_L CW_U DIGI_L DIGI_U NFM WFM AM */
+    uint8_t mute;            /* TRX.Mute */
+    uint8_t tune;            /* TRX_tune (carrier at the selected power) */
+    uint8_t key_down;        /* TRX_key_serial || TRX_ptt_hard || TRX_key_hard (CW keying, audio_processor.c:146) */
+    uint8_t rf_power;        /* TRX.RF_Power, percent of MAX_TX_AMPLITUDE (settings.h:13) */
+    uint8_t reserved[3];
+    uint16_t filter_width;   /* CurrentVFO()->Filter_Width (also selects the FM modulation index, :597-605) */
+    uint16_t ssb_hpf_pass;   /* TRX.SSB_HPF_pass */
+} ua3reo_tx_settings;
+
+void ua3reo_tx_defaults(ua3reo_tx_settings *s);
+int ua3reo_tx_enable(ua3reo_ctx *ctx, uint32_t max_blocks);
+int ua3reo_tx_set(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const ua3reo_tx_settings *settings);
+/* n_blocks x 192 codec samples per channel: mic_host is [n_channels][n_blocks*192][2] int16 (left, right), the
+ * layout of CODEC_Audio_Buffer_TX (wm8731.h:14).  One processTxAudio() per block. */
+int ua3reo_tx_process(ua3reo_ctx *ctx, const int16_t *mic_host, size_t n_blocks);
+/* I/Q of the last call: iq_words [n_channels][n_blocks*192][2] int16 (I, Q as sent on the wire) and/or iq_float
+ * (same shape, FPGA_Audio_SendBuffer_I/Q contents); either may be NULL. */
+int ua3reo_tx_read_iq(ua3reo_ctx *ctx, int16_t *iq_words, float *iq_float, size_t n_blocks);
+/* Runs the DUC over the I/Q words of the last ua3reo_tx_process() without leaving the device. */
+int ua3reo_tx_feed_duc(ua3reo_ctx *ctx);
+
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline):
  * after ua3reo_profile_begin(ctx, max_blocks) each processed ADC block records an event before and
  * after every kernel; ua3reo_profile_end() waits for the stream and sums the elapsed times per

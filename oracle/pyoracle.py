@@ -171,3 +171,31 @@ class GoldenDUC:
         otr = np.zeros(n * 1024, np.uint8)
         lib().ua3g_duc_push(self._st, tx_i.ctypes.data, tx_q.ctypes.data, n, dac.ctypes.data, otr.ctypes.data)
         return dac, otr
+
+
+FW_TX = os.path.join(_HERE, "_ref", "fw_tx")
+TX_PARAM_KEYS = {"mode": "mode", "filter_width": "filter_width", "ssb_hpf_pass": "hpf_pass", "rf_power": "rf_power",
+                 "mute": "mute", "tune": "tune", "key_down": "key"}
+
+
+def have_fw_tx():
+    return os.path.exists(FW_TX)
+
+
+def run_fw_tx(mic, settings, workdir=None):
+    """Runs the host-built reference firmware's processTxAudio() over int16 [n, 2] codec samples (n multiple of 192).
+    Returns (iq_words int16 [n, 2], iq_float float32 [n, 2])."""
+    import tempfile
+    mic = np.ascontiguousarray(mic, dtype=np.int16).reshape(-1, 2)
+    with tempfile.TemporaryDirectory(dir=workdir) as d:
+        pp, mp_, op = (os.path.join(d, n) for n in ("p.txt", "mic.bin", "out.bin"))
+        with open(pp, "w") as f:
+            for k, v in settings.items():
+                if k in TX_PARAM_KEYS:
+                    f.write("%s %d\n" % (TX_PARAM_KEYS[k], int(v)))
+        mic.tofile(mp_)
+        subprocess.check_call([FW_TX, pp, mp_, op])
+        raw = np.fromfile(op, dtype=np.uint8).reshape(-1, 192 * 2 * 4 + 192 * 2 * 2)
+        f = np.ascontiguousarray(raw[:, :1536]).view(np.float32).reshape(-1, 2)
+        w = np.ascontiguousarray(raw[:, 1536:]).view(np.int16).reshape(-1, 2)
+        return w, f

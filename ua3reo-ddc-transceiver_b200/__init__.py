@@ -37,6 +37,17 @@ MODE_LSB, MODE_USB, MODE_IQ, MODE_CW_L, MODE_CW_U, MODE_DIGI_L, MODE_DIGI_U, MOD
     MODE_LOOPBACK = range(12)
 
 
+class TxSettings(ctypes.Structure):
+    """struct ua3reo_tx_settings (include/ua3reo_b200.h)."""
+    _fields_ = [("mode", ctypes.c_uint8), ("mute", ctypes.c_uint8), ("tune", ctypes.c_uint8), ("key_down", ctypes.c_uint8),
+                ("rf_power", ctypes.c_uint8), ("reserved", ctypes.c_uint8 * 3), ("filter_width", ctypes.c_uint16),
+                ("ssb_hpf_pass", ctypes.c_uint16)]
+    FIELDS = ("mode", "mute", "tune", "key_down", "rf_power", "filter_width", "ssb_hpf_pass")
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k in self.FIELDS}
+
+
 class RxSettings(ctypes.Structure):
     """struct ua3reo_rx_settings (include/ua3reo_b200.h): the TRX fields processRxAudio()/FFT_doFFT() read."""
     _fields_ = [("mode", ctypes.c_uint8), ("agc", ctypes.c_uint8), ("agc_speed", ctypes.c_uint8), ("dnr", ctypes.c_uint8),
@@ -85,6 +96,12 @@ def _bind(lib):
         "ua3reo_duc_read_dac": (c.c_int, [vp, vp, sz]),
         "ua3reo_duc_dac_device": (c.c_int, [vp, c.POINTER(vp), c.POINTER(sz), c.POINTER(sz)]),
         "ua3reo_duc_read_otr": (c.c_int, [vp, vp]),
+        "ua3reo_tx_defaults": (None, [c.POINTER(TxSettings)]),
+        "ua3reo_tx_enable": (c.c_int, [vp, u32]),
+        "ua3reo_tx_set": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_tx_process": (c.c_int, [vp, vp, sz]),
+        "ua3reo_tx_read_iq": (c.c_int, [vp, vp, vp, sz]),
+        "ua3reo_tx_feed_duc": (c.c_int, [vp]),
         "ua3reo_sync": (c.c_int, [vp]),
         "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_launch_count": (c.c_uint64, [vp]),
@@ -279,6 +296,38 @@ class Receiver:
         out = np.empty(self.n_channels, np.uint32)
         self._chk(self.lib.ua3reo_duc_read_otr(self._h, out.ctypes.data))
         return out
+
+    # ---- transmit audio (processTxAudio) ----
+    def tx_defaults(self, **overrides):
+        s = TxSettings()
+        self.lib.ua3reo_tx_defaults(ctypes.byref(s))
+        for k, v in overrides.items():
+            setattr(s, k, v)
+        return s
+
+    def tx_enable(self, max_blocks=8):
+        self._chk(self.lib.ua3reo_tx_enable(self._h, int(max_blocks)))
+
+    def tx_set(self, settings, first=0):
+        if isinstance(settings, TxSettings):
+            settings = [settings] * (self.n_channels - first)
+        arr = (TxSettings * len(settings))(*settings)
+        self._chk(self.lib.ua3reo_tx_set(self._h, int(first), len(settings), ctypes.cast(arr, ctypes.c_void_p)))
+
+    def tx_process(self, mic):
+        """mic: int16 [n_channels, n_blocks*192, 2] (left, right).  Returns (iq_words int16, iq_float float32), same shape."""
+        a = np.ascontiguousarray(mic, dtype=np.int16)
+        assert a.ndim == 3 and a.shape[0] == self.n_channels and a.shape[1] % AUDIO_BLOCK == 0 and a.shape[2] == 2
+        nb = a.shape[1] // AUDIO_BLOCK
+        self._chk(self.lib.ua3reo_tx_process(self._h, a.ctypes.data, nb))
+        w = np.empty(a.shape, np.int16)
+        f = np.empty(a.shape, np.float32)
+        self._chk(self.lib.ua3reo_tx_read_iq(self._h, w.ctypes.data, f.ctypes.data, nb))
+        return w, f
+
+    def tx_feed_duc(self):
+        self._chk(self.lib.ua3reo_tx_feed_duc(self._h))
+        self._last_tx = None
 
     def sync(self):
         self._chk(self.lib.ua3reo_sync(self._h))

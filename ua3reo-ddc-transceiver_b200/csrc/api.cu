@@ -3,6 +3,7 @@
 #include "ddc_launch.h"
 #include "rx_launch.h"
 #include "duc_launch.h"
+#include "tx_launch.h"
 #include "ua3_common.cuh"
 #include <cmath>
 #include <cstdio>
@@ -70,6 +71,12 @@ struct ua3reo_ctx {
     bool duc_alloc = false;
     DucBuffers duc;
     size_t last_tx = 0;
+    // transmit audio (processTxAudio)
+    bool tx_alloc = false;
+    TxBuffers tx;
+    std::vector<TxParams> h_txpar;
+    uint8_t* tx_flags = nullptr;
+    size_t last_tx_blocks = 0;
 };
 
 template <class T>
@@ -213,6 +220,11 @@ int ua3reo_reset(ua3reo_ctx* c) {
         c->launches += (uint64_t)launches;
     }
     if (c->duc_alloc) UA3_CUDA(cudaMemsetAsync(c->duc.state, 0, sizeof(DucState) * (size_t)c->n_ch, c->stream));
+    if (c->tx_alloc) {
+        int launches = 0;
+        UA3_CUDA(tx_launch_init_state(c->tx, c->stream, &launches));
+        c->launches += (uint64_t)launches;
+    }
     c->last_tx = 0;
     return UA3_OK;
 }
@@ -584,6 +596,119 @@ int ua3reo_duc_read_otr(ua3reo_ctx* c, uint32_t* dst) {
     UA3_CUDA(cudaMemcpy2DAsync(dst, sizeof(uint32_t), reinterpret_cast<const uint8_t*>(c->duc.state) + offsetof(DucState, otr),
                                sizeof(DucState), sizeof(uint32_t), c->n_ch, cudaMemcpyDeviceToHost, c->stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// transmit audio
+// ------------------------------------------------------------------------------------------------
+void ua3reo_tx_defaults(ua3reo_tx_settings* s) {
+    if (!s) return;
+    std::memset(s, 0, sizeof *s);
+    s->mode = kModeUSB; s->rf_power = 20; s->filter_width = 2700; s->ssb_hpf_pass = 300;   // settings.c:33-94
+}
+
+int ua3reo_tx_enable(ua3reo_ctx* c, uint32_t max_blocks) {
+    if (!c || max_blocks == 0) return fail(UA3_E_INVAL, "ua3reo_tx_enable: bad arguments");
+    if (c->tx_alloc) return (max_blocks <= c->tx.max_blocks) ? UA3_OK : fail(UA3_E_STATE, "ua3reo_tx_enable: already enabled with fewer blocks");
+    UA3_CUDA(cudaSetDevice(c->device));
+    TxBuffers& t = c->tx;
+    t.n_ch = c->n_ch; t.max_blocks = max_blocks;
+    const size_t per_ch = (size_t)max_blocks * UA3_AUDIO_BLOCK * 2;
+    UA3_CUDA(dev_alloc(c, &t.params, (size_t)c->n_ch));
+    UA3_CUDA(dev_alloc(c, &t.state, (size_t)c->n_ch));
+    UA3_CUDA(dev_alloc(c, &t.mic, (size_t)c->n_ch * per_ch));
+    UA3_CUDA(dev_alloc(c, &t.iq_f, (size_t)c->n_ch * per_ch));
+    UA3_CUDA(dev_alloc(c, &t.iq_w, (size_t)c->n_ch * per_ch));
+    UA3_CUDA(dev_alloc(c, &c->tx_flags, (size_t)c->n_ch));
+    float T[513];
+    cmsis_sin_table(T);
+    UA3_CUDA(tx_upload_constants(T));
+    int launches = 0;
+    UA3_CUDA(tx_launch_init_state(t, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    ua3reo_tx_settings d;
+    ua3reo_tx_defaults(&d);
+    c->h_txpar.assign(c->n_ch, TxParams());
+    for (uint32_t i = 0; i < c->n_ch; ++i) {
+        std::memset(&c->h_txpar[i], 0, sizeof(TxParams));
+        c->h_txpar[i].fm_index = 2.0f;                                   // static float32_t modulation_index = 2.0f
+        bool a, b;
+        if (!tx_derive(d, c->h_txpar[i], a, b)) return fail(UA3_E_INVAL, "internal: default TX settings rejected");
+    }
+    UA3_CUDA(cudaMemcpyAsync(t.params, c->h_txpar.data(), sizeof(TxParams) * c->n_ch, cudaMemcpyHostToDevice, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    c->tx_alloc = true;
+    return UA3_OK;
+}
+
+int ua3reo_tx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_tx_settings* settings) {
+    if (!c || !settings || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_tx_set: range");
+    if (!c->tx_alloc) return fail(UA3_E_STATE, "ua3reo_tx_set: call ua3reo_tx_enable first");
+    UA3_CUDA(cudaSetDevice(c->device));
+    std::vector<TxParams> np(c->h_txpar.begin() + first, c->h_txpar.begin() + first + n);
+    std::vector<uint8_t> flags(n, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        bool cl = false, chp = false;
+        if (!tx_derive(settings[i], np[i], cl, chp)) return fail(UA3_E_INVAL, "ua3reo_tx_set: settings outside the firmware's tables");
+        flags[i] = (uint8_t)((cl ? 1 : 0) | (chp ? 2 : 0));
+    }
+    for (uint32_t i = 0; i < n; ++i) c->h_txpar[first + i] = np[i];
+    UA3_CUDA(cudaMemcpyAsync(c->tx.params + first, c->h_txpar.data() + first, sizeof(TxParams) * n, cudaMemcpyHostToDevice, c->stream));
+    UA3_CUDA(cudaMemcpyAsync(c->tx_flags, flags.data(), n, cudaMemcpyHostToDevice, c->stream));
+    int launches = 0;
+    UA3_CUDA(tx_launch_clear(c->tx, c->tx_flags, first, n, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_tx_process(ua3reo_ctx* c, const int16_t* mic_host, size_t n_blocks) {
+    if (!c || (!mic_host && n_blocks)) return fail(UA3_E_INVAL, "ua3reo_tx_process: null argument");
+    if (!c->tx_alloc) return fail(UA3_E_STATE, "ua3reo_tx_process: call ua3reo_tx_enable first");
+    if (n_blocks > c->tx.max_blocks) return fail(UA3_E_TOOBIG, "ua3reo_tx_process: more blocks than max_blocks");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t row = n_blocks * UA3_AUDIO_BLOCK * 2 * sizeof(int16_t);
+    if (n_blocks)
+        UA3_CUDA(cudaMemcpy2DAsync(c->tx.mic, (size_t)c->tx.max_blocks * UA3_AUDIO_BLOCK * 2 * sizeof(int16_t), mic_host, row, row,
+                                   c->n_ch, cudaMemcpyHostToDevice, c->stream));
+    int launches = 0;
+    UA3_CUDA(tx_launch_audio(c->tx, (uint32_t)n_blocks, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    c->last_tx_blocks = n_blocks;
+    return UA3_OK;
+}
+
+int ua3reo_tx_read_iq(ua3reo_ctx* c, int16_t* iq_words, float* iq_float, size_t n_blocks) {
+    if (!c) return fail(UA3_E_INVAL, "ua3reo_tx_read_iq: null argument");
+    if (!c->tx_alloc) return fail(UA3_E_STATE, "ua3reo_tx_read_iq: transmit audio not enabled");
+    if (n_blocks != c->last_tx_blocks) return fail(UA3_E_INVAL, "ua3reo_tx_read_iq: n_blocks != blocks of last call");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t n = n_blocks * UA3_AUDIO_BLOCK * 2, stride = (size_t)c->tx.max_blocks * UA3_AUDIO_BLOCK * 2;
+    if (n && iq_words)
+        UA3_CUDA(cudaMemcpy2DAsync(iq_words, n * sizeof(int16_t), c->tx.iq_w, stride * sizeof(int16_t), n * sizeof(int16_t), c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    if (n && iq_float)
+        UA3_CUDA(cudaMemcpy2DAsync(iq_float, n * sizeof(float), c->tx.iq_f, stride * sizeof(float), n * sizeof(float), c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_tx_feed_duc(ua3reo_ctx* c) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    if (!c->tx_alloc || !c->duc_alloc) return fail(UA3_E_STATE, "ua3reo_tx_feed_duc: enable the transmit audio stage and the DUC first");
+    const size_t n = c->last_tx_blocks * UA3_AUDIO_BLOCK;
+    if (n > c->duc.max_in) return fail(UA3_E_TOOBIG, "ua3reo_tx_feed_duc: DUC block smaller than the audio blocks");
+    UA3_CUDA(cudaSetDevice(c->device));
+    if (n)
+        UA3_CUDA(cudaMemcpy2DAsync(c->duc.iq_in, (size_t)c->duc.max_in * 2 * sizeof(int16_t), c->tx.iq_w,
+                                   (size_t)c->tx.max_blocks * UA3_AUDIO_BLOCK * 2 * sizeof(int16_t), n * 2 * sizeof(int16_t), c->n_ch,
+                                   cudaMemcpyDeviceToDevice, c->stream));
+    int launches = 0;
+    UA3_CUDA(duc_launch(c->duc, (uint32_t)n, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    c->last_tx = n;
     return UA3_OK;
 }
 
