@@ -123,7 +123,8 @@ typedef struct ua3reo_rx_settings {
     uint8_t fft_averaging;     /* TRX.FFT_Averaging */
     uint8_t fft_zoom;          /* TRX.FFT_Zoom: only 1 is implemented (ZoomFFT is a later row) */
     uint8_t iq_swap;           /* TRX_IQ_swap (functions.c:211-223) */
-    uint8_t reserved[3];
+    uint8_t cw_decoder;        /* TRX.CWDecoder: run the CW decoder's Goertzel front end in CW_L / CW_U (cw_decoder.c:43-66) */
+    uint8_t reserved[2];
     uint16_t filter_width;     /* CurrentVFO()->Filter_Width: 0 (LPF off) or one of the 32 table widths (audio_filters.c:59-122) */
     uint16_t ssb_hpf_pass;     /* TRX.SSB_HPF_pass: 60/100/200/300/400/500 */
     uint16_t notch_fc;         /* TRX.NotchFC, Hz */
@@ -150,6 +151,19 @@ int ua3reo_rx_counts(ua3reo_ctx *ctx, size_t *audio_blocks, size_t *fft_frames);
 int ua3reo_rx_read_audio(ua3reo_ctx *ctx, int32_t *dst_host, size_t n_blocks);
 /* Spectra: FFTOutput_mean (fft.c:27,324-328) after each FFT_doFFT(): dst is [n_channels][n_frames][256] float. */
 int ua3reo_rx_read_spectra(ua3reo_ctx *ctx, float *dst_host, size_t n_frames);
+/* Waterfall rows: what FFT_printFFT() writes into wtf_buffer[0] after each FFT (fft.c:361-379): per bin the
+ * column height (uint16_t)(mean * 30) mapped through getFFTColor() (fft.c:503-538) to RGB565, red (0xF800) when
+ * the column overflows, stored fft-shifted (bin x lands at x +/- 128).  dst is [n_channels][n_frames][256] uint16. */
+int ua3reo_rx_read_waterfall(ua3reo_ctx *ctx, uint16_t *dst_host, size_t n_frames);
+/* CW decoder front end (cw_decoder.c:43-66): the Goertzel magnitude at 350 Hz of every 192-sample block of the final
+ * audio, for channels in CW_L / CW_U with cw_decoder set (0 elsewhere).  dst is [n_channels][n_blocks] float. */
+int ua3reo_rx_read_cw(ua3reo_ctx *ctx, float *dst_host, size_t n_blocks);
+/* ADC_MIN / ADC_MAX tracking of stm32_interface.v:384-397 over the ADC samples pushed since the last reset (the FPGA
+ * resets to +2000 / -2000 when the MCU reads them with command 2, stm32_interface.v:172-205 <- fpga.c:222-284), and
+ * the number of samples at either rail of the 12-bit range (what the AD9226 flags on its OTR pin). */
+int ua3reo_adc_stats(ua3reo_ctx *ctx, int16_t *adc_min, int16_t *adc_max, uint32_t *n_rail, int reset);
+/* TRX_RX_dBm of the 100 ms housekeeping tick (stm32f4xx_it.c:398-409) from the S-meter extremes: pure host function. */
+int16_t ua3reo_smeter_dbm(float sample_max, float sample_min, uint8_t rf_gain);
 /* S-meter accumulators Processor_RX_Audio_Samples_MAX/MIN_value (audio_processor.c:491-501): dst [n_channels][2];
  * reset != 0 clears them afterwards, as the 1 s housekeeping tick does (stm32f4xx_it.c:398-409). */
 int ua3reo_rx_read_smeter(ua3reo_ctx *ctx, float *dst_host, int reset);

@@ -122,7 +122,7 @@ FW_RX = os.path.join(_HERE, "_ref", "fw_rx")
 RX_PARAM_KEYS = {"mode": "mode", "filter_width": "filter_width", "ssb_hpf_pass": "hpf_pass", "rf_gain": "rf_gain",
                  "agc": "agc", "agc_speed": "agc_speed", "dnr": "dnr", "notch": "notch", "notch_fc": "notch_fc",
                  "volume": "volume", "mute": "mute", "fm_sql_threshold": "fm_sql", "fft_enabled": "fft_enabled",
-                 "fft_zoom": "fft_zoom", "fft_averaging": "fft_averaging", "iq_swap": "iq_swap"}
+                 "fft_zoom": "fft_zoom", "fft_averaging": "fft_averaging", "iq_swap": "iq_swap", "cw_decoder": "cw_decoder"}
 
 
 def have_fw_rx():
@@ -132,7 +132,7 @@ def have_fw_rx():
 def run_fw_rx(frames, settings, workdir=None):
     """Runs the host-built reference firmware over uint8 [n_frames, 8] frames for one channel.
     settings: dict with the ua3reo_rx_settings field names.  Returns dict(audio int32 [nb, 384],
-    smeter float32 [nb, 2], spectra float32 [nf, 256], waterfall uint16 [nf, 256], fft_max float32 [nf])."""
+    smeter float32 [nb, 2], cw float32 [nb], spectra float32 [nf, 256], waterfall uint16 [nf, 256], fft_max float32 [nf])."""
     import tempfile
     frames = np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1, 8)
     with tempfile.TemporaryDirectory(dir=workdir) as d:
@@ -143,13 +143,14 @@ def run_fw_rx(frames, settings, workdir=None):
                     f.write("%s %d\n" % (RX_PARAM_KEYS[k], int(v)))
         frames.tofile(fp)
         subprocess.check_call([FW_RX, pp, fp, ap, sp])
-        a = np.fromfile(ap, dtype=np.int32).reshape(-1, 386)
+        a = np.fromfile(ap, dtype=np.int32).reshape(-1, 387)
         raw = np.fromfile(sp, dtype=np.uint8)
         rec = 256 * 4 + 256 * 2 + 4
         raw = raw[:rec * (raw.size // rec)].reshape(-1, rec)
         return {
             "audio": a[:, :384].copy(),
-            "smeter": a[:, 384:].copy().view(np.float32),
+            "smeter": a[:, 384:386].copy().view(np.float32),
+            "cw": a[:, 386].copy().view(np.float32),
             "spectra": np.ascontiguousarray(raw[:, :1024]).view(np.float32).reshape(-1, 256),
             "waterfall": np.ascontiguousarray(raw[:, 1024:1536]).view(np.uint16).reshape(-1, 256),
             "fft_max": np.ascontiguousarray(raw[:, 1536:1540]).view(np.float32).reshape(-1),

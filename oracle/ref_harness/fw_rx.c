@@ -14,7 +14,8 @@
  *     bus driver has filled 512 samples FFT_doFFT() runs, then FFT_printFFT() + the waterfall DMA chain,
  *     which is what feeds maxValueErrors back into the auto-range (fft.c:310-316,372) and re-arms FFT_need_fft
  *   - VFO frequency is held at 0 so that FFT_moveWaterfall() (fft.c:347-351) never shifts the averages
- * audio_out: per block 384 int32 (L,R interleaved; audio_processor.c:377-394) + 2 float (S-meter max,min)
+ * audio_out: per block 384 int32 (L,R interleaved; audio_processor.c:377-394) + 3 float (S-meter max, min,
+ *            CW decoder Goertzel magnitude of the block or 0)
  * fft_out  : per FFT frame 256 float (FFTOutput_mean) + 256 uint16 (waterfall row 0) + float maxValueFFT
  */
 #include "stm32f4xx_hal.h"
@@ -37,6 +38,9 @@ void ua3_lcd_stub_init(void);
 const float *ua3_fft_output_mean(void);
 const uint16_t *ua3_fft_wtf_row0(void);
 float ua3_fft_max_value(void);
+float ua3_cw_magnitude(void);
+void ua3_set_tick(uint32_t t);
+#include "cw_decoder.h"
 
 static void defaults(void)
 {
@@ -57,7 +61,7 @@ static int set_param(const char *k, long v)
     P("rf_gain", TRX.RF_Gain) P("agc", TRX.AGC) P("agc_speed", TRX.Agc_speed) P("dnr", TRX.DNR)
     P("notch", TRX.NotchFilter) P("notch_fc", TRX.NotchFC) P("volume", TRX.Volume) P("mute", TRX.Mute)
     P("fm_sql", TRX.FM_SQL_threshold) P("fft_enabled", TRX.FFT_Enabled) P("fft_zoom", TRX.FFT_Zoom)
-    P("fft_averaging", TRX.FFT_Averaging) P("iq_swap", TRX_IQ_swap) P("squelched", TRX_squelched)
+    P("fft_averaging", TRX.FFT_Averaging) P("iq_swap", TRX_IQ_swap) P("squelched", TRX_squelched) P("cw_decoder", TRX.CWDecoder)
 #undef P
     return 0;
 }
@@ -78,6 +82,7 @@ int main(int argc, char **argv)
     ua3_lcd_stub_init();
     /* init order of main.c:188-193 (the calls that touch the signal path) */
     FFT_Init();
+    CWDecoder_Init();                  /* TRX_Init() (trx_manager.c:63-68) */
     initAudioProcessor();              /* InitAudioFilters (incl. InitNoiseReduction, InitNotchFilter) + InitAGC */
     ReinitAudioFilters();              /* as TRX_setMode() does, trx_manager.c:217 */
     NeedFFTInputBuffer = true;         /* trx_manager.c:185 */
@@ -92,12 +97,15 @@ int main(int argc, char **argv)
         n++;
         if (n > 192 && (n % 192) == 1) {
             Processor_NeedRXBuffer = true;
+            /* HAL_GetTick() stays 0: the Morse timing logic (cw_decoder.c:88-240, host side, unbounded strcat) never fires;
+             * only the Goertzel front end (:56-66) is exercised */
             const uint8_t before = Processor_AudioBuffer_ReadyBuffer;
             processRxAudio();
             const int32_t *out = (before == 0) ? Processor_AudioBuffer_B : Processor_AudioBuffer_A;
             fwrite(out, sizeof(int32_t), FPGA_AUDIO_BUFFER_SIZE, fa);
-            float sm[2] = {Processor_RX_Audio_Samples_MAX_value, Processor_RX_Audio_Samples_MIN_value};
-            fwrite(sm, sizeof(float), 2, fa);
+            float sm[3] = {Processor_RX_Audio_Samples_MAX_value, Processor_RX_Audio_Samples_MIN_value, 0.0f};
+            if (TRX.CWDecoder && (TRX_getMode() == TRX_MODE_CW_L || TRX_getMode() == TRX_MODE_CW_U)) sm[2] = ua3_cw_magnitude();
+            fwrite(sm, sizeof(float), 3, fa);
         }
         if (!NeedFFTInputBuffer && TRX.FFT_Enabled) {
             FFT_doFFT();

@@ -106,11 +106,7 @@ volatile TRX_FrontPanel_Type TRX_FrontPanel;
 volatile uint8_t TRX_Time_InActive = 0, TRX_Fan_Timeout = 0;
 uint32_t TRX_getFrequency(void) { return CurrentVFO()->Freq; }
 
-/* ---- CW decoder: does not modify the audio buffer (cw_decoder.c:59-70); hook keeps the last block ---- */
-volatile uint16_t CW_Decoder_WPM = 0;
-char CW_Decoder_Text[CWDECODER_STRLEN];
-void CWDecoder_Init(void) {}
-void CWDecoder_Process(float32_t *bufferIn) { (void)bufferIn; }
+/* the CW decoder itself (cw_decoder.c) is compiled from the reference through cw_wrap.c */
 
 /* profiler.c */
 void StartProfiler(uint8_t pid) { (void)pid; }

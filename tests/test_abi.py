@@ -43,3 +43,15 @@ def test_phrase_from_frequency_host_function(pkg, oracle):
 def test_missing_library_raises(pkg, tmp_path):
     with pytest.raises(pkg.UA3Error, match="no CPU fallback"):
         pkg.load_library(str(tmp_path / "nope.so"))
+
+
+def test_smeter_dbm_host_function(pkg):
+    """TRX_RX_dBm (stm32f4xx_it.c:398-407): 10*log10(P/1mW) of the RF input voltage derived from the S-meter extremes."""
+    import math
+    lib = pkg.load_library()
+    for mx, mn, g in [(30000.0, -30000.0, 50), (500.0, -480.0, 50), (5.0, -5.0, 20), (0.0, 0.0, 50)]:
+        vpp = (mx / g - mn / g) / 16.0
+        v = max(vpp / 4095.0 * 0.3535 / 4 * 0.2, 1e-7)
+        want = 10 * math.log10(v * v / 0.05)
+        got = lib.ua3reo_smeter_dbm(mx, mn, g)
+        assert abs(got - want) <= 1.5, (mx, mn, g, got, want)      # log10f_fast is a cubic fit, result truncated to int16

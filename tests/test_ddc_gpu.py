@@ -169,3 +169,24 @@ def test_async_frame_reads_overlap_pushes(pkg, oracle):
     got = np.concatenate([o.numpy() for o in outs], axis=1)
     rx.close()
     assert np.array_equal(got, oracle.golden_frames(adc, fcw))
+
+
+def test_adc_min_max_tracking(pkg, oracle):
+    """ADC_MIN / ADC_MAX of stm32_interface.v:384-397: +2000 / -2000 after a reset, running extremes afterwards."""
+    rx = pkg.Receiver(4, 1 << 15)
+    assert rx.adc_stats() == (2000, -2000, 0)            # first call arms the tracker with the FPGA's reset values
+    adc = oracle.synth_adc(1 << 15, seed=3)
+    adc[100] = 2047
+    adc[200] = -2048
+    rx.push(adc[:20000])
+    rx.push(adc[20000:])
+    n_proc = (adc.size // 1024) * 1024                   # only whole frames have been through the chain
+    seen = adc[:n_proc]
+    mn, mx, rail = rx.adc_stats(reset=True)
+    assert (mn, mx) == (int(seen.min()), int(seen.max()))
+    assert rail == int(((seen <= -2048) | (seen >= 2047)).sum())
+    assert rx.adc_stats() == (2000, -2000, 0)
+    small = np.full(2048, 5, np.int16)
+    rx.push(small)
+    assert rx.adc_stats() == (5, 5, 0)                   # min(2000, 5), max(-2000, 5)
+    rx.close()

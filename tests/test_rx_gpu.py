@@ -55,11 +55,15 @@ def _run_frames_through_gpu(pkg, oracle, cases, n_adc, pushes, seed):
     rx.rx_enable(True)
     rx.rx_set([rx.rx_defaults(**c) for c in cases])
     frames, audio, spec, off = [], [], [], 0
+    extra = {}
     for p in pushes:
         rx.push(adc[off:off + p]); off += p
         frames.append(rx.read_frames()); audio.append(rx.read_audio()); spec.append(rx.read_spectra())
+        extra.setdefault("waterfall", []).append(rx.read_waterfall())
+        extra.setdefault("cw", []).append(rx.read_cw())
     sm = rx.read_smeter()
     rx.close()
+    _run_frames_through_gpu.extra = {k: np.concatenate(v, 1) for k, v in extra.items()}
     return np.concatenate(frames, 1), np.concatenate(audio, 1), np.concatenate(spec, 1), sm
 
 
@@ -69,7 +73,7 @@ def test_against_reference_firmware_fixtures(pkg, oracle, golden):
     n_frames = meta["n_frames"]
     # same ADC recipe as tools/gen_golden_rx.py -> the GPU DDC must reproduce the fixture's frames bit-exactly
     keys = ("mode", "agc", "agc_speed", "dnr", "notch", "mute", "volume", "rf_gain", "fm_sql_threshold", "fft_enabled",
-            "fft_averaging", "fft_zoom", "iq_swap", "filter_width", "ssb_hpf_pass", "notch_fc")
+            "fft_averaging", "fft_zoom", "iq_swap", "cw_decoder", "filter_width", "ssb_hpf_pass", "notch_fc")
     frames, audio, spec, sm = _run_frames_through_gpu(
         pkg, oracle, [{k: c["settings"][k] for k in keys} for c in cases], 1024 * n_frames, [1024 * n_frames], 20261018)
     assert np.array_equal(frames[0], z["frames"]), "GPU DDC frames differ from the fixture's golden frames"
@@ -84,6 +88,12 @@ def test_against_reference_firmware_fixtures(pkg, oracle, golden):
             check(spec[i], rs, c["name"] + " spectrum")
         rsm = z[c["name"] + "/smeter"][-1]
         assert np.allclose(sm[i], rsm, rtol=1e-5, atol=1e-3), c["name"] + " s-meter"
+        # next rows of SURVEY.md 8(f): waterfall colour rows (display half of fft.c) and the CW Goertzel front end
+        if c["settings"]["fft_enabled"]:
+            wf, rwf = _run_frames_through_gpu.extra["waterfall"][i], z[c["name"] + "/waterfall"]
+            assert (wf != rwf).mean() <= 0.01, c["name"] + " waterfall row"      # a height on a rounding edge may flip one column
+        cwm, rcw = _run_frames_through_gpu.extra["cw"][i], z[c["name"] + "/cw"]
+        assert np.allclose(cwm, rcw, rtol=1e-5, atol=1e-4), c["name"] + " CW Goertzel magnitude"
     # SSB/CW/DIGI/IQ/AM use only IEEE +,-,*,/,sqrt: those channels are expected to be bit-identical
     assert exact >= len(cases) - 3, "only %d of %d cases bit-exact" % (exact, len(cases))
 

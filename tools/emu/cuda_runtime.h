@@ -115,3 +115,8 @@ static inline cudaError_t cudaMemset2DAsync(void* p, size_t pitch, int v, size_t
     for (size_t i = 0; i < h; ++i) memset((char*)p + i * pitch, v, w);
     return 0;
 }
+#include <mutex>
+static std::mutex ua3_emu_atomic_mutex;
+static inline int atomicMin(int* p, int v) { std::lock_guard<std::mutex> g(ua3_emu_atomic_mutex); int o = *p; if (v < o) *p = v; return o; }
+static inline int atomicMax(int* p, int v) { std::lock_guard<std::mutex> g(ua3_emu_atomic_mutex); int o = *p; if (v > o) *p = v; return o; }
+static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { std::lock_guard<std::mutex> g(ua3_emu_atomic_mutex); uint32_t o = *p; *p = o + v; return o; }

@@ -30,9 +30,11 @@ CASES = [
     dict(name="usb_mute_fftavg1", settings=dict(mode=1, mute=1, fft_averaging=1)),
     dict(name="lsb_lpf_off_agcfast", settings=dict(mode=0, filter_width=0, agc_speed=10)),
     dict(name="usb_fft_off", settings=dict(mode=1, fft_enabled=0)),
+    dict(name="cw_u_decoder", settings=dict(mode=4, filter_width=500, cw_decoder=1)),
+    dict(name="usb_strong_rf_gain", settings=dict(mode=1, rf_gain=250, fft_averaging=2)),
 ]
 DEFAULTS = dict(mode=0, agc=1, agc_speed=3, dnr=0, notch=0, mute=0, volume=20, rf_gain=50, fm_sql_threshold=1, fft_enabled=1,
-                fft_averaging=4, fft_zoom=1, iq_swap=0, filter_width=2700, ssb_hpf_pass=300, notch_fc=1000)
+                fft_averaging=4, fft_zoom=1, iq_swap=0, cw_decoder=0, filter_width=2700, ssb_hpf_pass=300, notch_fc=1000)
 
 
 def make_frames(seed, n_frames):
@@ -61,7 +63,7 @@ def main():
     for c in CASES:
         s = {**DEFAULTS, **c["settings"]}
         r = pyoracle.run_fw_rx(frames, s)
-        for k in ("audio", "smeter", "spectra", "waterfall", "fft_max"):
+        for k in ("audio", "smeter", "cw", "spectra", "waterfall", "fft_max"):
             out[c["name"] + "/" + k] = r[k]
         print("%-28s audio %s spectra %s  rms L %.1f" % (c["name"], r["audio"].shape, r["spectra"].shape,
                                                          r["audio"][:, 0::2].astype(float).std()))

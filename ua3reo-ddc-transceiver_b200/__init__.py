@@ -53,12 +53,13 @@ class RxSettings(ctypes.Structure):
     _fields_ = [("mode", ctypes.c_uint8), ("agc", ctypes.c_uint8), ("agc_speed", ctypes.c_uint8), ("dnr", ctypes.c_uint8),
                 ("notch", ctypes.c_uint8), ("mute", ctypes.c_uint8), ("volume", ctypes.c_uint8), ("rf_gain", ctypes.c_uint8),
                 ("fm_sql_threshold", ctypes.c_uint8), ("fft_enabled", ctypes.c_uint8), ("fft_averaging", ctypes.c_uint8),
-                ("fft_zoom", ctypes.c_uint8), ("iq_swap", ctypes.c_uint8), ("reserved", ctypes.c_uint8 * 3),
+                ("fft_zoom", ctypes.c_uint8), ("iq_swap", ctypes.c_uint8), ("cw_decoder", ctypes.c_uint8),
+                ("reserved", ctypes.c_uint8 * 2),
                 ("filter_width", ctypes.c_uint16), ("ssb_hpf_pass", ctypes.c_uint16), ("notch_fc", ctypes.c_uint16),
                 ("reserved2", ctypes.c_uint16)]
 
     FIELDS = ("mode", "agc", "agc_speed", "dnr", "notch", "mute", "volume", "rf_gain", "fm_sql_threshold", "fft_enabled",
-              "fft_averaging", "fft_zoom", "iq_swap", "filter_width", "ssb_hpf_pass", "notch_fc")
+              "fft_averaging", "fft_zoom", "iq_swap", "cw_decoder", "filter_width", "ssb_hpf_pass", "notch_fc")
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k in self.FIELDS}
@@ -91,6 +92,10 @@ def _bind(lib):
         "ua3reo_rx_read_audio": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_spectra": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_smeter": (c.c_int, [vp, vp, c.c_int]),
+        "ua3reo_rx_read_waterfall": (c.c_int, [vp, vp, sz]),
+        "ua3reo_rx_read_cw": (c.c_int, [vp, vp, sz]),
+        "ua3reo_adc_stats": (c.c_int, [vp, c.POINTER(c.c_int16), c.POINTER(c.c_int16), c.POINTER(u32), c.c_int]),
+        "ua3reo_smeter_dbm": (c.c_int16, [c.c_float, c.c_float, c.c_uint8]),
         "ua3reo_duc_enable": (c.c_int, [vp, u32]),
         "ua3reo_duc_push": (c.c_int, [vp, vp, sz]),
         "ua3reo_duc_read_dac": (c.c_int, [vp, vp, sz]),
@@ -268,6 +273,25 @@ class Receiver:
         ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
         self._chk(self.lib.ua3reo_rx_read_spectra(self._h, ptr, nf))
         return out
+
+    def read_waterfall(self):
+        """uint16 [n_channels, fft_frames_of_last_push, 256]: RGB565 waterfall rows (fft-shifted)."""
+        _, nf = self.rx_counts()
+        out = np.empty((self.n_channels, nf, FFT_BINS), np.uint16)
+        self._chk(self.lib.ua3reo_rx_read_waterfall(self._h, out.ctypes.data, nf))
+        return out
+
+    def read_cw(self):
+        """float32 [n_channels, blocks_of_last_push]: Goertzel magnitude of the CW decoder front end."""
+        nb, _ = self.rx_counts()
+        out = np.empty((self.n_channels, nb), np.float32)
+        self._chk(self.lib.ua3reo_rx_read_cw(self._h, out.ctypes.data, nb))
+        return out
+
+    def adc_stats(self, reset=False):
+        mn, mx, nr = ctypes.c_int16(), ctypes.c_int16(), ctypes.c_uint32()
+        self._chk(self.lib.ua3reo_adc_stats(self._h, ctypes.byref(mn), ctypes.byref(mx), ctypes.byref(nr), 1 if reset else 0))
+        return int(mn.value), int(mx.value), int(nr.value)
 
     def read_smeter(self, reset=False):
         out = np.empty((self.n_channels, 2), np.float32)

@@ -66,6 +66,8 @@ struct ua3reo_ctx {
     std::vector<ua3reo_rx_settings> h_set;
     std::vector<RxParams> h_par;
     uint8_t* rx_flags = nullptr;        // device scratch for rx_set's state-clear flags
+    int32_t* adc_stats = nullptr;       // device: min, max, samples at the rails (since the last reset)
+    bool adc_stats_on = false;
     size_t last_audio_blocks = 0, last_fft_frames = 0;
     // transmit DUC
     bool duc_alloc = false;
@@ -291,6 +293,8 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
     int launches = 0;
     cudaEvent_t* ev = nullptr;
     if (n_proc && c->prof_used < c->prof_cap) ev = c->prof_ev.data() + (size_t)(c->prof_used++) * (kDdcKernels + 1);
+    if (n_proc && c->adc_stats_on)
+        UA3_CUDA(adc_stats_launch(proc_src, n_proc, c->adc_stats, c->sm_count, c->stream, &launches));
     if (n_proc)
         UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, (uint32_t)(c->w_pos & c->b.ring_mask), c->sm_count, c->stream,
                                   &launches, ev));
@@ -409,11 +413,15 @@ static int rx_allocate(ua3reo_ctx* c) {
     UA3_CUDA(dev_alloc(c, &r.state, (size_t)c->n_ch));
     UA3_CUDA(dev_alloc(c, &r.audio_out, (size_t)c->n_ch * r.audio_ch_stride));
     UA3_CUDA(dev_alloc(c, &r.spectra, (size_t)c->n_ch * r.spec_ch_stride));
+    UA3_CUDA(dev_alloc(c, &r.waterfall, (size_t)c->n_ch * r.spec_ch_stride));
+    UA3_CUDA(dev_alloc(c, &r.cw_mag, (size_t)c->n_ch * r.max_audio_blocks));
     UA3_CUDA(dev_alloc(c, &c->rx_flags, (size_t)c->n_ch));
     std::vector<float> win(kFftSize), tw(2 * kFftSize);
     rx_build_window(win.data());
     rx_build_twiddles(tw.data());
-    UA3_CUDA(rx_upload_constants(win.data(), tw.data()));
+    uint16_t colors[32];
+    rx_build_colors(colors);
+    UA3_CUDA(rx_upload_constants(win.data(), tw.data(), colors));
     int launches = 0;
     UA3_CUDA(rx_launch_init_state(r, c->stream, &launches));
     c->launches += (uint64_t)launches;
@@ -503,6 +511,77 @@ int ua3reo_rx_read_spectra(ua3reo_ctx* c, float* dst, size_t n_frames) {
                                    cudaMemcpyDeviceToHost, c->stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
     return UA3_OK;
+}
+
+int ua3reo_rx_read_waterfall(ua3reo_ctx* c, uint16_t* dst, size_t n_frames) {
+    if (!c || (!dst && n_frames)) return fail(UA3_E_INVAL, "ua3reo_rx_read_waterfall: null argument");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_waterfall: STM32 stage not enabled");
+    if (n_frames != c->last_fft_frames) return fail(UA3_E_INVAL, "ua3reo_rx_read_waterfall: n_frames != FFT frames of last push");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t row = n_frames * UA3_FFT_BINS * sizeof(uint16_t);
+    if (n_frames)
+        UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.waterfall, (size_t)c->rx.spec_ch_stride * sizeof(uint16_t), row, c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_rx_read_cw(ua3reo_ctx* c, float* dst, size_t n_blocks) {
+    if (!c || (!dst && n_blocks)) return fail(UA3_E_INVAL, "ua3reo_rx_read_cw: null argument");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_cw: STM32 stage not enabled");
+    if (n_blocks != c->last_audio_blocks) return fail(UA3_E_INVAL, "ua3reo_rx_read_cw: n_blocks != blocks of last push");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t row = n_blocks * sizeof(float);
+    if (n_blocks)
+        UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.cw_mag, (size_t)c->rx.max_audio_blocks * sizeof(float), row, c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+static int adc_stats_reset(ua3reo_ctx* c) {
+    const int32_t init[3] = {2000, -2000, 0};          // stm32_interface.v:385-389
+    UA3_CUDA(cudaMemcpyAsync(c->adc_stats, init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_adc_stats(ua3reo_ctx* c, int16_t* adc_min, int16_t* adc_max, uint32_t* n_rail, int reset) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    UA3_CUDA(cudaSetDevice(c->device));
+    if (!c->adc_stats) {
+        UA3_CUDA(dev_alloc(c, &c->adc_stats, 4));
+        const int rc = adc_stats_reset(c);
+        if (rc != UA3_OK) return rc;
+        c->adc_stats_on = true;                        // tracking starts with the first call
+    }
+    int32_t h[3];
+    UA3_CUDA(cudaMemcpyAsync(h, c->adc_stats, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    if (adc_min) *adc_min = (int16_t)h[0];
+    if (adc_max) *adc_max = (int16_t)h[1];
+    if (n_rail) *n_rail = (uint32_t)h[2];
+    return reset ? adc_stats_reset(c) : UA3_OK;
+}
+
+int16_t ua3reo_smeter_dbm(float sample_max, float sample_min, uint8_t rf_gain) {
+    // stm32f4xx_it.c:398-407, settings.h:11,19-21 (ADC_BITS 12, FPGA_BUS_BITS 16, ADC_VREF 1.0, ratio 4, calibration 0.2)
+    float vpp = (sample_max / (float)rf_gain) - (sample_min / (float)rf_gain);
+    for (int i = 0; i < (16 - 12); i++) vpp = vpp / 2;
+    const float adc_vpp = vpp * 1.0f / ((float)std::pow(2.0, 12) - 1);
+    const float vrms = adc_vpp * 0.3535f;
+    float rf_in = (vrms / 4) * 0.2f;
+    if (rf_in < 0.0000001f) rf_in = 0.0000001f;
+    // log10f_fast (functions.c:247-262)
+    const float X = (rf_in * rf_in) / (50.0f * 0.001f);
+    int E;
+    const float F = std::frexp(std::fabs(X), &E);
+    float Y = 1.23149591368684f;
+    Y *= F; Y += -4.11852516267426f;
+    Y *= F; Y += 6.02197014179219f;
+    Y *= F; Y += -3.13396450166353f;
+    Y += E;
+    return (int16_t)(10 * (Y * 0.3010299956639812f));
 }
 
 int ua3reo_rx_read_smeter(ua3reo_ctx* c, float* dst, int reset) {

@@ -17,6 +17,7 @@ namespace ua3 {
 
 __constant__ float c_fft_window[kFftSize];
 __constant__ float c_fft_twiddle[2 * kFftSize];
+__constant__ uint16_t c_fft_colors[32];
 
 #if defined(UA3_HOST_EMU)
 #define UA3_FULL_MASK 0xffffffffu
@@ -53,7 +54,7 @@ UA3_D int16_t frame_word(uint64_t f, int w) {
 __global__ void __launch_bounds__(32)
 rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t frame_ch_stride, uint32_t start,
                 uint32_t n_blocks, const RxParams* __restrict__ params, RxState* __restrict__ state, uint32_t n_ch,
-                int32_t* __restrict__ audio_out, uint32_t out_ch_stride) {
+                int32_t* __restrict__ audio_out, uint32_t out_ch_stride, float* __restrict__ cw_mag, uint32_t cw_ch_stride) {
     __shared__ float s_buf[kAudioBlock][32];            // [sample][lane]: lane's own rail, conflict free
     __shared__ float s_win[kLmsTaps - 1 + kSubBlock][16];   // NLMS input window of the I lanes
 
@@ -253,6 +254,21 @@ rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_
                 for (int i = 0; i < kAudioBlock; ++i) s_buf[i][lane] = s_buf[i][lane] * agc_gain;
             }
         }
+        // ---------------- doCW_Decode (:437-443): Goertzel front end of CWDecoder_Process (cw_decoder.c:56-66) ------
+        if (live && rail == 0) {
+            float mag = 0.0f;
+            if (P.cw_on) {
+                float Q1 = 0.0f, Q2 = 0.0f;
+                const float coeff = P.cw_coeff;
+                for (int i = 0; i < kAudioBlock; ++i) {
+                    const float Q0 = ((coeff * Q1) - Q2) + s_buf[i][lane];
+                    Q2 = Q1; Q1 = Q0;
+                }
+                const float msq = ((Q1 * Q1) + (Q2 * Q2)) - ((Q1 * Q2) * coeff);
+                mag = sqrtf(msq);
+            }
+            cw_mag[(size_t)ch * cw_ch_stride + blk] = mag;
+        }
         __syncwarp();
         // ---------------- output: COPYCHANNEL, volume, float -> int32, L/R interleave (:365-394) ----
         if (live) {
@@ -331,7 +347,7 @@ UA3_D void radix8(C8& z) {
 __global__ void __launch_bounds__(32)
 rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t frame_ch_stride, uint32_t start,
               uint32_t n_frames, const RxParams* __restrict__ params, RxState* __restrict__ state, uint32_t n_ch,
-              float* __restrict__ spectra, uint32_t spec_ch_stride) {
+              float* __restrict__ spectra, uint32_t spec_ch_stride, uint16_t* __restrict__ waterfall) {
     __shared__ float s_re[kFftSize], s_im[kFftSize];
     const int lane = threadIdx.x & 31;
     const uint32_t ch = blockIdx.x;
@@ -454,6 +470,7 @@ rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t 
         // temporal averaging into FFTOutput_mean (:324-328) and the display pass's overflow count (:369-373)
         uint32_t nerr = 0;
         float* out = spectra + (size_t)ch * spec_ch_stride + (size_t)fi * kFftBins;
+        uint16_t* wf = waterfall + (size_t)ch * spec_ch_stride + (size_t)fi * kFftBins;
 #pragma unroll
         for (int q = 0; q < kFftBins / 32; ++q) {
             const int bin = q * 32 + lane;
@@ -466,6 +483,8 @@ rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t 
             // height = (uint16_t)(mean * FFT_MAX_HEIGHT); if (height > FFT_MAX_HEIGHT - 1) maxValueErrors++
             const uint32_t height = (uint32_t)(int32_t)(m * 30.0f) & 0xFFFFu;
             nerr += (height > 29u) ? 1u : 0u;
+            // FFT_printFFT (fft.c:361-379): colour of the column, stored fft-shifted
+            wf[bin ^ 128] = c_fft_colors[height > 29u ? 30u : height];
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nerr += __shfl_xor_sync(UA3_FULL_MASK, nerr, o);
@@ -500,16 +519,51 @@ cudaError_t rx_launch_init_state(const RxBuffers& b, cudaStream_t st, int* launc
     return cudaGetLastError();
 }
 
-cudaError_t rx_upload_constants(const float* window, const float* twiddle) {
+cudaError_t rx_upload_constants(const float* window, const float* twiddle, const uint16_t* colors) {
     cudaError_t e = cudaMemcpyToSymbol(c_fft_window, window, sizeof(float) * kFftSize);
     if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_fft_colors, colors, sizeof(uint16_t) * 32);
+    if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_fft_twiddle, twiddle, sizeof(float) * 2 * kFftSize);
+}
+
+// ------------------------------------------------------------------------------------------------
+// ADC_MIN / ADC_MAX tracking (stm32_interface.v:384-397) + samples at the rails, one reduction per ADC block
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adc_stats_kernel(const int16_t* __restrict__ adc, uint32_t n, int32_t* __restrict__ stats /* min, max, n_rail */) {
+    int32_t mn = 32767, mx = -32768;
+    uint32_t rail = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int32_t v = adc[i];
+        mn = min(mn, v); mx = max(mx, v);
+        rail += (v <= -2048 || v >= 2047) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        rail += __shfl_xor_sync(0xffffffffu, rail, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&stats[0], mn);
+        atomicMax(&stats[1], mx);
+        atomicAdd(reinterpret_cast<uint32_t*>(&stats[2]), rail);
+    }
+}
+
+cudaError_t adc_stats_launch(const int16_t* adc, uint32_t n, int32_t* stats, int sm_count, cudaStream_t st, int* launches) {
+    if (!n) return cudaSuccess;
+    const uint32_t grid = (uint32_t)min((uint64_t)(n + 255u) / 256u, (uint64_t)sm_count * 8);
+    UA3_LAUNCH(adc_stats_kernel, grid, 256, 0, st, adc, n, stats);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
 }
 
 cudaError_t rx_launch_audio(const RxBuffers& b, uint32_t start, uint32_t n_blocks, cudaStream_t st, int* launches) {
     if (!n_blocks) return cudaSuccess;
     UA3_LAUNCH(rx_audio_kernel, (b.n_ch + 15u) / 16u, 32, 0, st, b.frames, b.ring_mask, b.frame_ch_stride, start, n_blocks,
-               b.params, b.state, b.n_ch, b.audio_out, b.audio_ch_stride);
+               b.params, b.state, b.n_ch, b.audio_out, b.audio_ch_stride, b.cw_mag, b.max_audio_blocks);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }
@@ -517,7 +571,7 @@ cudaError_t rx_launch_audio(const RxBuffers& b, uint32_t start, uint32_t n_block
 cudaError_t rx_launch_fft(const RxBuffers& b, uint32_t start, uint32_t n_frames, cudaStream_t st, int* launches) {
     if (!n_frames) return cudaSuccess;
     UA3_LAUNCH(rx_fft_kernel, b.n_ch, 32, 0, st, b.frames, b.ring_mask, b.frame_ch_stride, start, n_frames, b.params,
-               b.state, b.n_ch, b.spectra, b.spec_ch_stride);
+               b.state, b.n_ch, b.spectra, b.spec_ch_stride, b.waterfall);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -14,11 +14,14 @@ struct RxBuffers {
     RxState* state = nullptr;           // [n_ch]
     int32_t* audio_out = nullptr;       // [n_ch][max_audio_blocks][384]
     uint32_t audio_ch_stride = 0, max_audio_blocks = 0;
+    float* cw_mag = nullptr;            // [n_ch][max_audio_blocks] Goertzel magnitude (CW decoder front end)
     float* spectra = nullptr;           // [n_ch][max_fft_frames][256]
+    uint16_t* waterfall = nullptr;      // [n_ch][max_fft_frames][256] RGB565 rows, fft-shifted
     uint32_t spec_ch_stride = 0, max_fft_frames = 0;
 };
 
-cudaError_t rx_upload_constants(const float* window, const float* twiddle);
+cudaError_t rx_upload_constants(const float* window, const float* twiddle, const uint16_t* colors);
+cudaError_t adc_stats_launch(const int16_t* adc, uint32_t n, int32_t* stats, int sm_count, cudaStream_t st, int* launches);
 cudaError_t rx_launch_audio(const RxBuffers& b, uint32_t start, uint32_t n_blocks, cudaStream_t st, int* launches);
 cudaError_t rx_launch_fft(const RxBuffers& b, uint32_t start, uint32_t n_frames, cudaStream_t st, int* launches);
 cudaError_t rx_launch_clear(const RxBuffers& b, const uint8_t* flags_dev, uint32_t first, uint32_t n, cudaStream_t st,

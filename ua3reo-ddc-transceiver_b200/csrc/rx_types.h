@@ -28,12 +28,14 @@ struct RxParams {
     uint8_t mode, agc_on, dnr_on, notch_on, mute, iq_swap, fm_sql_threshold, fft_enabled;
     uint8_t lpf_on;          // Filter_Width > 0 (audio_processor.c:448)
     uint8_t hpf_set;         // HPF coefficients have been initialised at least once
-    uint8_t pad[2];
+    uint8_t cw_on;           // TRX.CWDecoder && mode is CW_L / CW_U (audio_processor.c:437-443)
+    uint8_t pad[1];
     float rf_gain;           // (float)TRX.RF_Gain
     float volume;            // (float)TRX.Volume / 100.0f
     float agc_step_up;       // 500.0f / Agc_speed (agc.c:17)
     float agc_step_down;     // step_up / 10.0f   (agc.c:18)
     float fft_averaging;     // (float)TRX.FFT_Averaging
+    float cw_coeff;          // Goertzel coefficient 2*cos(omega) of CWDecoder_Init (cw_decoder.c:43-54)
     // lattice coefficients, TOP-PADDED with zero stages to the maximum stage count: a stage with
     // k = v = 0 leaves f and the accumulator bit-identical, so 7-stage filters run in the 11-stage loop.
     float lpf_k[kLpfMax];
