@@ -365,10 +365,10 @@ class Receiver:
         self._chk(self.lib.ua3reo_profile_begin(self._h, int(max_blocks)))
 
     def profile_end(self):
-        ms = (ctypes.c_double * 5)()
+        ms = (ctypes.c_double * 7)()
         nb = ctypes.c_uint32(0)
-        self._chk(self.lib.ua3reo_profile_end(self._h, ms, 5, ctypes.byref(nb)))
-        names = ["front", "cic", "comp", "hilb", "rotate"]
+        self._chk(self.lib.ua3reo_profile_end(self._h, ms, 7, ctypes.byref(nb)))
+        names = ["front", "cic", "comp", "hilb", "rotate", "rx_audio", "rx_fft"]
         return {k: float(v) for k, v in zip(names, ms)}, int(nb.value)
 
     def launch_count(self):

@@ -16,6 +16,7 @@
 using namespace ua3;
 #include "rx_host.cpp.inc"
 
+static constexpr int kProfEvents = kDdcKernels + 3;   // 5 DDC kernels, rx_audio, rx_fft: 8 event points per block
 static thread_local std::string g_err;
 
 static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -292,7 +293,7 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
     }
     int launches = 0;
     cudaEvent_t* ev = nullptr;
-    if (n_proc && c->prof_used < c->prof_cap) ev = c->prof_ev.data() + (size_t)(c->prof_used++) * (kDdcKernels + 1);
+    if (n_proc && c->prof_used < c->prof_cap) ev = c->prof_ev.data() + (size_t)(c->prof_used++) * kProfEvents;
     if (n_proc && c->adc_stats_on)
         UA3_CUDA(adc_stats_launch(proc_src, n_proc, c->adc_stats, c->sm_count, c->stream, &launches));
     if (n_proc)
@@ -304,13 +305,16 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
         const uint32_t nb = (uint32_t)((c->w_pos - c->a_pos) / UA3_AUDIO_BLOCK);
         const uint32_t nf = (uint32_t)((c->w_pos - c->f_pos) / UA3_FFT_SIZE);
         UA3_CUDA(rx_launch_audio(c->rx, (uint32_t)(c->a_pos & c->b.ring_mask), nb, c->stream, &launches));
+        if (ev) cudaEventRecord(ev[kDdcKernels + 1], c->stream);
         UA3_CUDA(rx_launch_fft(c->rx, (uint32_t)(c->f_pos & c->b.ring_mask), nf, c->stream, &launches));
+        if (ev) cudaEventRecord(ev[kDdcKernels + 2], c->stream);
         c->a_pos += (uint64_t)nb * UA3_AUDIO_BLOCK;
         c->f_pos += (uint64_t)nf * UA3_FFT_SIZE;
         c->last_audio_blocks = nb;
         c->last_fft_frames = nf;
     } else {
         c->a_pos = c->f_pos = c->w_pos;
+        if (ev) { cudaEventRecord(ev[kDdcKernels + 1], c->stream); cudaEventRecord(ev[kDdcKernels + 2], c->stream); }
     }
     c->launches += (uint64_t)launches;
     UA3_CUDA(cudaEventRecord(c->ev_push, c->stream));
@@ -794,7 +798,7 @@ int ua3reo_tx_feed_duc(ua3reo_ctx* c) {
 int ua3reo_profile_begin(ua3reo_ctx* c, uint32_t max_blocks) {
     if (!c) return fail(UA3_E_INVAL, "null context");
     UA3_CUDA(cudaSetDevice(c->device));
-    while (c->prof_ev.size() < (size_t)max_blocks * (kDdcKernels + 1)) {
+    while (c->prof_ev.size() < (size_t)max_blocks * kProfEvents) {
         cudaEvent_t e;
         UA3_CUDA(cudaEventCreate(&e));
         c->prof_ev.push_back(e);
@@ -810,9 +814,9 @@ int ua3reo_profile_end(ua3reo_ctx* c, double* kernel_ms, uint32_t n_kernels, uin
     UA3_CUDA(cudaStreamSynchronize(c->stream));
     for (uint32_t k = 0; k < n_kernels; ++k) kernel_ms[k] = 0.0;
     for (uint32_t b = 0; b < c->prof_used; ++b)
-        for (uint32_t k = 0; k < (uint32_t)kDdcKernels && k < n_kernels; ++k) {
+        for (uint32_t k = 0; k < (uint32_t)kProfEvents - 1 && k < n_kernels; ++k) {
             float ms = 0.f;
-            const cudaEvent_t* ev = c->prof_ev.data() + (size_t)b * (kDdcKernels + 1);
+            const cudaEvent_t* ev = c->prof_ev.data() + (size_t)b * kProfEvents;
             UA3_CUDA(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
             kernel_ms[k] += (double)ms;
         }

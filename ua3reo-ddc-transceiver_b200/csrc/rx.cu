@@ -57,6 +57,7 @@ rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_
                 int32_t* __restrict__ audio_out, uint32_t out_ch_stride, float* __restrict__ cw_mag, uint32_t cw_ch_stride) {
     __shared__ float s_buf[kAudioBlock][32];            // [sample][lane]: lane's own rail, conflict free
     __shared__ float s_win[kLmsTaps - 1 + kSubBlock][16];   // NLMS input window of the I lanes
+    __shared__ float s_ref[2 * kSubBlock][16];              // lms2_reference of the I lanes
 
     const int lane = threadIdx.x & 31, pair = lane >> 1, rail = lane & 1;
     const uint32_t ch_raw = blockIdx.x * 16u + (uint32_t)pair;
@@ -104,18 +105,23 @@ rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_
     for (int i = 0; i < kLmsTaps; ++i) w[i] = S.lms_w[i];
     float lms_energy = S.lms_energy, lms_x0 = S.lms_x0;
     uint32_t idx_old = S.lms_idx_old, idx_new = S.lms_idx_new;
-    if (rail == 0)
+    if (rail == 0) {
         for (int i = 0; i < kLmsTaps - 1; ++i) s_win[i][pair] = S.lms_hist[i];
+        if (P.dnr_on) for (int i = 0; i < 2 * kSubBlock; ++i) s_ref[i][pair] = S.lms_ref[i];
+    }
 
     const uint64_t* fr = frames + (size_t)ch * frame_ch_stride;
 
     for (uint32_t blk = 0; blk < n_blocks; ++blk) {
         const uint32_t base = start + blk * (uint32_t)kAudioBlock;
         float angle0 = 0.0f;
+        // ---------------- pass 0: the lane's 192 input words -> shared memory (independent loads, many in flight) ----
+#pragma unroll 8
+        for (int i = 0; i < kAudioBlock; ++i)
+            s_buf[i][lane] = (float)frame_word(__ldg(fr + ((base + (uint32_t)i) & ring_mask)), widx);   // int16 -> float32 (fpga.c:303-385)
         // ---------------- pass 1: per-sample chain up to NOTCH + SMETER -----------------------------
         for (int i = 0; i < kAudioBlock; ++i) {
-            const uint64_t f = fr[(base + (uint32_t)i) & ring_mask];
-            float x = (float)frame_word(f, widx);                    // int16 -> float32 (fpga.c:303-385)
+            float x = s_buf[i][lane];
             {   // dc_filter (audio_filters.c:358-373)
                 const float delta_x = x - dc_x;
                 const float a1_y_prev = A1 * dc_y;
@@ -199,7 +205,7 @@ rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_
                 // arm_copy_f32(bufferIn, &lms2_reference[reference_index_new], 64)
                 for (int n = 0; n < kSubBlock; ++n) {
                     const float v = s_buf[sb * kSubBlock + n][lane];
-                    S.lms_ref[idx_new + n] = v;
+                    s_ref[idx_new + n][pair] = v;
                     s_win[kLmsTaps - 1 + n][pair] = v;
                 }
                 for (int n = 0; n < kSubBlock; ++n) {                // arm_lms_norm_f32
@@ -213,7 +219,7 @@ rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_
 #pragma unroll
                     for (int t = 0; t < kLmsTaps; ++t) acc += win[t] * w[t];
                     s_buf[sb * kSubBlock + n][lane] = acc;           // output = prediction, in place
-                    const float e = S.lms_ref[idx_old + n] - acc;
+                    const float e = s_ref[idx_old + n][pair] - acc;
                     const float wg = (e * 0.000001f) / (lms_energy + 0.000000119209289f);
 #pragma unroll
                     for (int t = 0; t < kLmsTaps; ++t) w[t] += wg * win[t];
@@ -299,6 +305,7 @@ rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_
 #pragma unroll
             for (int i = 0; i < kLmsTaps; ++i) S.lms_w[i] = w[i];
             for (int i = 0; i < kLmsTaps - 1; ++i) S.lms_hist[i] = s_win[i][pair];
+            if (P.dnr_on) for (int i = 0; i < 2 * kSubBlock; ++i) S.lms_ref[i] = s_ref[i][pair];
             S.lms_energy = lms_energy; S.lms_x0 = lms_x0;
             S.lms_idx_old = idx_old; S.lms_idx_new = idx_new;
         }
@@ -361,16 +368,22 @@ rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t 
 
     for (uint32_t fi = 0; fi < n_frames; ++fi) {
         const uint32_t base = start + fi * (uint32_t)kFftSize;
+        // all lanes: the frame's SPEC words -> shared memory (FFT_buff filling of fpga.c:305-341, with the I/Q swap)
+        for (int i = lane; i < kFftSize; i += 32) {
+            const uint64_t f = __ldg(fr + ((base + (uint32_t)i) & ring_mask));
+            s_re[i] = (float)frame_word(f, swap ? 0 : 1);
+            s_im[i] = (float)frame_word(f, swap ? 1 : 0);
+        }
+        __syncwarp();
         // lanes 0/1: dc_filter(FFTInput_I, 512, 4) / dc_filter(FFTInput_Q, 512, 5) and the optional notch (:225-233)
         if (lane < 2) {
             const int rail = lane;                                    // 0 = I, 1 = Q
-            const int widx = (rail == 0) != (swap != 0) ? 1 : 0;      // SPEC_I is word 1, SPEC_Q word 0 (fpga.c:305-341)
             float dx = S.dc_x[4 + rail], dy = S.dc_y[4 + rail];
             float d1 = S.notch_fft_d[rail][0], d2 = S.notch_fft_d[rail][1];
             const float b0 = P.notch[0], b1 = P.notch[1], b2 = P.notch[2], a1 = P.notch[3], a2 = P.notch[4];
             float* dst = rail == 0 ? s_re : s_im;
             for (int i = 0; i < kFftSize; ++i) {
-                float x = (float)frame_word(fr[(base + (uint32_t)i) & ring_mask], widx);
+                float x = dst[i];
                 const float delta_x = x - dx;
                 const float a1y = A1 * dy;
                 const float y = delta_x + a1y;
