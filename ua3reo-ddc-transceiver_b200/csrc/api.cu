@@ -5,6 +5,7 @@
 #include "duc_launch.h"
 #include "tx_launch.h"
 #include "ua3_common.cuh"
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -404,6 +405,20 @@ void ua3reo_rx_defaults(ua3reo_rx_settings* s) {
     s->filter_width = 2700; s->ssb_hpf_pass = 300; s->notch_fc = 1000;
 }
 
+// slot -> channel permutation that groups channels taking the same branches of rx_audio_kernel (stable sort)
+static int rx_upload_order(ua3reo_ctx* c) {
+    std::vector<uint32_t> order(c->n_ch);
+    for (uint32_t i = 0; i < c->n_ch; ++i) order[i] = i;
+    auto key = [&](uint32_t ch) {
+        const RxParams& p = c->h_par[ch];
+        return ((uint32_t)p.mode << 8) | ((uint32_t)p.dnr_on << 2) | ((uint32_t)p.notch_on << 1) | (uint32_t)p.cw_on;
+    };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+    UA3_CUDA(cudaMemcpyAsync(c->rx.order, order.data(), sizeof(uint32_t) * c->n_ch, cudaMemcpyHostToDevice, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
 static int rx_allocate(ua3reo_ctx* c) {
     if (c->rx_alloc) return UA3_OK;
     RxBuffers& r = c->rx;
@@ -415,6 +430,7 @@ static int rx_allocate(ua3reo_ctx* c) {
     r.spec_ch_stride = r.max_fft_frames * UA3_FFT_BINS;
     UA3_CUDA(dev_alloc(c, &r.params, (size_t)c->n_ch));
     UA3_CUDA(dev_alloc(c, &r.state, (size_t)c->n_ch));
+    UA3_CUDA(dev_alloc(c, &r.order, (size_t)c->n_ch));
     UA3_CUDA(dev_alloc(c, &r.audio_out, (size_t)c->n_ch * r.audio_ch_stride));
     UA3_CUDA(dev_alloc(c, &r.spectra, (size_t)c->n_ch * r.spec_ch_stride));
     UA3_CUDA(dev_alloc(c, &r.waterfall, (size_t)c->n_ch * r.spec_ch_stride));
@@ -441,6 +457,8 @@ static int rx_allocate(ua3reo_ctx* c) {
     }
     UA3_CUDA(cudaMemcpyAsync(r.params, c->h_par.data(), sizeof(RxParams) * c->n_ch, cudaMemcpyHostToDevice, c->stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
+    const int rc = rx_upload_order(c);
+    if (rc != UA3_OK) return rc;
     c->rx_alloc = true;
     return UA3_OK;
 }
@@ -481,7 +499,7 @@ int ua3reo_rx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_rx_set
     UA3_CUDA(rx_launch_clear(c->rx, c->rx_flags, first, n, c->stream, &launches));
     c->launches += (uint64_t)launches;
     UA3_CUDA(cudaStreamSynchronize(c->stream));
-    return UA3_OK;
+    return rx_upload_order(c);
 }
 
 int ua3reo_rx_counts(ua3reo_ctx* c, size_t* audio_blocks, size_t* fft_frames) {

@@ -54,15 +54,19 @@ UA3_D int16_t frame_word(uint64_t f, int w) {
 __global__ void __launch_bounds__(32)
 rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t frame_ch_stride, uint32_t start,
                 uint32_t n_blocks, const RxParams* __restrict__ params, RxState* __restrict__ state, uint32_t n_ch,
-                int32_t* __restrict__ audio_out, uint32_t out_ch_stride, float* __restrict__ cw_mag, uint32_t cw_ch_stride) {
+                int32_t* __restrict__ audio_out, uint32_t out_ch_stride, float* __restrict__ cw_mag, uint32_t cw_ch_stride,
+                const uint32_t* __restrict__ order) {
     __shared__ float s_buf[kAudioBlock][32];            // [sample][lane]: lane's own rail, conflict free
     __shared__ float s_win[kLmsTaps - 1 + kSubBlock][16];   // NLMS input window of the I lanes
     __shared__ float s_ref[2 * kSubBlock][16];              // lms2_reference of the I lanes
 
     const int lane = threadIdx.x & 31, pair = lane >> 1, rail = lane & 1;
-    const uint32_t ch_raw = blockIdx.x * 16u + (uint32_t)pair;
-    const bool live = ch_raw < n_ch;
-    const uint32_t ch = live ? ch_raw : (n_ch - 1u);    // dead pairs shadow the last channel and never store
+    // Channels are visited in the host-built order that groups equal (mode, DNR, notch) settings, so that the
+    // 16 channels of a warp take the same branches (mode is per-channel data; without the grouping a warp with
+    // mixed modes executes every demodulator for every sample).
+    const uint32_t slot = blockIdx.x * 16u + (uint32_t)pair;
+    const bool live = slot < n_ch;
+    const uint32_t ch = order[live ? slot : (n_ch - 1u)];   // dead pairs shadow the last slot's channel and never store
     const RxParams& P = params[ch];
     RxState& S = state[ch];
 
@@ -576,7 +580,7 @@ cudaError_t adc_stats_launch(const int16_t* adc, uint32_t n, int32_t* stats, int
 cudaError_t rx_launch_audio(const RxBuffers& b, uint32_t start, uint32_t n_blocks, cudaStream_t st, int* launches) {
     if (!n_blocks) return cudaSuccess;
     UA3_LAUNCH(rx_audio_kernel, (b.n_ch + 15u) / 16u, 32, 0, st, b.frames, b.ring_mask, b.frame_ch_stride, start, n_blocks,
-               b.params, b.state, b.n_ch, b.audio_out, b.audio_ch_stride, b.cw_mag, b.max_audio_blocks);
+               b.params, b.state, b.n_ch, b.audio_out, b.audio_ch_stride, b.cw_mag, b.max_audio_blocks, b.order);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -12,6 +12,7 @@ struct RxBuffers {
     uint32_t ring_mask = 0, frame_ch_stride = 0;
     RxParams* params = nullptr;         // [n_ch]
     RxState* state = nullptr;           // [n_ch]
+    uint32_t* order = nullptr;          // [n_ch] channel visited by slot i: groups equal settings into the same warp
     int32_t* audio_out = nullptr;       // [n_ch][max_audio_blocks][384]
     uint32_t audio_ch_stride = 0, max_audio_blocks = 0;
     float* cw_mag = nullptr;            // [n_ch][max_audio_blocks] Goertzel magnitude (CW decoder front end)
