@@ -162,7 +162,6 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     b.max_chunks = max_block_samples / kCicR;
     b.max_frames = max_block_samples / kFrameAdc;
     b.l_ch_stride = (kLHalo + b.max_chunks) * kLRec;
-    b.u_rail_stride = (kUHalo + b.max_chunks + 7u) & ~7u;
     b.yi_stride = (kYIHalo + b.max_frames + 7u) & ~7u;
     b.yq_stride = (kYQHalo + b.max_frames + 7u) & ~7u;
     uint32_t ring = 1024;
@@ -183,7 +182,6 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     UA3_TRY(dev_alloc(c, &b.fcw, c->n_ch_pad));
     UA3_TRY(dev_alloc(c, &b.phase, c->n_ch_pad));
     UA3_TRY(dev_alloc(c, &b.L, (size_t)c->n_ch_pad * b.l_ch_stride));
-    UA3_TRY(dev_alloc(c, &b.U, (size_t)c->n_ch_pad * 2 * b.u_rail_stride));
     UA3_TRY(dev_alloc(c, &b.YI, (size_t)c->n_ch_pad * b.yi_stride));
     UA3_TRY(dev_alloc(c, &b.YQ, (size_t)c->n_ch_pad * b.yq_stride));
     UA3_TRY(dev_alloc(c, &b.frames, (size_t)c->n_ch * b.frame_ch_stride));
@@ -212,7 +210,6 @@ int ua3reo_reset(ua3reo_ctx* c) {
     const DdcBuffers& b = c->b;
     UA3_CUDA(cudaMemsetAsync(b.phase, 0, sizeof(uint32_t) * c->n_ch_pad, c->stream));
     UA3_CUDA(cudaMemsetAsync(b.L, 0, sizeof(uint64_t) * (size_t)c->n_ch_pad * b.l_ch_stride, c->stream));
-    UA3_CUDA(cudaMemsetAsync(b.U, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * 2 * b.u_rail_stride, c->stream));
     UA3_CUDA(cudaMemsetAsync(b.YI, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * b.yi_stride, c->stream));
     UA3_CUDA(cudaMemsetAsync(b.YQ, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * b.yq_stride, c->stream));
     c->carry = 0; c->last_frames = 0; c->pushed = false;

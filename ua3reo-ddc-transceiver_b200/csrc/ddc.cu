@@ -3,10 +3,10 @@
 // Launch sequence per ADC block of n = 512*M samples (M even), all on one stream:
 //   ddc_front_kernel   : ADC tile -> shared memory once per CTA, 32 channels x 8 chunks per tile,
 //                        one warp per chunk, lane = channel; writes chunk partial states L
-//   ddc_cic_kernel     : L (5-chunk window) -> 96 kHz CIC outputs U (int16)
-//   ddc_comp_kernel    : U (65-tap window) -> 48 kHz compensator outputs YI/YQ (int16)
+//   ddc_ciccomp_kernel : L (5-chunk comb window) -> 96 kHz CIC outputs (shared memory only) -> 65-tap compensator
+//                        -> 48 kHz outputs YI/YQ (int16)
 //   ddc_hilb_kernel    : YI (256-tap window), YQ (130 delay) -> 8-byte frames
-//   ddc_rotate_kernel  : move the tails of L/U/YI/YQ into their halos, advance the NCO phases
+//   ddc_rotate_kernel  : move the tails of L/YI/YQ into their halos, advance the NCO phases
 #include "ddc_launch.h"
 #include "ddc_front.cuh"
 #include "ddc_back.cuh"
@@ -197,35 +197,42 @@ ddc_front_bt_kernel(const int16_t* __restrict__ adc, uint32_t n_chunks, const ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// cic: one thread per (channel, chunk, rail)
+// cic combs + compensator FIR, fused: CTA = (channel, tile of 128 frames).  The tile's chunk records (256 chunks
+// plus the 68-chunk halo, both rails, 80 B each) are staged once in shared memory with 16-byte coalesced loads;
+// the 96 kHz CIC outputs live only in shared memory.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-ddc_cic_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_t n_chunks, uint32_t n_ch,
-               int16_t* __restrict__ U, uint32_t u_rail_stride /* int16 per (channel, rail) */) {
-    const uint32_t m = blockIdx.y * blockDim.x + threadIdx.x;
-    const uint32_t rail = blockIdx.x & 1, ch = blockIdx.x >> 1;
-    if (m >= n_chunks || ch >= n_ch) return;
-    const uint64_t* rec = L + (size_t)ch * l_ch_stride + (size_t)(kLHalo + m) * kLRec + rail * 5;
-    U[((size_t)ch * 2 + rail) * u_rail_stride + kUHalo + m] = cic_combine(rec, c_cic_g);
-}
+constexpr int kCcFrames = 128;                         // frames per CTA tile
+constexpr int kCcChunks = 2 * kCcFrames;               // chunks per tile
+constexpr int kCcRecs = kCcChunks + kLHalo;            // records staged
 
-// ------------------------------------------------------------------------------------------------
-// comp: CTA = (channel, rail, tile of 256 frames); window staged in shared memory
-// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ddc_comp_kernel(const int16_t* __restrict__ U, uint32_t u_rail_stride, uint32_t n_frames,
-                int16_t* __restrict__ YI, uint32_t yi_stride, int16_t* __restrict__ YQ, uint32_t yq_stride) {
-    __shared__ int16_t s_u[2 * 256 + kUHalo + 2];
-    const uint32_t rail = blockIdx.x & 1, ch = blockIdx.x >> 1;
-    const uint32_t k0 = blockIdx.y * 256;
-    const uint32_t nk = min(256u, n_frames - k0);
-    const int16_t* src = U + ((size_t)ch * 2 + rail) * u_rail_stride + 2 * k0;   // window start of frame k0
-    for (uint32_t i = threadIdx.x; i < 2 * nk + kUHalo; i += 256) s_u[i] = src[i];
+ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_t n_frames, int16_t* __restrict__ YI,
+                   uint32_t yi_stride, int16_t* __restrict__ YQ, uint32_t yq_stride) {
+    __shared__ __align__(16) uint64_t s_l[kCcRecs * kLRec];          // 324 x 80 B = 25.9 KB
+    __shared__ int16_t s_u[2][kCcChunks + kUHalo + 2];
+    const uint32_t ch = blockIdx.x;
+    const uint32_t k0 = blockIdx.y * kCcFrames;                      // first frame of the tile
+    const uint32_t nk = min((uint32_t)kCcFrames, n_frames - k0);
+    const uint32_t n_rec = 2 * nk + kLHalo;
+    // record index (array, halo included) of the tile's first staged record: chunk 2*k0 - 68 -> array index 2*k0
+    const uint64_t* src = L + (size_t)ch * l_ch_stride + (size_t)(2 * k0) * kLRec;
+    {
+        const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
+        ulonglong2* d2 = reinterpret_cast<ulonglong2*>(s_l);
+        for (uint32_t i = threadIdx.x; i < n_rec * (kLRec / 2); i += 256) d2[i] = s2[i];
+    }
     __syncthreads();
-    if (threadIdx.x < nk) {
-        const int16_t y = comp_fir(s_u, c_comp_h, (int)threadIdx.x);
-        if (rail == 0) YI[(size_t)ch * yi_stride + kYIHalo + k0 + threadIdx.x] = y;
-        else           YQ[(size_t)ch * yq_stride + kYQHalo + k0 + threadIdx.x] = y;
+    // CIC outputs u'[c] for chunks c = 2*k0 - 64 .. 2*k0 + 2*nk - 1  ->  s_u[rail][0 .. 64 + 2*nk)
+    for (uint32_t i = threadIdx.x; i < 2 * (2 * nk + kUHalo); i += 256) {
+        const uint32_t rail = i & 1, m = i >> 1;                      // m-th output of the tile (halo first)
+        s_u[rail][m] = cic_combine(s_l + (size_t)(m + 4) * kLRec + rail * 5, c_cic_g);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 2 * nk; i += 256) {
+        const uint32_t rail = i & 1, k = i >> 1;
+        const int16_t y = comp_fir(s_u[rail], c_comp_h, (int)k);
+        if (rail == 0) YI[(size_t)ch * yi_stride + kYIHalo + k0 + k] = y;
+        else           YQ[(size_t)ch * yq_stride + kYQHalo + k0 + k] = y;
     }
 }
 
@@ -256,24 +263,23 @@ ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_
 // rotate: CTA per channel; tails -> halos (read everything, barrier, write), NCO phase advance
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-ddc_rotate_kernel(uint64_t* __restrict__ L, uint32_t l_ch_stride, int16_t* __restrict__ U, uint32_t u_rail_stride,
+ddc_rotate_kernel(uint64_t* __restrict__ L, uint32_t l_ch_stride,
                   int16_t* __restrict__ YI, uint32_t yi_stride, int16_t* __restrict__ YQ, uint32_t yq_stride,
                   uint32_t n_chunks, uint32_t n_frames, uint32_t* __restrict__ phase, const uint32_t* __restrict__ fcw,
                   uint32_t n_ch) {
     const uint32_t ch = blockIdx.x, t = threadIdx.x;
     uint64_t* l = L + (size_t)ch * l_ch_stride;
-    int16_t* u0 = U + ((size_t)ch * 2) * u_rail_stride;
-    int16_t* u1 = u0 + u_rail_stride;
     int16_t* yi = YI + (size_t)ch * yi_stride;
     int16_t* yq = YQ + (size_t)ch * yq_stride;
-    uint64_t vl = 0; int16_t vu0 = 0, vu1 = 0, vyi = 0, vyq = 0;
-    if (t < kLHalo * kLRec) vl = l[(size_t)n_chunks * kLRec + t];
-    if (t < kUHalo) { vu0 = u0[n_chunks + t]; vu1 = u1[n_chunks + t]; }
+    constexpr int kLPer = (kLHalo * kLRec + 255) / 256;               // halo words per thread
+    uint64_t vl[kLPer]; int16_t vyi = 0, vyq = 0;
+#pragma unroll
+    for (int q = 0; q < kLPer; ++q) { const uint32_t w = t + 256u * q; vl[q] = (w < kLHalo * kLRec) ? l[(size_t)n_chunks * kLRec + w] : 0; }
     if (t < kYIHalo) vyi = yi[n_frames + t];
     if (t < kYQHalo) vyq = yq[n_frames + t];
     __syncthreads();
-    if (t < kLHalo * kLRec) l[t] = vl;
-    if (t < kUHalo) { u0[t] = vu0; u1[t] = vu1; }
+#pragma unroll
+    for (int q = 0; q < kLPer; ++q) { const uint32_t w = t + 256u * q; if (w < kLHalo * kLRec) l[w] = vl[q]; }
     if (t < kYIHalo) yi[t] = vyi;
     if (t < kYQHalo) yq[t] = vyq;
     if (t == 0 && ch < n_ch) phase[ch] = (phase[ch] + fcw[ch] * (n_chunks * (uint32_t)kCicR)) & 0x3FFFFFu;
@@ -346,19 +352,17 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
                    b.L, b.l_ch_stride);
     }
     if (ev) cudaEventRecord(ev[1], st);
-    UA3_LAUNCH(ddc_cic_kernel, dim3(b.n_ch * 2, (n_chunks + 255) / 256), 256, 0, st, b.L, b.l_ch_stride, n_chunks,
-               b.n_ch, b.U, b.u_rail_stride);
-    if (ev) cudaEventRecord(ev[2], st);
-    UA3_LAUNCH(ddc_comp_kernel, dim3(b.n_ch * 2, (n_frames + 255) / 256), 256, 0, st, b.U, b.u_rail_stride, n_frames,
+    UA3_LAUNCH(ddc_ciccomp_kernel, dim3(b.n_ch, (n_frames + kCcFrames - 1) / kCcFrames), 256, 0, st, b.L, b.l_ch_stride, n_frames,
                b.YI, b.yi_stride, b.YQ, b.yq_stride);
+    if (ev) cudaEventRecord(ev[2], st);
     if (ev) cudaEventRecord(ev[3], st);
     UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + 255) / 256), 256, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
                n_frames, b.frames, b.frame_ch_stride, ring_start, b.ring_mask);
     if (ev) cudaEventRecord(ev[4], st);
-    UA3_LAUNCH(ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.U, b.u_rail_stride, b.YI, b.yi_stride,
+    UA3_LAUNCH(ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.YI, b.yi_stride,
                b.YQ, b.yq_stride, n_chunks, n_frames, b.phase, b.fcw, b.n_ch_pad);
     if (ev) cudaEventRecord(ev[5], st);
-    if (launches) *launches += kDdcKernels;
+    if (launches) *launches += kDdcKernels - 1;
     return cudaGetLastError();
 }
 

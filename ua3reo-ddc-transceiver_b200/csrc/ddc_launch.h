@@ -15,8 +15,6 @@ struct DdcBuffers {
     uint32_t* phase = nullptr;     // [n_ch_pad] 22-bit phase at the start of the next block
     uint64_t* L = nullptr;         // [n_ch_pad][kLHalo + max_chunks][2][5]
     uint32_t l_ch_stride = 0;
-    int16_t* U = nullptr;          // [n_ch_pad][2][kUHalo + max_chunks]
-    uint32_t u_rail_stride = 0;
     int16_t* YI = nullptr;         // [n_ch_pad][kYIHalo + max_frames]
     uint32_t yi_stride = 0;
     int16_t* YQ = nullptr;         // [n_ch_pad][kYQHalo + max_frames]
@@ -32,7 +30,7 @@ void build_nco_big_table(uint32_t* tab);
 cudaError_t ddc_prepare_kernels();
 constexpr int kNcoBigTabWords = 2048 * 26;
 cudaError_t ddc_upload_constants();
-constexpr int kDdcKernels = 5;   // front, cic, comp, hilb, rotate
+constexpr int kDdcKernels = 5;   // profile slots: front, cic+comp, (unused), hilb, rotate
 // ev: optional array of kDdcKernels + 1 events recorded before/after each kernel (profiling mode)
 // ring_start: ring index that receives the block's first frame
 cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, uint32_t ring_start,

@@ -32,7 +32,7 @@ constexpr int kFrameBytes = 8;      // stm32_interface.v:228-271
 
 // ---- layout of the per-chunk CIC partial-state records in HBM ----
 // One record per (channel, 512-sample chunk): 2 rails x 5 integrator partial states (u64).
-constexpr int kLHalo = 4;           // chunks of history needed by the 5-chunk comb window
+constexpr int kLHalo = 68;          // chunks of history: 64 CIC outputs for the 65-tap compensator + 4 for the 5-chunk comb window
 constexpr int kLRec = 10;           // u64 per record: [rail][stage]
 constexpr int kUHalo = 64;          // 96 kHz samples of history for the 65-tap compensator
 constexpr int kYIHalo = 255;        // 48 kHz samples of history for the 256-tap Hilbert FIR
