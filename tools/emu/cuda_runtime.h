@@ -109,6 +109,18 @@ static inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, int m) {
 static inline int32_t __shfl_xor_sync(unsigned, int32_t v, int m) {
     float f; memcpy(&f, &v, 4); f = ua3_emu_shfl(f, (int)(threadIdx.x & 31) ^ m); memcpy(&v, &f, 4); return v;
 }
+extern uint32_t ua3_emu_pred_slots[1024];
+static inline uint32_t __ballot_sync(unsigned, int pred) {
+    ua3_emu_pred_slots[threadIdx.x] = pred ? 1u : 0u;
+    ua3_emu_barrier->arrive_and_wait();
+    uint32_t w = 0;
+    const unsigned base = threadIdx.x & ~31u;
+    for (unsigned l = 0; l < 32; ++l) w |= ua3_emu_pred_slots[base + l] << l;
+    ua3_emu_barrier->arrive_and_wait();
+    return w;
+}
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31)); }
 static inline void __syncwarp() { ua3_emu_barrier->arrive_and_wait(); }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }

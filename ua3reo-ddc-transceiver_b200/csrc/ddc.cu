@@ -15,7 +15,8 @@
 namespace ua3 {
 
 __constant__ int16_t c_comp_h[kCompTaps];
-__constant__ int16_t c_hilb_c[kHilbTaps];
+__constant__ int32_t c_hilb_c32[kHilbTaps];       // Hilbert coefficients widened to 32 bit (direct constant-bank IMAD operand)
+__constant__ uint32_t c_hilb_b0[8], c_hilb_b1[8];    // bit 0 / bit 1 of the coefficients, reversed (see ddc_hilb_kernel)
 __constant__ uint64_t c_cic_g[25];
 
 // ------------------------------------------------------------------------------------------------
@@ -205,10 +206,14 @@ constexpr int kCcFrames = 128;                         // frames per CTA tile
 constexpr int kCcChunks = 2 * kCcFrames;               // chunks per tile
 constexpr int kCcRecs = kCcChunks + kLHalo;            // records staged
 
+constexpr int kCcPitch = kCcRecs + 1;                  // odd pitch: the transposing stores spread over the banks
+
 __global__ void __launch_bounds__(256)
 ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_t n_frames, int16_t* __restrict__ YI,
                    uint32_t yi_stride, int16_t* __restrict__ YQ, uint32_t yq_stride) {
-    __shared__ __align__(16) uint64_t s_l[kCcRecs * kLRec];          // 324 x 80 B = 25.9 KB
+    // field-major (structure of arrays): s_l[field][record], field = rail * 5 + stage.  Threads that work on
+    // neighbouring chunks then read neighbouring 8-byte words: conflict-free 64-bit shared loads.
+    __shared__ __align__(16) uint64_t s_l[kLRec * kCcPitch];         // 10 x 325 x 8 B = 26 KB
     __shared__ int16_t s_u[2][kCcChunks + kUHalo + 2];
     const uint32_t ch = blockIdx.x;
     const uint32_t k0 = blockIdx.y * kCcFrames;                      // first frame of the tile
@@ -218,18 +223,28 @@ ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_
     const uint64_t* src = L + (size_t)ch * l_ch_stride + (size_t)(2 * k0) * kLRec;
     {
         const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
-        ulonglong2* d2 = reinterpret_cast<ulonglong2*>(s_l);
-        for (uint32_t i = threadIdx.x; i < n_rec * (kLRec / 2); i += 256) d2[i] = s2[i];
+        for (uint32_t i = threadIdx.x; i < n_rec * (kLRec / 2); i += 256) {
+            const ulonglong2 v = s2[i];                               // coalesced 16-byte loads of the record stream
+            const uint32_t rec = i / (kLRec / 2), f = 2 * (i % (kLRec / 2));
+            s_l[f * kCcPitch + rec] = v.x;
+            s_l[(f + 1) * kCcPitch + rec] = v.y;
+        }
     }
     __syncthreads();
     // CIC outputs u'[c] for chunks c = 2*k0 - 64 .. 2*k0 + 2*nk - 1  ->  s_u[rail][0 .. 64 + 2*nk)
     for (uint32_t i = threadIdx.x; i < 2 * (2 * nk + kUHalo); i += 256) {
-        const uint32_t rail = i & 1, m = i >> 1;                      // m-th output of the tile (halo first)
-        s_u[rail][m] = cic_combine(s_l + (size_t)(m + 4) * kLRec + rail * 5, c_cic_g);
+        const uint32_t rail = i / (2 * nk + kUHalo), m = i % (2 * nk + kUHalo);   // consecutive threads: consecutive chunks
+        const uint64_t* base = s_l + (size_t)(rail * 5) * kCcPitch + (m + 4);
+        uint64_t acc = 0;
+#pragma unroll
+        for (int p = 0; p < 5; ++p)
+#pragma unroll
+            for (int k = 0; k < 5; ++k) acc += c_cic_g[p * 5 + k] * base[(size_t)k * kCcPitch - p];
+        s_u[rail][m] = (int16_t)(uint16_t)(acc >> 44);                // output_typeconvert <= section_out10(59 DOWNTO 44)
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < 2 * nk; i += 256) {
-        const uint32_t rail = i & 1, k = i >> 1;
+        const uint32_t rail = i / nk, k = i % nk;
         const int16_t y = comp_fir(s_u[rail], c_comp_h, (int)k);
         if (rail == 0) YI[(size_t)ch * yi_stride + kYIHalo + k0 + k] = y;
         else           YQ[(size_t)ch * yq_stride + kYQHalo + k0 + k] = y;
@@ -239,21 +254,61 @@ ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_
 // ------------------------------------------------------------------------------------------------
 // hilb + delay + frame pack: CTA = (channel, tile of 256 frames)
 // ------------------------------------------------------------------------------------------------
+// rx_hilb.vhd:903 rounds every product: pr = (p + p[1]) >> 1 (convergent).  Because 2*pr = p + adj with
+// adj = +1 if p mod 4 == 3, -1 if p mod 4 == 1, 0 otherwise, the 256-tap sum is exactly
+//     sum pr = ( sum p + 2 * #{p mod 4 == 3} - #{p odd} ) / 2,
+// and p mod 4 depends only on the two low bits of coefficient and sample.  The kernel therefore does one plain
+// IMAD per tap (two 32-bit half sums, each provably < 2^31) and gets the rounding term from 256-bit popcounts over
+// bit planes of the samples (built with warp ballots) against bit planes of the coefficients.
 __global__ void __launch_bounds__(256)
 ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_t* __restrict__ YQ, uint32_t yq_stride,
                 uint32_t n_frames, uint64_t* __restrict__ frames, uint32_t frame_ch_stride, uint32_t ring_start,
                 uint32_t ring_mask) {
-    __shared__ int16_t s_y[256 + kYIHalo + 1];
+    __shared__ int16_t s_y[512];                  // window: s_y[i] = yI[k0 - 255 + i], zero padded
+    __shared__ uint32_t s_b0[17], s_b1[17];       // bit planes of the window, 32 samples per word
     const uint32_t ch = blockIdx.x;
     const uint32_t k0 = blockIdx.y * 256;
     const uint32_t nk = min(256u, n_frames - k0);
+    const uint32_t tid = threadIdx.x;
     const int16_t* src = YI + (size_t)ch * yi_stride + k0;
-    for (uint32_t i = threadIdx.x; i < nk + kYIHalo; i += 256) s_y[i] = src[i];
+    for (uint32_t i = tid; i < 512; i += 256) s_y[i] = (i < nk + kYIHalo) ? src[i] : (int16_t)0;
+    if (tid == 0) { s_b0[16] = 0; s_b1[16] = 0; }
     __syncthreads();
-    if (threadIdx.x < nk) {
-        const uint32_t k = k0 + threadIdx.x;
-        const int16_t vi = hilb_fir(s_y, c_hilb_c, (int)threadIdx.x);
-        const int16_t yi = s_y[kYIHalo + threadIdx.x];
+    for (uint32_t i = tid; i < 512; i += 256) {    // every warp: 32 consecutive samples -> one word per plane
+        const int32_t v = s_y[i];
+        const uint32_t w0 = __ballot_sync(0xffffffffu, v & 1), w1 = __ballot_sync(0xffffffffu, v & 2);
+        if ((tid & 31) == 0) { s_b0[i >> 5] = w0; s_b1[i >> 5] = w1; }
+    }
+    __syncthreads();
+    if (tid < nk) {
+        const uint32_t k = k0 + tid;
+        // ---- sum of the raw products, taps 0..127 and 128..255 in separate 32-bit accumulators ----
+        const int16_t* w = s_y + tid;             // w[255 - t] = yI[k - t]
+        int32_t s1 = 0, s2 = 0;
+#pragma unroll 16
+        for (int t = 0; t < 128; ++t) {
+            s1 += c_hilb_c32[t] * (int32_t)w[255 - t];
+            s2 += c_hilb_c32[128 + t] * (int32_t)w[127 - t];
+        }
+        // ---- rounding term: u = 255 - t runs over the window from bit `tid` on ----
+        const uint32_t wsel = tid >> 5, sh = tid & 31;
+        uint32_t n_odd = 0, n_three = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t x0 = __funnelshift_r(s_b0[wsel + j], s_b0[wsel + j + 1], sh);
+            const uint32_t x1 = __funnelshift_r(s_b1[wsel + j], s_b1[wsel + j + 1], sh);
+            const uint32_t q0 = x0 & c_hilb_b0[j];
+            const uint32_t q1 = (x0 & c_hilb_b1[j]) ^ (x1 & c_hilb_b0[j]);
+            n_odd += __popc(q0);
+            n_three += __popc(q0 & q1);
+        }
+        const int64_t twice = (int64_t)s1 + (int64_t)s2 + 2 * (int64_t)n_three - (int64_t)n_odd;
+        const int32_t acc = (int32_t)(twice >> 1);                       // exact: the sum is even
+        // rx_hilb.vhd:935: low 30 bits + 0x1FFF + bit14, wrap at 30 bits, >> 14, keep 16 bits
+        const uint32_t a30 = (uint32_t)acc & 0x3FFFFFFFu;
+        const uint32_t r30 = (a30 + 0x1FFFu + (((uint32_t)acc >> 14) & 1u)) & 0x3FFFFFFFu;
+        const int16_t vi = (int16_t)((int32_t)(r30 << 2) >> 16);
+        const int16_t yi = s_y[kYIHalo + tid];
         const int16_t* q = YQ + (size_t)ch * yq_stride + k;   // q[kYQHalo] = yQ[k], q[0] = yQ[k-130]
         frames[(size_t)ch * frame_ch_stride + ((ring_start + k) & ring_mask)] = frame_pack(q[kYQHalo], yi, q[0], vi);
     }
@@ -330,7 +385,19 @@ cudaError_t ddc_upload_constants() {
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_comp_h, UA3_RXCOMP_H, sizeof(int16_t) * kCompTaps);
     if (e != cudaSuccess) return e;
-    return cudaMemcpyToSymbol(c_hilb_c, UA3_RXHILB_C, sizeof(int16_t) * kHilbTaps);
+    int32_t c32[kHilbTaps];
+    uint32_t b0[8] = {0}, b1[8] = {0};
+    for (int t = 0; t < kHilbTaps; ++t) {
+        c32[t] = UA3_RXHILB_C[t];
+        const int u = kHilbTaps - 1 - t;                               // window position of tap t
+        b0[u >> 5] |= (uint32_t)(UA3_RXHILB_C[t] & 1) << (u & 31);
+        b1[u >> 5] |= (uint32_t)((UA3_RXHILB_C[t] >> 1) & 1) << (u & 31);
+    }
+    e = cudaMemcpyToSymbol(c_hilb_c32, c32, sizeof c32);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_hilb_b0, b0, sizeof b0);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_hilb_b1, b1, sizeof b1);
 }
 
 cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, uint32_t ring_start,
