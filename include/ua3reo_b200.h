@@ -121,7 +121,7 @@ typedef struct ua3reo_rx_settings {
     uint8_t fm_sql_threshold;  /* TRX.FM_SQL_threshold */
     uint8_t fft_enabled;       /* TRX.FFT_Enabled */
     uint8_t fft_averaging;     /* TRX.FFT_Averaging */
-    uint8_t fft_zoom;          /* TRX.FFT_Zoom: only 1 is implemented (ZoomFFT is a later row) */
+    uint8_t fft_zoom;          /* TRX.FFT_Zoom: 1, 2, 4, 8 or 16 (ZoomFFT, fft.c:236-261) */
     uint8_t iq_swap;           /* TRX_IQ_swap (functions.c:211-223) */
     uint8_t cw_decoder;        /* TRX.CWDecoder: run the CW decoder's Goertzel front end in CW_L / CW_U (cw_decoder.c:43-66) */
     uint8_t reserved[2];
@@ -149,6 +149,9 @@ int ua3reo_rx_set(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const ua3reo_rx_s
  * [n_channels][n_blocks][384]; n_blocks must equal *audio_blocks of ua3reo_rx_counts(). */
 int ua3reo_rx_counts(ua3reo_ctx *ctx, size_t *audio_blocks, size_t *fft_frames);
 int ua3reo_rx_read_audio(ua3reo_ctx *ctx, int32_t *dst_host, size_t n_blocks);
+/* The same audio as processRxAudio() hands to the USB audio class (audio_processor.c:415-432): volume undone,
+ * int16, L/R interleaved.  dst is [n_channels][n_blocks][384] int16. */
+int ua3reo_rx_read_audio_usb(ua3reo_ctx *ctx, int16_t *dst_host, size_t n_blocks);
 /* Spectra: FFTOutput_mean (fft.c:27,324-328) after each FFT_doFFT(): dst is [n_channels][n_frames][256] float. */
 int ua3reo_rx_read_spectra(ua3reo_ctx *ctx, float *dst_host, size_t n_frames);
 /* Waterfall rows: what FFT_printFFT() writes into wtf_buffer[0] after each FFT (fft.c:361-379): per bin the

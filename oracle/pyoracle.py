@@ -143,7 +143,7 @@ def run_fw_rx(frames, settings, workdir=None):
                     f.write("%s %d\n" % (RX_PARAM_KEYS[k], int(v)))
         frames.tofile(fp)
         subprocess.check_call([FW_RX, pp, fp, ap, sp])
-        a = np.fromfile(ap, dtype=np.int32).reshape(-1, 387)
+        a = np.fromfile(ap, dtype=np.int32).reshape(-1, 387 + 192)
         raw = np.fromfile(sp, dtype=np.uint8)
         rec = 256 * 4 + 256 * 2 + 4
         raw = raw[:rec * (raw.size // rec)].reshape(-1, rec)
@@ -151,6 +151,7 @@ def run_fw_rx(frames, settings, workdir=None):
             "audio": a[:, :384].copy(),
             "smeter": a[:, 384:386].copy().view(np.float32),
             "cw": a[:, 386].copy().view(np.float32),
+            "usb": np.ascontiguousarray(a[:, 387:]).view(np.int16).reshape(-1, 384),
             "spectra": np.ascontiguousarray(raw[:, :1024]).view(np.float32).reshape(-1, 256),
             "waterfall": np.ascontiguousarray(raw[:, 1024:1536]).view(np.uint16).reshape(-1, 256),
             "fft_max": np.ascontiguousarray(raw[:, 1536:1540]).view(np.float32).reshape(-1),

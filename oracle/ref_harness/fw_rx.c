@@ -15,7 +15,7 @@
  *     which is what feeds maxValueErrors back into the auto-range (fft.c:310-316,372) and re-arms FFT_need_fft
  *   - VFO frequency is held at 0 so that FFT_moveWaterfall() (fft.c:347-351) never shifts the averages
  * audio_out: per block 384 int32 (L,R interleaved; audio_processor.c:377-394) + 3 float (S-meter max, min,
- *            CW decoder Goertzel magnitude of the block or 0)
+ *            CW decoder Goertzel magnitude of the block or 0) + 384 int16 (USB_AUDIO_rx_buffer_a)
  * fft_out  : per FFT frame 256 float (FFTOutput_mean) + 256 uint16 (waterfall row 0) + float maxValueFFT
  */
 #include "stm32f4xx_hal.h"
@@ -41,6 +41,7 @@ float ua3_fft_max_value(void);
 float ua3_cw_magnitude(void);
 void ua3_set_tick(uint32_t t);
 #include "cw_decoder.h"
+#include "usbd_audio_if.h"
 
 static void defaults(void)
 {
@@ -97,6 +98,8 @@ int main(int argc, char **argv)
         n++;
         if (n > 192 && (n % 192) == 1) {
             Processor_NeedRXBuffer = true;
+            USB_AUDIO_need_rx_buffer = true;   /* exercise the USB-audio int16 packing (audio_processor.c:415-432) */
+            USB_AUDIO_current_rx_buffer = false;
             /* HAL_GetTick() stays 0: the Morse timing logic (cw_decoder.c:88-240, host side, unbounded strcat) never fires;
              * only the Goertzel front end (:56-66) is exercised */
             const uint8_t before = Processor_AudioBuffer_ReadyBuffer;
@@ -106,6 +109,7 @@ int main(int argc, char **argv)
             float sm[3] = {Processor_RX_Audio_Samples_MAX_value, Processor_RX_Audio_Samples_MIN_value, 0.0f};
             if (TRX.CWDecoder && (TRX_getMode() == TRX_MODE_CW_L || TRX_getMode() == TRX_MODE_CW_U)) sm[2] = ua3_cw_magnitude();
             fwrite(sm, sizeof(float), 3, fa);
+            fwrite(USB_AUDIO_rx_buffer_a, sizeof(int16_t), FPGA_AUDIO_BUFFER_SIZE, fa);
         }
         if (!NeedFFTInputBuffer && TRX.FFT_Enabled) {
             FFT_doFFT();

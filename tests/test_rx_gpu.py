@@ -61,6 +61,7 @@ def _run_frames_through_gpu(pkg, oracle, cases, n_adc, pushes, seed):
         frames.append(rx.read_frames()); audio.append(rx.read_audio()); spec.append(rx.read_spectra())
         extra.setdefault("waterfall", []).append(rx.read_waterfall())
         extra.setdefault("cw", []).append(rx.read_cw())
+        extra.setdefault("usb", []).append(rx.read_audio_usb())
     sm = rx.read_smeter()
     rx.close()
     _run_frames_through_gpu.extra = {k: np.concatenate(v, 1) for k, v in extra.items()}
@@ -92,6 +93,8 @@ def test_against_reference_firmware_fixtures(pkg, oracle, golden):
         if c["settings"]["fft_enabled"]:
             wf, rwf = _run_frames_through_gpu.extra["waterfall"][i], z[c["name"] + "/waterfall"]
             assert (wf != rwf).mean() <= 0.01, c["name"] + " waterfall row"      # a height on a rounding edge may flip one column
+        usb, rusb = _run_frames_through_gpu.extra["usb"][i], z[c["name"] + "/usb"]
+        assert np.abs(usb.astype(np.int32) - rusb.astype(np.int32)).max() <= 1, c["name"] + " USB audio packing"
         cwm, rcw = _run_frames_through_gpu.extra["cw"][i], z[c["name"] + "/cw"]
         assert np.allclose(cwm, rcw, rtol=1e-5, atol=1e-4), c["name"] + " CW Goertzel magnitude"
     # SSB/CW/DIGI/IQ/AM use only IEEE +,-,*,/,sqrt: those channels are expected to be bit-identical
@@ -118,6 +121,8 @@ def test_live_against_host_built_firmware(pkg, oracle):
                  (4, 300, 0, 1, 600, 1, 80, 0), (5, 2900, 0, 0, 1000, 3, 50, 0), (6, 1800, 1, 0, 1000, 7, 10, 1),
                  (10, 10000, 0, 1, 2000, 3, 50, 0), (8, 9000, 0, 0, 1000, 3, 50, 0), (9, 15000, 1, 0, 1000, 3, 50, 0),
                  (2, 2700, 0, 0, 1000, 3, 50, 1), (1, 0, 0, 0, 1000, 3, 50, 0), (0, 5000, 0, 0, 1000, 9, 100, 0)]]
+    for i, zoom in enumerate([1, 2, 4, 8, 16, 1, 2, 4, 8, 16, 1, 2]):
+        cases[i]["fft_zoom"] = zoom
     n = 1024 * (192 * 12 + 1)
     frames, audio, spec, sm = _run_frames_through_gpu(pkg, oracle, cases, n, [n // 2 + 17, n - (n // 2 + 17)], 99)
     rx0 = pkg.Receiver(1, 1024)
@@ -136,7 +141,7 @@ def test_live_against_host_built_firmware(pkg, oracle):
 def test_rejects_settings_without_firmware_table(pkg):
     rx = pkg.Receiver(2, 1024)
     rx.rx_enable(True)
-    for bad in (dict(filter_width=2750), dict(mode=12), dict(agc_speed=0), dict(fft_zoom=2), dict(fft_averaging=0)):
+    for bad in (dict(filter_width=2750), dict(mode=12), dict(agc_speed=0), dict(fft_zoom=3), dict(fft_averaging=0)):
         with pytest.raises(pkg.UA3Error):
             rx.rx_set(rx.rx_defaults(**bad))
     rx.rx_set(rx.rx_defaults(mode=1, ssb_hpf_pass=60))     # no branch in ReinitAudioFilters: keeps the previous HPF

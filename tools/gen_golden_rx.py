@@ -32,6 +32,9 @@ CASES = [
     dict(name="usb_fft_off", settings=dict(mode=1, fft_enabled=0)),
     dict(name="cw_u_decoder", settings=dict(mode=4, filter_width=500, cw_decoder=1)),
     dict(name="usb_strong_rf_gain", settings=dict(mode=1, rf_gain=250, fft_averaging=2)),
+    dict(name="usb_zoom2", settings=dict(mode=1, fft_zoom=2)),
+    dict(name="lsb_zoom8_notch", settings=dict(mode=0, fft_zoom=8, notch=1)),
+    dict(name="am_zoom16", settings=dict(mode=10, filter_width=6000, fft_zoom=16)),
 ]
 DEFAULTS = dict(mode=0, agc=1, agc_speed=3, dnr=0, notch=0, mute=0, volume=20, rf_gain=50, fm_sql_threshold=1, fft_enabled=1,
                 fft_averaging=4, fft_zoom=1, iq_swap=0, cw_decoder=0, filter_width=2700, ssb_hpf_pass=300, notch_fc=1000)
@@ -63,7 +66,7 @@ def main():
     for c in CASES:
         s = {**DEFAULTS, **c["settings"]}
         r = pyoracle.run_fw_rx(frames, s)
-        for k in ("audio", "smeter", "cw", "spectra", "waterfall", "fft_max"):
+        for k in ("audio", "smeter", "cw", "usb", "spectra", "waterfall", "fft_max"):
             out[c["name"] + "/" + k] = r[k]
         print("%-28s audio %s spectra %s  rms L %.1f" % (c["name"], r["audio"].shape, r["spectra"].shape,
                                                          r["audio"][:, 0::2].astype(float).std()))

@@ -91,6 +91,7 @@ def _bind(lib):
         "ua3reo_rx_counts": (c.c_int, [vp, c.POINTER(sz), c.POINTER(sz)]),
         "ua3reo_rx_read_audio": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_spectra": (c.c_int, [vp, vp, sz]),
+        "ua3reo_rx_read_audio_usb": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_smeter": (c.c_int, [vp, vp, c.c_int]),
         "ua3reo_rx_read_waterfall": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_cw": (c.c_int, [vp, vp, sz]),
@@ -263,6 +264,13 @@ class Receiver:
             out = np.empty((self.n_channels, nb, 2 * AUDIO_BLOCK), np.int32)
         ptr = out.ctypes.data if isinstance(out, np.ndarray) else out.data_ptr()
         self._chk(self.lib.ua3reo_rx_read_audio(self._h, ptr, nb))
+        return out
+
+    def read_audio_usb(self):
+        """int16 [n_channels, blocks_of_last_push, 384]: the USB-audio packing of the same blocks."""
+        nb, _ = self.rx_counts()
+        out = np.empty((self.n_channels, nb, 2 * AUDIO_BLOCK), np.int16)
+        self._chk(self.lib.ua3reo_rx_read_audio_usb(self._h, out.ctypes.data, nb))
         return out
 
     def read_spectra(self, out=None):

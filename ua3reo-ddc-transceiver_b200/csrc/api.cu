@@ -438,7 +438,9 @@ static int rx_allocate(ua3reo_ctx* c) {
     rx_build_twiddles(tw.data());
     uint16_t colors[32];
     rx_build_colors(colors);
-    UA3_CUDA(rx_upload_constants(win.data(), tw.data(), colors));
+    float zb[4][20], zf[4][4];
+    rx_build_zoom(zb, zf);
+    UA3_CUDA(rx_upload_constants(win.data(), tw.data(), colors, &zb[0][0], &zf[0][0]));
     int launches = 0;
     UA3_CUDA(rx_launch_init_state(r, c->stream, &launches));
     c->launches += (uint64_t)launches;
@@ -486,7 +488,8 @@ int ua3reo_rx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_rx_set
             std::snprintf(msg, sizeof msg, "ua3reo_rx_set: channel %u: settings outside the firmware's tables", first + i);
             return fail(UA3_E_INVAL, msg);
         }
-        flags[i] = (uint8_t)((cl ? 1 : 0) | (chp ? 2 : 0));
+        const bool zoom_changed = np[i].fft_zoom != c->h_par[first + i].fft_zoom;
+        flags[i] = (uint8_t)((cl ? 1 : 0) | (chp ? 2 : 0) | (zoom_changed ? 4 : 0));
     }
     for (uint32_t i = 0; i < n; ++i) { c->h_par[first + i] = np[i]; c->h_set[first + i] = settings[i]; }
     UA3_CUDA(cudaMemcpyAsync(c->rx.params + first, c->h_par.data() + first, sizeof(RxParams) * n, cudaMemcpyHostToDevice,
@@ -529,6 +532,31 @@ int ua3reo_rx_read_spectra(ua3reo_ctx* c, float* dst, size_t n_frames) {
         UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.spectra, (size_t)c->rx.spec_ch_stride * sizeof(float), row, c->n_ch,
                                    cudaMemcpyDeviceToHost, c->stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_rx_read_audio_usb(ua3reo_ctx* c, int16_t* dst, size_t n_blocks) {
+    if (!c || (!dst && n_blocks)) return fail(UA3_E_INVAL, "ua3reo_rx_read_audio_usb: null argument");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_audio_usb: STM32 stage not enabled");
+    if (n_blocks != c->last_audio_blocks) return fail(UA3_E_INVAL, "ua3reo_rx_read_audio_usb: n_blocks != blocks of last push");
+    UA3_CUDA(cudaSetDevice(c->device));
+    if (!n_blocks) return UA3_OK;
+    const size_t n_words = n_blocks * 2 * UA3_AUDIO_BLOCK;
+    std::vector<float> undo(c->n_ch);
+    for (uint32_t i = 0; i < c->n_ch; ++i) undo[i] = 1.0f / (float)c->h_set[i].volume * 100.0f;   // audio_processor.c:420
+    float* undo_dev = nullptr;
+    int16_t* out_dev = nullptr;
+    UA3_CUDA(cudaMalloc(&undo_dev, sizeof(float) * c->n_ch));
+    cudaError_t e = cudaMalloc(&out_dev, sizeof(int16_t) * c->n_ch * n_words);
+    if (e != cudaSuccess) { cudaFree(undo_dev); return fail(UA3_E_CUDA, "cudaMalloc", e); }
+    int launches = 0;
+    e = cudaMemcpyAsync(undo_dev, undo.data(), sizeof(float) * c->n_ch, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = rx_launch_usb_pack(c->rx, (uint32_t)n_blocks, undo_dev, out_dev, c->stream, &launches);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, out_dev, sizeof(int16_t) * c->n_ch * n_words, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(undo_dev); cudaFree(out_dev);
+    c->launches += (uint64_t)launches;
+    if (e != cudaSuccess) return fail(UA3_E_CUDA, "ua3reo_rx_read_audio_usb", e);
     return UA3_OK;
 }
 

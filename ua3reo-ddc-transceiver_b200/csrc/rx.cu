@@ -18,6 +18,8 @@ namespace ua3 {
 __constant__ float c_fft_window[kFftSize];
 __constant__ float c_fft_twiddle[2 * kFftSize];
 __constant__ uint16_t c_fft_colors[32];
+__constant__ float c_zoom_biquad[4][20];      // zoom 2, 4, 8, 16: mag_coeffs (fft.c:72-121)
+__constant__ float c_zoom_fir[4][4];          // FirZoomFFTDecimate (fft.c:123-183)
 
 #if defined(UA3_HOST_EMU)
 #define UA3_FULL_MASK 0xffffffffu
@@ -360,6 +362,7 @@ rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t 
               uint32_t n_frames, const RxParams* __restrict__ params, RxState* __restrict__ state, uint32_t n_ch,
               float* __restrict__ spectra, uint32_t spec_ch_stride, uint16_t* __restrict__ waterfall) {
     __shared__ float s_re[kFftSize], s_im[kFftSize];
+    __shared__ float s_dec[2][kFftSize / 2];                           // decimated samples of the ZoomFFT branch
     const int lane = threadIdx.x & 31;
     const uint32_t ch = blockIdx.x;
     if (ch >= n_ch) return;
@@ -369,6 +372,8 @@ rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t 
     const uint64_t* fr = frames + (size_t)ch * frame_ch_stride;
     const float A1 = (float)(1.0 - 0.00048828125);
     const int swap = P.iq_swap ? 1 : 0;
+    const int zoom = P.fft_zoom > 1 ? P.fft_zoom : 1;
+    const int zsel = zoom == 2 ? 0 : (zoom == 4 ? 1 : (zoom == 8 ? 2 : 3));
 
     for (uint32_t fi = 0; fi < n_frames; ++fi) {
         const uint32_t base = start + fi * (uint32_t)kFftSize;
@@ -404,8 +409,53 @@ rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t 
             }
             S.dc_x[4 + rail] = dx; S.dc_y[4 + rail] = dy;
             S.notch_fft_d[rail][0] = d1; S.notch_fft_d[rail][1] = d2;
+            if (zoom > 1) {
+                // arm_biquad_cascade_df1_f32, 4 stages (fft.c:239-240), then arm_fir_decimate_f32, 4 taps, M = zoom (:242-243)
+                float st[4][4];
+#pragma unroll
+                for (int sg = 0; sg < 4; ++sg)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) st[sg][q] = S.zoom_biquad[rail][sg][q];
+                float h0 = S.zoom_fir[rail][0], h1 = S.zoom_fir[rail][1], h2 = S.zoom_fir[rail][2];
+                const float* bq = c_zoom_biquad[zsel];
+                const float f0 = c_zoom_fir[zsel][0], f1 = c_zoom_fir[zsel][1], f2 = c_zoom_fir[zsel][2], f3 = c_zoom_fir[zsel][3];
+                for (int i = 0; i < kFftSize; ++i) {
+                    float x = dst[i];
+#pragma unroll
+                    for (int sg = 0; sg < 4; ++sg) {
+                        const float acc = ((((bq[sg * 5] * x) + (bq[sg * 5 + 1] * st[sg][0])) + (bq[sg * 5 + 2] * st[sg][1])) +
+                                           (bq[sg * 5 + 3] * st[sg][2])) + (bq[sg * 5 + 4] * st[sg][3]);
+                        st[sg][1] = st[sg][0]; st[sg][0] = x; st[sg][3] = st[sg][2]; st[sg][2] = acc;
+                        x = acc;
+                    }
+                    // decimator: output o is computed right after the FIRST sample of its group of `zoom` inputs has been
+                    // shifted in (arm_fir_decimate_f32 copies M samples, then reads the window that starts M back)
+                    if (i % zoom == 0) {
+                        float sum0 = 0.0f;
+                        sum0 += h0 * f0; sum0 += h1 * f1; sum0 += h2 * f2; sum0 += x * f3;
+                        s_dec[rail][i / zoom] = sum0;
+                    }
+                    h0 = h1; h1 = h2; h2 = x;
+                }
+#pragma unroll
+                for (int sg = 0; sg < 4; ++sg)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) S.zoom_biquad[rail][sg][q] = st[sg][q];
+                S.zoom_fir[rail][0] = h0; S.zoom_fir[rail][1] = h1; S.zoom_fir[rail][2] = h2;
+            }
         }
         __syncwarp();
+        if (zoom > 1) {
+            // slide FFTInput_ZOOMFFT left by zoomed_width and append the new decimated samples (fft.c:245-260)
+            const int zw = kFftSize / zoom;
+            for (int i = lane; i < kFftSize; i += 32) {
+                if (i < kFftSize - zw) { s_re[i] = S.zoom_buf[2 * (i + zw)]; s_im[i] = S.zoom_buf[2 * (i + zw) + 1]; }
+                else { s_re[i] = s_dec[0][i - (kFftSize - zw)]; s_im[i] = s_dec[1][i - (kFftSize - zw)]; }
+            }
+            __syncwarp();
+            for (int i = lane; i < kFftSize; i += 32) { S.zoom_buf[2 * i] = s_re[i]; S.zoom_buf[2 * i + 1] = s_im[i]; }
+            __syncwarp();
+        }
         // Hamming window (:275-286)
         for (int i = lane; i < kFftSize; i += 32) {
             const float wm = c_fft_window[i];
@@ -520,6 +570,12 @@ __global__ void rx_clear_filters_kernel(RxState* __restrict__ state, const uint8
     const uint8_t f = flags[i];
     if (f & 1) for (int r = 0; r < 2; ++r) for (int k = 0; k < kLpfMax; ++k) S.lpf_g[r][k] = 0.0f;
     if (f & 2) for (int r = 0; r < 2; ++r) for (int k = 0; k < kHpfStages; ++k) S.hpf_g[r][k] = 0.0f;
+    if (f & 4) {                                   // FFT_Init() on a zoom change: biquad and decimator states cleared (fft.c:189-207)
+        for (int r = 0; r < 2; ++r) {
+            for (int sg = 0; sg < 4; ++sg) for (int q = 0; q < 4; ++q) S.zoom_biquad[r][sg][q] = 0.0f;
+            for (int q = 0; q < 3; ++q) S.zoom_fir[r][q] = 0.0f;
+        }
+    }
 }
 
 // power-on values of the firmware's statics: everything zero except AGC_need_gain_old = 1.0f (agc.c:12)
@@ -536,8 +592,13 @@ cudaError_t rx_launch_init_state(const RxBuffers& b, cudaStream_t st, int* launc
     return cudaGetLastError();
 }
 
-cudaError_t rx_upload_constants(const float* window, const float* twiddle, const uint16_t* colors) {
+cudaError_t rx_upload_constants(const float* window, const float* twiddle, const uint16_t* colors, const float* zoom_biquad,
+                                const float* zoom_fir) {
     cudaError_t e = cudaMemcpyToSymbol(c_fft_window, window, sizeof(float) * kFftSize);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_zoom_biquad, zoom_biquad, sizeof(float) * 80);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_zoom_fir, zoom_fir, sizeof(float) * 16);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_fft_colors, colors, sizeof(uint16_t) * 32);
     if (e != cudaSuccess) return e;
@@ -573,6 +634,26 @@ cudaError_t adc_stats_launch(const int16_t* adc, uint32_t n, int32_t* stats, int
     if (!n) return cudaSuccess;
     const uint32_t grid = (uint32_t)min((uint64_t)(n + 255u) / 256u, (uint64_t)sm_count * 8);
     UA3_LAUNCH(adc_stats_kernel, grid, 256, 0, st, adc, n, stats);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// USB-audio packing of processRxAudio (audio_processor.c:415-432): int16 = (int32 sample) * (1.0f / Volume * 100.0f)
+__global__ void __launch_bounds__(256)
+rx_usb_pack_kernel(const int32_t* __restrict__ audio, uint32_t audio_ch_stride, uint32_t n_words, const float* __restrict__ undo,
+                   int16_t* __restrict__ out) {
+    const uint32_t ch = blockIdx.y;
+    const float k = undo[ch];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x)
+        out[(size_t)ch * n_words + i] = (int16_t)(int32_t)((float)audio[(size_t)ch * audio_ch_stride + i] * k);
+}
+
+cudaError_t rx_launch_usb_pack(const RxBuffers& b, uint32_t n_blocks, const float* undo_dev, int16_t* out_dev, cudaStream_t st,
+                               int* launches) {
+    if (!n_blocks) return cudaSuccess;
+    const uint32_t n_words = n_blocks * 2u * (uint32_t)kAudioBlock;
+    UA3_LAUNCH(rx_usb_pack_kernel, dim3((n_words + 255u) / 256u, b.n_ch), 256, 0, st, b.audio_out, b.audio_ch_stride, n_words, undo_dev,
+               out_dev);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -21,8 +21,11 @@ struct RxBuffers {
     uint32_t spec_ch_stride = 0, max_fft_frames = 0;
 };
 
-cudaError_t rx_upload_constants(const float* window, const float* twiddle, const uint16_t* colors);
+cudaError_t rx_upload_constants(const float* window, const float* twiddle, const uint16_t* colors, const float* zoom_biquad,
+                                const float* zoom_fir);
 cudaError_t adc_stats_launch(const int16_t* adc, uint32_t n, int32_t* stats, int sm_count, cudaStream_t st, int* launches);
+cudaError_t rx_launch_usb_pack(const RxBuffers& b, uint32_t n_blocks, const float* undo_dev, int16_t* out_dev, cudaStream_t st,
+                               int* launches);
 cudaError_t rx_launch_audio(const RxBuffers& b, uint32_t start, uint32_t n_blocks, cudaStream_t st, int* launches);
 cudaError_t rx_launch_fft(const RxBuffers& b, uint32_t start, uint32_t n_frames, cudaStream_t st, int* launches);
 cudaError_t rx_launch_clear(const RxBuffers& b, const uint8_t* flags_dev, uint32_t first, uint32_t n, cudaStream_t st,

@@ -29,7 +29,7 @@ struct RxParams {
     uint8_t lpf_on;          // Filter_Width > 0 (audio_processor.c:448)
     uint8_t hpf_set;         // HPF coefficients have been initialised at least once
     uint8_t cw_on;           // TRX.CWDecoder && mode is CW_L / CW_U (audio_processor.c:437-443)
-    uint8_t pad[1];
+    uint8_t fft_zoom;        // TRX.FFT_Zoom: 1, 2, 4, 8 or 16 (fft.c:185-210)
     float rf_gain;           // (float)TRX.RF_Gain
     float volume;            // (float)TRX.Volume / 100.0f
     float agc_step_up;       // 500.0f / Agc_speed (agc.c:17)
@@ -67,6 +67,10 @@ struct RxState {
     float fft_max_value;                 // maxValueFFT
     uint32_t fft_max_errors;             // maxValueErrors (fed back from the display pass, fft.c:372)
     float fft_mean[kFftBins];            // FFTOutput_mean
+    // ZoomFFT (fft.c:236-261)
+    float zoom_biquad[2][4][4];          // IIR_biquad_Zoom_FFT_I/Q state: per stage x[n-1], x[n-2], y[n-1], y[n-2]
+    float zoom_fir[2][3];                // decimZoomFFTI/QState: the 3 newest filtered samples
+    float zoom_buf[2 * kFftSize];        // FFTInput_ZOOMFFT, interleaved re, im
 };
 
 // user-facing settings block (mirrors the TRX fields the path reads); declared in include/ua3reo_b200.h
