@@ -138,6 +138,11 @@ void ua3reo_rx_defaults(ua3reo_rx_settings *s);
  * 512-sample FFT frames that have become available (frames are buffered across pushes).  */
 int ua3reo_rx_enable(ua3reo_ctx *ctx, int enable);
 
+/* The STM32 stage alone over I/Q frames that come from elsewhere - what FPGA_fpgadata_getiq() (fpga.c:286-401)
+ * receives from a real FPGA, or BASELINE config 1's synthetic 48 kSPS I/Q: frames_host is [n_channels][n][8] bytes in
+ * the bus order of stm32_interface.v:228-271; they enter the same ring the DDC writes and are processed like a push. */
+int ua3reo_rx_push_frames(ua3reo_ctx *ctx, const uint8_t *frames_host, size_t n);
+
 /* TRX_setMode()/ReinitAudioFilters()/InitNotchFilter()/InitAGC() for channels [first, first+n)
  * (trx_manager.c:193-220, audio_filters.c:141-346, agc.c:14-19).  As in the firmware, selecting filters
  * clears the lattice filter states of the channel.  Fails with UA3_E_INVAL for a filter width, HPF

@@ -170,3 +170,25 @@ def test_full_chain_many_channels_consistency(pkg, oracle):
     assert a.shape == (n_ch, 2, 384) and s.shape == (n_ch, 1, 256)
     for c in range(20, n_ch):
         assert np.array_equal(a[c], a[c - 20]) and np.array_equal(s[c], s[c - 20])   # period lcm(10,20)=20 in settings, 2 in fcw
+
+
+def test_stm32_stage_alone_on_external_frames(pkg, golden):
+    """BASELINE config 1 shape: the STM32 stage fed with I/Q frames directly (no DDC), ragged pushes; equals the
+    reference firmware fixtures exactly like the DDC-fed run."""
+    z, meta = golden
+    frames = z["frames"]
+    cases = [c for c in meta["cases"] if c["name"] in ("usb_default", "lsb_dnr", "am_6k_notch", "nfm_15k", "usb_zoom2")]
+    keys = ("mode", "agc", "agc_speed", "dnr", "notch", "mute", "volume", "rf_gain", "fm_sql_threshold", "fft_enabled",
+            "fft_averaging", "fft_zoom", "iq_swap", "cw_decoder", "filter_width", "ssb_hpf_pass", "notch_fc")
+    rx = pkg.Receiver(len(cases), 1 << 20)
+    rx.rx_enable(True)
+    rx.rx_set([rx.rx_defaults(**{k: c["settings"][k] for k in keys}) for c in cases])
+    audio, spec = [], []
+    for a, b in [(0, 100), (100, 700), (700, 1023), (1023, frames.shape[0])]:
+        rx.rx_push_frames(np.repeat(frames[None, a:b], len(cases), 0))
+        audio.append(rx.read_audio()); spec.append(rx.read_spectra())
+    rx.close()
+    audio, spec = np.concatenate(audio, 1), np.concatenate(spec, 1)
+    for i, c in enumerate(cases):
+        check(audio[i], z[c["name"] + "/audio"], c["name"] + " audio (external frames)")
+        check(spec[i], z[c["name"] + "/spectra"], c["name"] + " spectrum (external frames)")

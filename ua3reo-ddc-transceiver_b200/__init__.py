@@ -88,6 +88,7 @@ def _bind(lib):
         "ua3reo_rx_defaults": (None, [c.POINTER(RxSettings)]),
         "ua3reo_rx_enable": (c.c_int, [vp, c.c_int]),
         "ua3reo_rx_set": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_rx_push_frames": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_counts": (c.c_int, [vp, c.POINTER(sz), c.POINTER(sz)]),
         "ua3reo_rx_read_audio": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_spectra": (c.c_int, [vp, vp, sz]),
@@ -251,6 +252,14 @@ class Receiver:
             settings = [settings] * (self.n_channels - first)
         arr = (RxSettings * len(settings))(*settings)
         self._chk(self.lib.ua3reo_rx_set(self._h, int(first), len(settings), ctypes.cast(arr, ctypes.c_void_p)))
+
+    def rx_push_frames(self, frames):
+        """frames: uint8 [n_channels, n, 8] I/Q frames (stm32_interface byte order) fed straight to the STM32 stage."""
+        a = np.ascontiguousarray(frames, dtype=np.uint8)
+        assert a.ndim == 3 and a.shape[0] == self.n_channels and a.shape[2] == FRAME_BYTES
+        self._keep_frames = a
+        self._chk(self.lib.ua3reo_rx_push_frames(self._h, a.ctypes.data, a.shape[1]))
+        self.last_frames = a.shape[1]
 
     def rx_counts(self):
         a, f = ctypes.c_size_t(), ctypes.c_size_t()

@@ -502,6 +502,46 @@ int ua3reo_rx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_rx_set
     return rx_upload_order(c);
 }
 
+// The STM32 stage alone, over I/Q frames that come from elsewhere (a real FPGA, a recording, BASELINE config 1's
+// synthetic 48 kSPS I/Q): the frames enter the same per-channel ring the DDC writes.
+int ua3reo_rx_push_frames(ua3reo_ctx* c, const uint8_t* frames_host, size_t n) {
+    if (!c || (!frames_host && n)) return fail(UA3_E_INVAL, "ua3reo_rx_push_frames: null argument");
+    if (!c->rx_on) return fail(UA3_E_STATE, "ua3reo_rx_push_frames: call ua3reo_rx_enable first");
+    if (n > c->b.max_frames) return fail(UA3_E_TOOBIG, "ua3reo_rx_push_frames: more frames than one block holds");
+    UA3_CUDA(cudaSetDevice(c->device));
+    if (c->copy_pending[c->n_push & 1]) {
+        UA3_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[c->n_push & 1], 0));
+        c->copy_pending[c->n_push & 1] = false;
+    }
+    const uint32_t ring = c->b.frame_ch_stride;
+    const uint32_t first = (uint32_t)(c->w_pos & c->b.ring_mask);
+    const size_t n1 = (first + n <= ring) ? n : (size_t)(ring - first);
+    const size_t pitch = (size_t)ring * UA3_FRAME_BYTES;
+    uint8_t* base = reinterpret_cast<uint8_t*>(c->b.frames);
+    if (n1)
+        UA3_CUDA(cudaMemcpy2DAsync(base + (size_t)first * UA3_FRAME_BYTES, pitch, frames_host, n * UA3_FRAME_BYTES,
+                                   n1 * UA3_FRAME_BYTES, c->n_ch, cudaMemcpyHostToDevice, c->stream));
+    if (n1 < n)
+        UA3_CUDA(cudaMemcpy2DAsync(base, pitch, frames_host + n1 * UA3_FRAME_BYTES, n * UA3_FRAME_BYTES,
+                                   (n - n1) * UA3_FRAME_BYTES, c->n_ch, cudaMemcpyHostToDevice, c->stream));
+    c->w_pos += n;
+    int launches = 0;
+    const uint32_t nb = (uint32_t)((c->w_pos - c->a_pos) / UA3_AUDIO_BLOCK);
+    const uint32_t nf = (uint32_t)((c->w_pos - c->f_pos) / UA3_FFT_SIZE);
+    UA3_CUDA(rx_launch_audio(c->rx, (uint32_t)(c->a_pos & c->b.ring_mask), nb, c->stream, &launches));
+    UA3_CUDA(rx_launch_fft(c->rx, (uint32_t)(c->f_pos & c->b.ring_mask), nf, c->stream, &launches));
+    c->a_pos += (uint64_t)nb * UA3_AUDIO_BLOCK;
+    c->f_pos += (uint64_t)nf * UA3_FFT_SIZE;
+    c->last_audio_blocks = nb;
+    c->last_fft_frames = nf;
+    c->last_frames = n;
+    c->pushed = true;
+    c->launches += (uint64_t)launches;
+    UA3_CUDA(cudaEventRecord(c->ev_push, c->stream));
+    c->n_push++;
+    return UA3_OK;
+}
+
 int ua3reo_rx_counts(ua3reo_ctx* c, size_t* audio_blocks, size_t* fft_frames) {
     if (!c) return fail(UA3_E_INVAL, "null context");
     if (audio_blocks) *audio_blocks = c->last_audio_blocks;
