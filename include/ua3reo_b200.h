@@ -148,6 +148,14 @@ int ua3reo_rx_push_frames(ua3reo_ctx *ctx, const uint8_t *frames_host, size_t n)
  * clears the lattice filter states of the channel.  Fails with UA3_E_INVAL for a filter width, HPF
  * corner or mode the firmware has no table/branch for. */
 int ua3reo_rx_set(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const ua3reo_rx_settings *settings);
+/* The fields processRxAudio()/FFT_doFFT() read from TRX on EVERY call (mode, AGC/DNR/notch switches, volume, mute,
+ * RF gain, squelch threshold, FFT averaging/enable, IQ swap, CW decoder; `Filter_Width > 0`, audio_processor.c:448),
+ * applied without what ReinitAudioFilters()/InitNotchFilter()/FFT_Init() do: filter tables, notch coefficients and
+ * the ZoomFFT decimator stay as the last ua3reo_rx_set() left them and no filter state is cleared. */
+int ua3reo_rx_set_live(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const ua3reo_rx_settings *settings);
+/* InitNotchFilter() (audio_filters.c:341-346) alone: recomputes the notch biquad for notch_fc[i] Hz (one per channel
+ * of the range); like the firmware it leaves the biquad states as they are. */
+int ua3reo_rx_set_notch(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const uint16_t *notch_fc);
 
 /* Results of the last push.  Audio: what processRxAudio() leaves in Processor_AudioBuffer_A/B
  * (audio_processor.c:377-394): per channel and block 384 int32, L/R interleaved.  dst is
@@ -211,6 +219,9 @@ typedef struct ua3reo_tx_settings {
 void ua3reo_tx_defaults(ua3reo_tx_settings *s);
 int ua3reo_tx_enable(ua3reo_ctx *ctx, uint32_t max_blocks);
 int ua3reo_tx_set(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const ua3reo_tx_settings *settings);
+/* Like ua3reo_rx_set_live(): mode, mute, tune, key, power and the FM index follow the settings, the lattice tables
+ * selected by the last ua3reo_tx_set() (ReinitAudioFilters) stay and no filter state is cleared. */
+int ua3reo_tx_set_live(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const ua3reo_tx_settings *settings);
 /* n_blocks x 192 codec samples per channel: mic_host is [n_channels][n_blocks*192][2] int16 (left, right), the
  * layout of CODEC_Audio_Buffer_TX (wm8731.h:14).  One processTxAudio() per block. */
 int ua3reo_tx_process(ua3reo_ctx *ctx, const int16_t *mic_host, size_t n_blocks);

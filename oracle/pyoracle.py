@@ -129,9 +129,15 @@ def have_fw_rx():
     return os.path.exists(FW_RX)
 
 
-def run_fw_rx(frames, settings, workdir=None):
+FW_RX_B200 = os.path.join(_HERE, "_ref", "fw_rx_b200")     # same driver, firmware DSP units replaced by the GPU shim
+FW_TX_B200 = os.path.join(_HERE, "_ref", "fw_tx_b200")
+
+
+def run_fw_rx(frames, settings, workdir=None, events=(), binary=None, env=None):
     """Runs the host-built reference firmware over uint8 [n_frames, 8] frames for one channel.
-    settings: dict with the ua3reo_rx_settings field names.  Returns dict(audio int32 [nb, 384],
+    settings: dict with the ua3reo_rx_settings field names.  events: (frame_index, key, value) applied mid-stream
+    without re-initialisation; keys are settings names or the pseudo keys reinit / notch_init / fft_init.
+    binary: another build of the same driver (FW_RX_B200).  Returns dict(audio int32 [nb, 384],
     smeter float32 [nb, 2], cw float32 [nb], spectra float32 [nf, 256], waterfall uint16 [nf, 256], fft_max float32 [nf])."""
     import tempfile
     frames = np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1, 8)
@@ -141,8 +147,10 @@ def run_fw_rx(frames, settings, workdir=None):
             for k, v in settings.items():
                 if k in RX_PARAM_KEYS:
                     f.write("%s %d\n" % (RX_PARAM_KEYS[k], int(v)))
+            for at, k, v in events:
+                f.write("at %d %s %d\n" % (int(at), RX_PARAM_KEYS.get(k, k), int(v)))
         frames.tofile(fp)
-        subprocess.check_call([FW_RX, pp, fp, ap, sp])
+        subprocess.check_call([binary or FW_RX, pp, fp, ap, sp], env=env)
         a = np.fromfile(ap, dtype=np.int32).reshape(-1, 387 + 192)
         raw = np.fromfile(sp, dtype=np.uint8)
         rec = 256 * 4 + 256 * 2 + 4
@@ -184,7 +192,7 @@ def have_fw_tx():
     return os.path.exists(FW_TX)
 
 
-def run_fw_tx(mic, settings, workdir=None):
+def run_fw_tx(mic, settings, workdir=None, binary=None, env=None):
     """Runs the host-built reference firmware's processTxAudio() over int16 [n, 2] codec samples (n multiple of 192).
     Returns (iq_words int16 [n, 2], iq_float float32 [n, 2])."""
     import tempfile
@@ -196,7 +204,7 @@ def run_fw_tx(mic, settings, workdir=None):
                 if k in TX_PARAM_KEYS:
                     f.write("%s %d\n" % (TX_PARAM_KEYS[k], int(v)))
         mic.tofile(mp_)
-        subprocess.check_call([FW_TX, pp, mp_, op])
+        subprocess.check_call([binary or FW_TX, pp, mp_, op], env=env)
         raw = np.fromfile(op, dtype=np.uint8).reshape(-1, 192 * 2 * 4 + 192 * 2 * 2)
         f = np.ascontiguousarray(raw[:, :1536]).view(np.float32).reshape(-1, 2)
         w = np.ascontiguousarray(raw[:, 1536:]).view(np.int16).reshape(-1, 2)

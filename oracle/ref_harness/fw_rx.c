@@ -14,6 +14,10 @@
  *     bus driver has filled 512 samples FFT_doFFT() runs, then FFT_printFFT() + the waterfall DMA chain,
  *     which is what feeds maxValueErrors back into the auto-range (fft.c:310-316,372) and re-arms FFT_need_fft
  *   - VFO frequency is held at 0 so that FFT_moveWaterfall() (fft.c:347-351) never shifts the averages
+ * params.txt: `key value` lines applied before the init calls, and `at N key value` lines applied when N frames have
+ *   been consumed (before that frame's processing) WITHOUT any re-initialisation - what a menu handler writing TRX
+ *   does; the pseudo keys `reinit`, `notch_init` and `fft_init` call ReinitAudioFilters(), InitNotchFilter() and
+ *   FFT_Init() at that point, as TRX_setMode() / the 1 s tick / the zoom menu do (trx_manager.c:217, stm32f4xx_it.c:395).
  * audio_out: per block 384 int32 (L,R interleaved; audio_processor.c:377-394) + 3 float (S-meter max, min,
  *            CW decoder Goertzel magnitude of the block or 0) + 384 int16 (USB_AUDIO_rx_buffer_a)
  * fft_out  : per FFT frame 256 float (FFTOutput_mean) + 256 uint16 (waterfall row 0) + float maxValueFFT
@@ -67,6 +71,18 @@ static int set_param(const char *k, long v)
     return 0;
 }
 
+struct event { unsigned long at; char key[32]; long val; };
+static struct event events[64];
+static int n_events;
+
+static void fire(const struct event *e)
+{
+    if (!strcmp(e->key, "reinit")) ReinitAudioFilters();
+    else if (!strcmp(e->key, "notch_init")) InitNotchFilter();
+    else if (!strcmp(e->key, "fft_init")) FFT_Init();
+    else if (!set_param(e->key, e->val)) { fprintf(stderr, "unknown parameter %s\n", e->key); exit(2); }
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 5) { fprintf(stderr, "usage: fw_rx params.txt frames.bin audio_out.bin fft_out.bin\n"); return 2; }
@@ -74,8 +90,15 @@ int main(int argc, char **argv)
     FILE *fp = fopen(argv[1], "r");
     if (!fp) { perror(argv[1]); return 2; }
     char key[64]; long val;
-    while (fscanf(fp, "%63s %ld", key, &val) == 2)
-        if (!set_param(key, val)) { fprintf(stderr, "unknown parameter %s\n", key); return 2; }
+    while (fscanf(fp, "%63s", key) == 1) {
+        if (!strcmp(key, "at")) {
+            struct event *e = &events[n_events];
+            if (n_events >= 64 || fscanf(fp, "%lu %31s %ld", &e->at, e->key, &e->val) != 3) { fprintf(stderr, "bad `at` line\n"); return 2; }
+            n_events++;
+            continue;
+        }
+        if (fscanf(fp, "%ld", &val) != 1 || !set_param(key, val)) { fprintf(stderr, "unknown parameter %s\n", key); return 2; }
+    }
     fclose(fp);
     FILE *fi = fopen(argv[2], "rb"), *fa = fopen(argv[3], "wb"), *ff = fopen(argv[4], "wb");
     if (!fi || !fa || !ff) { perror("open"); return 2; }
@@ -92,6 +115,7 @@ int main(int argc, char **argv)
     uint8_t frame[8];
     unsigned long n = 0;
     while (fread(frame, 1, 8, fi) == 8) {
+        for (int e = 0; e < n_events; e++) if (events[e].at == n) fire(&events[e]);
         memcpy(ua3_bus_frame, frame, 8);
         ua3_bus_pos = 0;
         FPGA_fpgadata_iqclock();

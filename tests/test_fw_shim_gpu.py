@@ -1,0 +1,106 @@
+"""The firmware-name shim (ua3reo-ddc-transceiver_b200/host/ua3reo_fw_shim.c) as a drop-in: the SAME firmware driver
+(oracle/ref_harness/fw_rx.c / fw_tx.c around the reference's own fpga.c bus driver and functions.c) is built twice -
+once with the reference's DSP translation units (oracle/_ref/fw_rx, all CPU) and once with those units replaced by
+the shim over libua3reo_b200.so (oracle/_ref/fw_rx_b200, numbers from the GPU) - and both run over the same frames.
+Every processRxAudio()/processTxAudio()/FFT_doFFT() result must agree: bit-exact int32 audio / int16 USB audio /
+RGB565 rows, floats within the north_star tolerance (1e-5 relative, 120 dB SNR).
+Also covers the settings semantics the shim relies on: values the firmware reads on every call change without
+clearing state (ua3reo_rx_set_live), ReinitAudioFilters()/InitNotchFilter()/FFT_Init() do what the firmware's do."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from test_rx_gpu import check
+
+pytestmark = pytest.mark.gpu
+
+BASE = dict(mode=0, filter_width=2700, ssb_hpf_pass=300, rf_gain=50, agc=1, agc_speed=3, dnr=0, notch=0, notch_fc=1000,
+            volume=20, mute=0, fm_sql_threshold=1, fft_enabled=1, fft_zoom=1, fft_averaging=4, iq_swap=0, cw_decoder=0)
+
+
+def _need(oracle):
+    for b in (oracle.FW_RX, oracle.FW_RX_B200, oracle.FW_TX, oracle.FW_TX_B200):
+        if not os.path.exists(b):
+            pytest.skip("host-built firmware harness %s did not travel with the snapshot" % os.path.basename(b))
+
+
+def _shim_env(pkg, tmp_path_factory):
+    """Normally the shim binary finds lib/libua3reo_b200.so through its RUNPATH; the emulation aid swaps the library."""
+    env = dict(os.environ)
+    if os.path.basename(pkg.LIB_PATH) != "libua3reo_b200.so":
+        d = tmp_path_factory.mktemp("emulib")
+        os.symlink(pkg.LIB_PATH, os.path.join(d, "libua3reo_b200.so"))
+        env["LD_LIBRARY_PATH"] = str(d)
+    return env
+
+
+def _frames(n, seed):
+    rng = np.random.default_rng(seed)
+    t = np.arange(n)
+    w = np.zeros((n, 4))
+    for k in range(4):
+        w[:, k] = 2500 * np.sin(2 * np.pi * (0.011 + 0.004 * k) * t + k) + 900 * np.sin(2 * np.pi * 0.19 * t) + rng.normal(0, 250, n)
+    w *= (1.0 + 0.6 * np.sin(2 * np.pi * t / 4096.0))[:, None]
+    return np.clip(np.rint(w), -32768, 32767).astype(np.int16).astype(">i2").view(np.uint8).reshape(n, 8)
+
+
+def _compare(ref, got, what):
+    for k in ("audio", "usb", "waterfall"):
+        assert ref[k].shape == got[k].shape, "%s: %s shape" % (what, k)
+        if k == "waterfall":
+            assert np.mean(ref[k] != got[k]) <= 2e-3, "%s: waterfall rows differ" % what      # a colour step on a rounding tie
+        else:
+            check(got[k], ref[k], "%s: %s" % (what, k))
+    for k in ("smeter", "cw", "spectra"):
+        assert ref[k].shape == got[k].shape, "%s: %s shape" % (what, k)
+        check(got[k], ref[k], "%s: %s" % (what, k))
+
+
+RX_CASES = [
+    ("lsb", dict(mode=0), ()),
+    ("usb_notch_dnr", dict(mode=1, notch=1, dnr=1, notch_fc=1400), ()),
+    ("am_noagc", dict(mode=10, agc=0, filter_width=6000), ()),
+    ("nfm", dict(mode=8, filter_width=15000), ()),
+    ("cw_decoder", dict(mode=3, cw_decoder=1, filter_width=500), ()),
+    ("iq_swap_zoom4", dict(mode=2, iq_swap=1, fft_zoom=4, filter_width=0), ()),
+    # values the firmware reads on every call, changed mid-stream with no re-initialisation
+    ("live_changes", dict(mode=0), ((700, "volume", 55), (900, "agc", 0), (1300, "mode", 1), (1500, "notch", 1),
+                                    (1700, "rf_gain", 30), (2100, "dnr", 1), (2500, "mute", 1), (2700, "mute", 0),
+                                    (2900, "fft_averaging", 2))),
+    # TRX_setMode(): new mode and filter, then ReinitAudioFilters(); the notch corner moves and InitNotchFilter() follows later
+    ("reinit", dict(mode=0, notch=1), ((1000, "mode", 10), (1000, "filter_width", 6000), (1000, "reinit", 0),
+                                       (1600, "notch_fc", 2200), (2000, "notch_init", 0),
+                                       (2400, "fft_zoom", 2), (2400, "fft_init", 0))),
+]
+
+
+@pytest.mark.parametrize("name,over,events", RX_CASES, ids=[c[0] for c in RX_CASES])
+def test_rx_firmware_driver_cpu_vs_gpu_shim(pkg, oracle, tmp_path_factory, name, over, events):
+    _need(oracle)
+    s = dict(BASE); s.update(over)
+    fr = _frames(192 * 20, 77)
+    ref = oracle.run_fw_rx(fr, s, events=events)
+    got = oracle.run_fw_rx(fr, s, events=events, binary=oracle.FW_RX_B200, env=_shim_env(pkg, tmp_path_factory))
+    assert ref["audio"].shape[0] == 19 and ref["spectra"].shape[0] >= 6
+    _compare(ref, got, name)
+
+
+TX_BASE = dict(mode=1, filter_width=2700, ssb_hpf_pass=300, rf_power=20, mute=0, tune=0, key_down=0)
+TX_CASES = [("usb", dict(mode=1)), ("lsb_1k8", dict(mode=0, filter_width=1800)), ("am", dict(mode=10, filter_width=6000)),
+            ("nfm", dict(mode=8, filter_width=8000)), ("cw_key", dict(mode=3, key_down=1)), ("tune", dict(mode=1, tune=1))]
+
+
+@pytest.mark.parametrize("name,over", TX_CASES, ids=[c[0] for c in TX_CASES])
+def test_tx_firmware_driver_cpu_vs_gpu_shim(pkg, oracle, tmp_path_factory, name, over):
+    _need(oracle)
+    s = dict(TX_BASE); s.update(over)
+    rng = np.random.default_rng(5)
+    t = np.arange(192 * 12)
+    mic = np.stack([6000 * np.sin(2 * np.pi * 0.02 * t) + rng.normal(0, 500, t.size),
+                    3000 * np.sin(2 * np.pi * 0.031 * t) + rng.normal(0, 500, t.size)], 1).astype(np.int16)
+    ref_w, ref_f = oracle.run_fw_tx(mic, s)
+    got_w, got_f = oracle.run_fw_tx(mic, s, binary=oracle.FW_TX_B200, env=_shim_env(pkg, tmp_path_factory))
+    assert np.array_equal(ref_w, got_w), name + ": I/Q words on the wire differ"
+    check(got_f, ref_f, name + ": FPGA_Audio_SendBuffer")

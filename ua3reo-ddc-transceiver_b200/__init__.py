@@ -88,6 +88,8 @@ def _bind(lib):
         "ua3reo_rx_defaults": (None, [c.POINTER(RxSettings)]),
         "ua3reo_rx_enable": (c.c_int, [vp, c.c_int]),
         "ua3reo_rx_set": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_rx_set_live": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_rx_set_notch": (c.c_int, [vp, u32, u32, vp]),
         "ua3reo_rx_push_frames": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_counts": (c.c_int, [vp, c.POINTER(sz), c.POINTER(sz)]),
         "ua3reo_rx_read_audio": (c.c_int, [vp, vp, sz]),
@@ -106,6 +108,7 @@ def _bind(lib):
         "ua3reo_tx_defaults": (None, [c.POINTER(TxSettings)]),
         "ua3reo_tx_enable": (c.c_int, [vp, u32]),
         "ua3reo_tx_set": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_tx_set_live": (c.c_int, [vp, u32, u32, vp]),
         "ua3reo_tx_process": (c.c_int, [vp, vp, sz]),
         "ua3reo_tx_read_iq": (c.c_int, [vp, vp, vp, sz]),
         "ua3reo_tx_feed_duc": (c.c_int, [vp]),
@@ -246,12 +249,22 @@ class Receiver:
     def rx_enable(self, on=True):
         self._chk(self.lib.ua3reo_rx_enable(self._h, 1 if on else 0))
 
-    def rx_set(self, settings, first=0):
-        """settings: one RxSettings (applied to every channel from `first`) or a list, one per channel."""
+    def rx_set(self, settings, first=0, live=False):
+        """settings: one RxSettings (applied to every channel from `first`) or a list, one per channel.
+        live=True: only the fields the firmware reads on every call (no filter reselection, no state cleared)."""
         if isinstance(settings, RxSettings):
             settings = [settings] * (self.n_channels - first)
         arr = (RxSettings * len(settings))(*settings)
-        self._chk(self.lib.ua3reo_rx_set(self._h, int(first), len(settings), ctypes.cast(arr, ctypes.c_void_p)))
+        fn = self.lib.ua3reo_rx_set_live if live else self.lib.ua3reo_rx_set
+        self._chk(fn(self._h, int(first), len(settings), ctypes.cast(arr, ctypes.c_void_p)))
+
+    def rx_set_notch(self, notch_fc, first=0):
+        """InitNotchFilter() alone: notch_fc is one corner in Hz or one per channel from `first`."""
+        a = np.atleast_1d(np.asarray(notch_fc, dtype=np.uint16))
+        if a.size == 1:
+            a = np.repeat(a, self.n_channels - first)
+        a = np.ascontiguousarray(a)
+        self._chk(self.lib.ua3reo_rx_set_notch(self._h, int(first), a.size, a.ctypes.data))
 
     def rx_push_frames(self, frames):
         """frames: uint8 [n_channels, n, 8] I/Q frames (stm32_interface byte order) fed straight to the STM32 stage."""
@@ -349,11 +362,12 @@ class Receiver:
     def tx_enable(self, max_blocks=8):
         self._chk(self.lib.ua3reo_tx_enable(self._h, int(max_blocks)))
 
-    def tx_set(self, settings, first=0):
+    def tx_set(self, settings, first=0, live=False):
         if isinstance(settings, TxSettings):
             settings = [settings] * (self.n_channels - first)
         arr = (TxSettings * len(settings))(*settings)
-        self._chk(self.lib.ua3reo_tx_set(self._h, int(first), len(settings), ctypes.cast(arr, ctypes.c_void_p)))
+        fn = self.lib.ua3reo_tx_set_live if live else self.lib.ua3reo_tx_set
+        self._chk(fn(self._h, int(first), len(settings), ctypes.cast(arr, ctypes.c_void_p)))
 
     def tx_process(self, mic):
         """mic: int16 [n_channels, n_blocks*192, 2] (left, right).  Returns (iq_words int16, iq_float float32), same shape."""

@@ -474,7 +474,11 @@ int ua3reo_rx_enable(ua3reo_ctx* c, int enable) {
     return UA3_OK;
 }
 
-int ua3reo_rx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_rx_settings* settings) {
+// live == false: TRX_setMode() + ReinitAudioFilters() + InitNotchFilter() (filter tables reselected, their states cleared).
+// live == true : only the fields processRxAudio()/FFT_doFFT() read from TRX on every call; the lattice tables, the
+//                notch coefficients and the ZoomFFT decimator stay as the last full set left them, no state is cleared.
+static int rx_apply_settings(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_rx_settings* settings, bool live,
+                             const char* who) {
     if (!c || !settings || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_rx_set: range");
     UA3_CUDA(cudaSetDevice(c->device));
     const int rc = rx_allocate(c);
@@ -483,23 +487,72 @@ int ua3reo_rx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_rx_set
     std::vector<uint8_t> flags(n, 0);
     for (uint32_t i = 0; i < n; ++i) {
         bool cl = false, chp = false;
-        if (!rx_derive(settings[i], np[i], cl, chp)) {
+        const RxParams old = np[i];
+        ua3reo_rx_settings s = settings[i];
+        if (live) { s.filter_width = c->h_set[first + i].filter_width; s.ssb_hpf_pass = c->h_set[first + i].ssb_hpf_pass; }
+        if (!rx_derive(s, np[i], cl, chp)) {
             char msg[128];
-            std::snprintf(msg, sizeof msg, "ua3reo_rx_set: channel %u: settings outside the firmware's tables", first + i);
+            std::snprintf(msg, sizeof msg, "%s: channel %u: settings outside the firmware's tables", who, first + i);
             return fail(UA3_E_INVAL, msg);
         }
-        const bool zoom_changed = np[i].fft_zoom != c->h_par[first + i].fft_zoom;
-        flags[i] = (uint8_t)((cl ? 1 : 0) | (chp ? 2 : 0) | (zoom_changed ? 4 : 0));
+        if (live) {
+            std::memcpy(np[i].lpf_k, old.lpf_k, sizeof old.lpf_k); std::memcpy(np[i].lpf_v, old.lpf_v, sizeof old.lpf_v);
+            std::memcpy(np[i].hpf_k, old.hpf_k, sizeof old.hpf_k); std::memcpy(np[i].hpf_v, old.hpf_v, sizeof old.hpf_v);
+            std::memcpy(np[i].notch, old.notch, sizeof old.notch);
+            np[i].hpf_set = old.hpf_set; np[i].fft_zoom = old.fft_zoom;
+            np[i].lpf_on = settings[i].filter_width > 0;          // `if (CurrentVFO()->Filter_Width > 0)` is read per block (audio_processor.c:448)
+        } else {
+            const bool zoom_changed = np[i].fft_zoom != old.fft_zoom;
+            flags[i] = (uint8_t)((cl ? 1 : 0) | (chp ? 2 : 0) | (zoom_changed ? 4 : 0));
+        }
     }
-    for (uint32_t i = 0; i < n; ++i) { c->h_par[first + i] = np[i]; c->h_set[first + i] = settings[i]; }
+    for (uint32_t i = 0; i < n; ++i) {
+        c->h_par[first + i] = np[i];
+        if (live) {
+            const uint16_t fw = c->h_set[first + i].filter_width, hp = c->h_set[first + i].ssb_hpf_pass, nf = c->h_set[first + i].notch_fc;
+            const uint8_t zoom = c->h_set[first + i].fft_zoom;
+            c->h_set[first + i] = settings[i];
+            c->h_set[first + i].filter_width = fw; c->h_set[first + i].ssb_hpf_pass = hp; c->h_set[first + i].notch_fc = nf;
+            c->h_set[first + i].fft_zoom = zoom;
+        } else {
+            c->h_set[first + i] = settings[i];
+        }
+    }
     UA3_CUDA(cudaMemcpyAsync(c->rx.params + first, c->h_par.data() + first, sizeof(RxParams) * n, cudaMemcpyHostToDevice,
                              c->stream));
-    UA3_CUDA(cudaMemcpyAsync(c->rx_flags, flags.data(), n, cudaMemcpyHostToDevice, c->stream));
-    int launches = 0;
-    UA3_CUDA(rx_launch_clear(c->rx, c->rx_flags, first, n, c->stream, &launches));
-    c->launches += (uint64_t)launches;
+    if (!live) {
+        UA3_CUDA(cudaMemcpyAsync(c->rx_flags, flags.data(), n, cudaMemcpyHostToDevice, c->stream));
+        int launches = 0;
+        UA3_CUDA(rx_launch_clear(c->rx, c->rx_flags, first, n, c->stream, &launches));
+        c->launches += (uint64_t)launches;
+    }
     UA3_CUDA(cudaStreamSynchronize(c->stream));
     return rx_upload_order(c);
+}
+
+int ua3reo_rx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_rx_settings* settings) {
+    return rx_apply_settings(c, first, n, settings, false, "ua3reo_rx_set");
+}
+
+int ua3reo_rx_set_live(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_rx_settings* settings) {
+    return rx_apply_settings(c, first, n, settings, true, "ua3reo_rx_set_live");
+}
+
+// InitNotchFilter() (audio_filters.c:341-346): new biquad coefficients for TRX.NotchFC, states untouched (the firmware's
+// arm_biquad_cascade_df2T_init_f32 call there is commented out).
+int ua3reo_rx_set_notch(ua3reo_ctx* c, uint32_t first, uint32_t n, const uint16_t* notch_fc) {
+    if (!c || !notch_fc || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_rx_set_notch: range");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const int rc = rx_allocate(c);
+    if (rc != UA3_OK) return rc;
+    for (uint32_t i = 0; i < n; ++i) {
+        rx_notch_coeffs(notch_fc[i], c->h_par[first + i].notch);
+        c->h_set[first + i].notch_fc = notch_fc[i];
+    }
+    UA3_CUDA(cudaMemcpyAsync(c->rx.params + first, c->h_par.data() + first, sizeof(RxParams) * n, cudaMemcpyHostToDevice,
+                             c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
 }
 
 // The STM32 stage alone, over I/Q frames that come from elsewhere (a real FPGA, a recording, BASELINE config 1's
@@ -808,7 +861,7 @@ int ua3reo_tx_enable(ua3reo_ctx* c, uint32_t max_blocks) {
     return UA3_OK;
 }
 
-int ua3reo_tx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_tx_settings* settings) {
+static int tx_apply_settings(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_tx_settings* settings, bool live) {
     if (!c || !settings || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_tx_set: range");
     if (!c->tx_alloc) return fail(UA3_E_STATE, "ua3reo_tx_set: call ua3reo_tx_enable first");
     UA3_CUDA(cudaSetDevice(c->device));
@@ -816,17 +869,34 @@ int ua3reo_tx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_tx_set
     std::vector<uint8_t> flags(n, 0);
     for (uint32_t i = 0; i < n; ++i) {
         bool cl = false, chp = false;
+        const TxParams old = np[i];
         if (!tx_derive(settings[i], np[i], cl, chp)) return fail(UA3_E_INVAL, "ua3reo_tx_set: settings outside the firmware's tables");
-        flags[i] = (uint8_t)((cl ? 1 : 0) | (chp ? 2 : 0));
+        if (live) {            // keep what the last ReinitAudioFilters() selected; nothing is cleared
+            std::memcpy(np[i].lpf_k, old.lpf_k, sizeof old.lpf_k); std::memcpy(np[i].lpf_v, old.lpf_v, sizeof old.lpf_v);
+            std::memcpy(np[i].hpf_k, old.hpf_k, sizeof old.hpf_k); std::memcpy(np[i].hpf_v, old.hpf_v, sizeof old.hpf_v);
+            np[i].hpf_set = old.hpf_set;
+        } else {
+            flags[i] = (uint8_t)((cl ? 1 : 0) | (chp ? 2 : 0));
+        }
     }
     for (uint32_t i = 0; i < n; ++i) c->h_txpar[first + i] = np[i];
     UA3_CUDA(cudaMemcpyAsync(c->tx.params + first, c->h_txpar.data() + first, sizeof(TxParams) * n, cudaMemcpyHostToDevice, c->stream));
-    UA3_CUDA(cudaMemcpyAsync(c->tx_flags, flags.data(), n, cudaMemcpyHostToDevice, c->stream));
-    int launches = 0;
-    UA3_CUDA(tx_launch_clear(c->tx, c->tx_flags, first, n, c->stream, &launches));
-    c->launches += (uint64_t)launches;
+    if (!live) {
+        UA3_CUDA(cudaMemcpyAsync(c->tx_flags, flags.data(), n, cudaMemcpyHostToDevice, c->stream));
+        int launches = 0;
+        UA3_CUDA(tx_launch_clear(c->tx, c->tx_flags, first, n, c->stream, &launches));
+        c->launches += (uint64_t)launches;
+    }
     UA3_CUDA(cudaStreamSynchronize(c->stream));
     return UA3_OK;
+}
+
+int ua3reo_tx_set(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_tx_settings* settings) {
+    return tx_apply_settings(c, first, n, settings, false);
+}
+
+int ua3reo_tx_set_live(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_tx_settings* settings) {
+    return tx_apply_settings(c, first, n, settings, true);
 }
 
 int ua3reo_tx_process(ua3reo_ctx* c, const int16_t* mic_host, size_t n_blocks) {
