@@ -171,6 +171,15 @@ int ua3reo_rx_read_spectra(ua3reo_ctx *ctx, float *dst_host, size_t n_frames);
  * column height (uint16_t)(mean * 30) mapped through getFFTColor() (fft.c:503-538) to RGB565, red (0xF800) when
  * the column overflows, stored fft-shifted (bin x lands at x +/- 128).  dst is [n_channels][n_frames][256] uint16. */
 int ua3reo_rx_read_waterfall(ua3reo_ctx *ctx, uint16_t *dst_host, size_t n_frames);
+/* Waterfall history: wtf_buffer[FFT_WTF_HEIGHT = 50][256] (fft.c:29,353-379) of every channel, row 0 the newest;
+ * dst is [n_channels][50][256] uint16. */
+#define UA3_WTF_ROWS 50u
+int ua3reo_rx_read_waterfall_history(ua3reo_ctx *ctx, uint16_t *dst_host);
+/* A retune as FFT_printFFT() sees it (fft.c:347-351): freq_diff_hz[i] = new VFO frequency - previous one for channel
+ * first+i.  The next FFT frame of the channel applies FFT_moveWaterfall() (fft.c:458-504) between its averaging and
+ * its row: every stored row moves (freq_diff / 187) * FFT_Zoom pixels with zero fill and FFTOutput_mean is rotated in
+ * place the way the firmware's loop does it.  Differences queued before that frame add up. */
+int ua3reo_rx_move_waterfall(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const int32_t *freq_diff_hz);
 /* CW decoder front end (cw_decoder.c:43-66): the Goertzel magnitude at 350 Hz of every 192-sample block of the final
  * audio, for channels in CW_L / CW_U with cw_decoder set (0 elsewhere).  dst is [n_channels][n_blocks] float. */
 int ua3reo_rx_read_cw(ua3reo_ctx *ctx, float *dst_host, size_t n_blocks);

@@ -122,7 +122,7 @@ FW_RX = os.path.join(_HERE, "_ref", "fw_rx")
 RX_PARAM_KEYS = {"mode": "mode", "filter_width": "filter_width", "ssb_hpf_pass": "hpf_pass", "rf_gain": "rf_gain",
                  "agc": "agc", "agc_speed": "agc_speed", "dnr": "dnr", "notch": "notch", "notch_fc": "notch_fc",
                  "volume": "volume", "mute": "mute", "fm_sql_threshold": "fm_sql", "fft_enabled": "fft_enabled",
-                 "fft_zoom": "fft_zoom", "fft_averaging": "fft_averaging", "iq_swap": "iq_swap", "cw_decoder": "cw_decoder"}
+                 "fft_zoom": "fft_zoom", "fft_averaging": "fft_averaging", "iq_swap": "iq_swap", "cw_decoder": "cw_decoder", "freq": "freq"}
 
 
 def have_fw_rx():
@@ -142,7 +142,7 @@ def run_fw_rx(frames, settings, workdir=None, events=(), binary=None, env=None):
     import tempfile
     frames = np.ascontiguousarray(frames, dtype=np.uint8).reshape(-1, 8)
     with tempfile.TemporaryDirectory(dir=workdir) as d:
-        pp, fp, ap, sp = (os.path.join(d, n) for n in ("p.txt", "frames.bin", "audio.bin", "fft.bin"))
+        pp, fp, ap, sp, wp = (os.path.join(d, n) for n in ("p.txt", "frames.bin", "audio.bin", "fft.bin", "wtf.bin"))
         with open(pp, "w") as f:
             for k, v in settings.items():
                 if k in RX_PARAM_KEYS:
@@ -150,7 +150,7 @@ def run_fw_rx(frames, settings, workdir=None, events=(), binary=None, env=None):
             for at, k, v in events:
                 f.write("at %d %s %d\n" % (int(at), RX_PARAM_KEYS.get(k, k), int(v)))
         frames.tofile(fp)
-        subprocess.check_call([binary or FW_RX, pp, fp, ap, sp], env=env)
+        subprocess.check_call([binary or FW_RX, pp, fp, ap, sp, wp], env=env)
         a = np.fromfile(ap, dtype=np.int32).reshape(-1, 387 + 192)
         raw = np.fromfile(sp, dtype=np.uint8)
         rec = 256 * 4 + 256 * 2 + 4
@@ -163,6 +163,7 @@ def run_fw_rx(frames, settings, workdir=None, events=(), binary=None, env=None):
             "spectra": np.ascontiguousarray(raw[:, :1024]).view(np.float32).reshape(-1, 256),
             "waterfall": np.ascontiguousarray(raw[:, 1024:1536]).view(np.uint16).reshape(-1, 256),
             "fft_max": np.ascontiguousarray(raw[:, 1536:1540]).view(np.float32).reshape(-1),
+            "wtf_history": np.fromfile(wp, dtype=np.uint16).reshape(50, 256),
         }
 
 

@@ -21,6 +21,9 @@
  * audio_out: per block 384 int32 (L,R interleaved; audio_processor.c:377-394) + 3 float (S-meter max, min,
  *            CW decoder Goertzel magnitude of the block or 0) + 384 int16 (USB_AUDIO_rx_buffer_a)
  * fft_out  : per FFT frame 256 float (FFTOutput_mean) + 256 uint16 (waterfall row 0) + float maxValueFFT
+ * optional 5th argument: file that receives wtf_buffer (50 x 256 uint16, row 0 newest) as it stands at the end
+ * `freq` (as key or event) sets CurrentVFO()->Freq only - nothing retunes, FFT_printFFT() just sees the difference and
+ *   moves the waterfall and the averages (fft.c:347-351,458-504)
  */
 #include "stm32f4xx_hal.h"
 #include "arm_math.h"
@@ -41,6 +44,7 @@ extern int ua3_bus_pos;
 void ua3_lcd_stub_init(void);
 const float *ua3_fft_output_mean(void);
 const uint16_t *ua3_fft_wtf_row0(void);
+const uint16_t *ua3_fft_wtf_all(void);
 float ua3_fft_max_value(void);
 float ua3_cw_magnitude(void);
 void ua3_set_tick(uint32_t t);
@@ -66,7 +70,7 @@ static int set_param(const char *k, long v)
     P("rf_gain", TRX.RF_Gain) P("agc", TRX.AGC) P("agc_speed", TRX.Agc_speed) P("dnr", TRX.DNR)
     P("notch", TRX.NotchFilter) P("notch_fc", TRX.NotchFC) P("volume", TRX.Volume) P("mute", TRX.Mute)
     P("fm_sql", TRX.FM_SQL_threshold) P("fft_enabled", TRX.FFT_Enabled) P("fft_zoom", TRX.FFT_Zoom)
-    P("fft_averaging", TRX.FFT_Averaging) P("iq_swap", TRX_IQ_swap) P("squelched", TRX_squelched) P("cw_decoder", TRX.CWDecoder)
+    P("fft_averaging", TRX.FFT_Averaging) P("freq", TRX.VFO_A.Freq) P("iq_swap", TRX_IQ_swap) P("squelched", TRX_squelched) P("cw_decoder", TRX.CWDecoder)
 #undef P
     return 0;
 }
@@ -146,5 +150,11 @@ int main(int argc, char **argv)
         }
     }
     fclose(fi); fclose(fa); fclose(ff);
+    if (argc > 5) {
+        FILE *fw = fopen(argv[5], "wb");
+        if (!fw) { perror(argv[5]); return 2; }
+        fwrite(ua3_fft_wtf_all(), sizeof(uint16_t), FFT_WTF_HEIGHT * FFT_PRINT_SIZE, fw);
+        fclose(fw);
+    }
     return 0;
 }

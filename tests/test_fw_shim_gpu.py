@@ -47,9 +47,9 @@ def _frames(n, seed):
 
 
 def _compare(ref, got, what):
-    for k in ("audio", "usb", "waterfall"):
+    for k in ("audio", "usb", "waterfall", "wtf_history"):
         assert ref[k].shape == got[k].shape, "%s: %s shape" % (what, k)
-        if k == "waterfall":
+        if k in ("waterfall", "wtf_history"):
             assert np.mean(ref[k] != got[k]) <= 2e-3, "%s: waterfall rows differ" % what      # a colour step on a rounding tie
         else:
             check(got[k], ref[k], "%s: %s" % (what, k))
@@ -73,6 +73,9 @@ RX_CASES = [
     ("reinit", dict(mode=0, notch=1), ((1000, "mode", 10), (1000, "filter_width", 6000), (1000, "reinit", 0),
                                        (1600, "notch_fc", 2200), (2000, "notch_init", 0),
                                        (2400, "fft_zoom", 2), (2400, "fft_init", 0))),
+    # retunes as FFT_printFFT() sees them: rows and averages move sideways (FFT_moveWaterfall, fft.c:458-504)
+    ("retune_up_down", dict(mode=0), ((1100, "freq", 3000), (2300, "freq", 1000), (3300, "freq", 1100))),
+    ("retune_zoom2_far", dict(mode=0, fft_zoom=2), ((1500, "freq", 20000), (2800, "freq", 2000))),
 ]
 
 

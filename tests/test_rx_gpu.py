@@ -40,7 +40,7 @@ def golden():
     return z, json.loads(bytes(z["meta"]).decode())
 
 
-def _run_frames_through_gpu(pkg, oracle, cases, n_adc, pushes, seed):
+def _run_frames_through_gpu(pkg, oracle, cases, n_adc, pushes, seed, retune_hz=None):
     """Frames come from the GPU DDC itself (all channels share tuning word and ADC stream)."""
     fs = 49152000.0
     t = np.arange(n_adc, dtype=np.float64)
@@ -54,6 +54,8 @@ def _run_frames_through_gpu(pkg, oracle, cases, n_adc, pushes, seed):
     rx.set_fcw([605867] * len(cases))
     rx.rx_enable(True)
     rx.rx_set([rx.rx_defaults(**c) for c in cases])
+    if retune_hz is not None and any(retune_hz):
+        rx.move_waterfall(np.asarray(retune_hz, np.int32))     # seen by the first FFT frame's display pass
     frames, audio, spec, off = [], [], [], 0
     extra = {}
     for p in pushes:
@@ -63,8 +65,10 @@ def _run_frames_through_gpu(pkg, oracle, cases, n_adc, pushes, seed):
         extra.setdefault("cw", []).append(rx.read_cw())
         extra.setdefault("usb", []).append(rx.read_audio_usb())
     sm = rx.read_smeter()
+    hist = rx.read_waterfall_history()
     rx.close()
     _run_frames_through_gpu.extra = {k: np.concatenate(v, 1) for k, v in extra.items()}
+    _run_frames_through_gpu.extra["wtf_history"] = hist
     return np.concatenate(frames, 1), np.concatenate(audio, 1), np.concatenate(spec, 1), sm
 
 
@@ -76,7 +80,8 @@ def test_against_reference_firmware_fixtures(pkg, oracle, golden):
     keys = ("mode", "agc", "agc_speed", "dnr", "notch", "mute", "volume", "rf_gain", "fm_sql_threshold", "fft_enabled",
             "fft_averaging", "fft_zoom", "iq_swap", "cw_decoder", "filter_width", "ssb_hpf_pass", "notch_fc")
     frames, audio, spec, sm = _run_frames_through_gpu(
-        pkg, oracle, [{k: c["settings"][k] for k in keys} for c in cases], 1024 * n_frames, [1024 * n_frames], 20261018)
+        pkg, oracle, [{k: c["settings"][k] for k in keys} for c in cases], 1024 * n_frames, [1024 * n_frames], 20261018,
+        retune_hz=[c.get("retune_hz", 0) for c in cases])
     assert np.array_equal(frames[0], z["frames"]), "GPU DDC frames differ from the fixture's golden frames"
     exact = 0
     for i, c in enumerate(cases):
@@ -93,6 +98,11 @@ def test_against_reference_firmware_fixtures(pkg, oracle, golden):
         if c["settings"]["fft_enabled"]:
             wf, rwf = _run_frames_through_gpu.extra["waterfall"][i], z[c["name"] + "/waterfall"]
             assert (wf != rwf).mean() <= 0.01, c["name"] + " waterfall row"      # a height on a rounding edge may flip one column
+            # the 50-row history ring (wtf_buffer, fft.c:29,353-358) incl. the sideways move of a retune (:458-504)
+            hist, rhist = _run_frames_through_gpu.extra["wtf_history"][i], z[c["name"] + "/wtf_history"]
+            assert hist.shape == rhist.shape == (50, 256)
+            assert (hist != rhist).mean() <= 0.01 * 2 / 50, c["name"] + " waterfall history"
+            assert np.array_equal(hist[0], wf[-1]) and not hist[2:].any()
         usb, rusb = _run_frames_through_gpu.extra["usb"][i], z[c["name"] + "/usb"]
         assert np.abs(usb.astype(np.int32) - rusb.astype(np.int32)).max() <= 1, c["name"] + " USB audio packing"
         cwm, rcw = _run_frames_through_gpu.extra["cw"][i], z[c["name"] + "/cw"]

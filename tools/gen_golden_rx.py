@@ -35,6 +35,9 @@ CASES = [
     dict(name="usb_zoom2", settings=dict(mode=1, fft_zoom=2)),
     dict(name="lsb_zoom8_notch", settings=dict(mode=0, fft_zoom=8, notch=1)),
     dict(name="am_zoom16", settings=dict(mode=10, filter_width=6000, fft_zoom=16)),
+    # retune seen by the first FFT_printFFT(): FFT_moveWaterfall() rotates the averages in place (fft.c:347-351,458-504)
+    dict(name="usb_retune_up", settings=dict(mode=1), retune_hz=3000),
+    dict(name="lsb_zoom2_retune_down", settings=dict(mode=0, fft_zoom=2), retune_hz=-4000),
 ]
 DEFAULTS = dict(mode=0, agc=1, agc_speed=3, dnr=0, notch=0, mute=0, volume=20, rf_gain=50, fm_sql_threshold=1, fft_enabled=1,
                 fft_averaging=4, fft_zoom=1, iq_swap=0, cw_decoder=0, filter_width=2700, ssb_hpf_pass=300, notch_fc=1000)
@@ -60,13 +63,15 @@ def main():
     n_frames = 192 * 7 + 1            # 7 audio blocks, 2 FFT frames
     frames = make_frames(20261018, n_frames)
     out = {"frames": frames, "meta": np.frombuffer(json.dumps(
-        {"cases": [dict(name=c["name"], settings={**DEFAULTS, **c["settings"]}) for c in CASES],
+        {"cases": [dict(name=c["name"], settings={**DEFAULTS, **c["settings"]}, retune_hz=c.get("retune_hz", 0)) for c in CASES],
          "n_frames": n_frames, "generator": "tools/gen_golden_rx.py", "source": "oracle/_ref/fw_rx (reference firmware C, host-built)"}
     ).encode(), dtype=np.uint8)}
     for c in CASES:
         s = {**DEFAULTS, **c["settings"]}
-        r = pyoracle.run_fw_rx(frames, s)
-        for k in ("audio", "smeter", "cw", "usb", "spectra", "waterfall", "fft_max"):
+        # the VFO frequency is a uint32: a downward retune is the wrapped difference, as in Freq - currentFFTFreq
+        ev = ((100, "freq", c["retune_hz"] & 0xFFFFFFFF),) if c.get("retune_hz") else ()
+        r = pyoracle.run_fw_rx(frames, s, events=ev)
+        for k in ("audio", "smeter", "cw", "usb", "spectra", "waterfall", "fft_max", "wtf_history"):
             out[c["name"] + "/" + k] = r[k]
         print("%-28s audio %s spectra %s  rms L %.1f" % (c["name"], r["audio"].shape, r["spectra"].shape,
                                                          r["audio"][:, 0::2].astype(float).std()))

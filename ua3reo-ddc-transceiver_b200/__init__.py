@@ -97,6 +97,8 @@ def _bind(lib):
         "ua3reo_rx_read_audio_usb": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_smeter": (c.c_int, [vp, vp, c.c_int]),
         "ua3reo_rx_read_waterfall": (c.c_int, [vp, vp, sz]),
+        "ua3reo_rx_read_waterfall_history": (c.c_int, [vp, vp]),
+        "ua3reo_rx_move_waterfall": (c.c_int, [vp, u32, u32, vp]),
         "ua3reo_rx_read_cw": (c.c_int, [vp, vp, sz]),
         "ua3reo_adc_stats": (c.c_int, [vp, c.POINTER(c.c_int16), c.POINTER(c.c_int16), c.POINTER(u32), c.c_int]),
         "ua3reo_smeter_dbm": (c.c_int16, [c.c_float, c.c_float, c.c_uint8]),
@@ -310,6 +312,20 @@ class Receiver:
         out = np.empty((self.n_channels, nf, FFT_BINS), np.uint16)
         self._chk(self.lib.ua3reo_rx_read_waterfall(self._h, out.ctypes.data, nf))
         return out
+
+    def read_waterfall_history(self):
+        """uint16 [n_channels, 50, 256]: the firmware's wtf_buffer per channel, row 0 the newest."""
+        out = np.empty((self.n_channels, 50, FFT_BINS), np.uint16)
+        self._chk(self.lib.ua3reo_rx_read_waterfall_history(self._h, out.ctypes.data))
+        return out
+
+    def move_waterfall(self, freq_diff_hz, first=0):
+        """A retune as FFT_printFFT() sees it: Hz difference per channel (or one for all), applied by the next FFT frame."""
+        a = np.atleast_1d(np.asarray(freq_diff_hz, dtype=np.int32))
+        if a.size == 1:
+            a = np.repeat(a, self.n_channels - first)
+        a = np.ascontiguousarray(a)
+        self._chk(self.lib.ua3reo_rx_move_waterfall(self._h, int(first), a.size, a.ctypes.data))
 
     def read_cw(self):
         """float32 [n_channels, blocks_of_last_push]: Goertzel magnitude of the CW decoder front end."""

@@ -432,6 +432,9 @@ static int rx_allocate(ua3reo_ctx* c) {
     UA3_CUDA(dev_alloc(c, &r.spectra, (size_t)c->n_ch * r.spec_ch_stride));
     UA3_CUDA(dev_alloc(c, &r.waterfall, (size_t)c->n_ch * r.spec_ch_stride));
     UA3_CUDA(dev_alloc(c, &r.cw_mag, (size_t)c->n_ch * r.max_audio_blocks));
+    UA3_CUDA(dev_alloc(c, &r.wtf_hist, (size_t)c->n_ch * kWtfRows * kFftBins));
+    UA3_CUDA(dev_alloc(c, &r.wtf_head, (size_t)c->n_ch));
+    UA3_CUDA(dev_alloc(c, &r.wtf_pending_hz, (size_t)c->n_ch));
     UA3_CUDA(dev_alloc(c, &c->rx_flags, (size_t)c->n_ch));
     std::vector<float> win(kFftSize), tw(2 * kFftSize);
     rx_build_window(win.data());
@@ -663,6 +666,40 @@ int ua3reo_rx_read_waterfall(ua3reo_ctx* c, uint16_t* dst, size_t n_frames) {
         UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.waterfall, (size_t)c->rx.spec_ch_stride * sizeof(uint16_t), row, c->n_ch,
                                    cudaMemcpyDeviceToHost, c->stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+// CurrentVFO()->Freq - currentFFTFreq of FFT_printFFT() (fft.c:347-351): recorded per channel and applied by the next
+// FFT frame between its averaging and its row, where the firmware's display pass applies it.
+int ua3reo_rx_move_waterfall(ua3reo_ctx* c, uint32_t first, uint32_t n, const int32_t* freq_diff_hz) {
+    if (!c || !freq_diff_hz || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_rx_move_waterfall: range");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_move_waterfall: STM32 stage not enabled");
+    UA3_CUDA(cudaSetDevice(c->device));
+    // accumulate on the host copy so that two retunes between FFT frames add up like Freq - currentFFTFreq does
+    std::vector<int32_t> pend(n);
+    UA3_CUDA(cudaMemcpyAsync(pend.data(), c->rx.wtf_pending_hz + first, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; ++i) pend[i] += freq_diff_hz[i];
+    UA3_CUDA(cudaMemcpyAsync(c->rx.wtf_pending_hz + first, pend.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+// wtf_buffer (fft.c:29) of every channel in the firmware's row order: row 0 is the newest.
+int ua3reo_rx_read_waterfall_history(ua3reo_ctx* c, uint16_t* dst) {
+    if (!c || !dst) return fail(UA3_E_INVAL, "ua3reo_rx_read_waterfall_history: null argument");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_waterfall_history: STM32 stage not enabled");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t per_ch = (size_t)kWtfRows * kFftBins;
+    std::vector<uint16_t> ring((size_t)c->n_ch * per_ch);
+    std::vector<uint32_t> head(c->n_ch);
+    UA3_CUDA(cudaMemcpyAsync(ring.data(), c->rx.wtf_hist, ring.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaMemcpyAsync(head.data(), c->rx.wtf_head, head.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    for (uint32_t ch = 0; ch < c->n_ch; ++ch)
+        for (int y = 0; y < kWtfRows; ++y)
+            std::memcpy(dst + ch * per_ch + (size_t)y * kFftBins,
+                        ring.data() + ch * per_ch + (size_t)((head[ch] + (uint32_t)y) % kWtfRows) * kFftBins, kFftBins * sizeof(uint16_t));
     return UA3_OK;
 }
 

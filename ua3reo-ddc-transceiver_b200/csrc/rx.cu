@@ -360,7 +360,8 @@ UA3_D void radix8(C8& z) {
 __global__ void __launch_bounds__(32)
 rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t frame_ch_stride, uint32_t start,
               uint32_t n_frames, const RxParams* __restrict__ params, RxState* __restrict__ state, uint32_t n_ch,
-              float* __restrict__ spectra, uint32_t spec_ch_stride, uint16_t* __restrict__ waterfall) {
+              float* __restrict__ spectra, uint32_t spec_ch_stride, uint16_t* __restrict__ waterfall,
+              uint16_t* __restrict__ wtf_hist, uint32_t* __restrict__ wtf_head, int32_t* __restrict__ wtf_pending_hz) {
     __shared__ float s_re[kFftSize], s_im[kFftSize];
     __shared__ float s_dec[2][kFftSize / 2];                           // decimated samples of the ZoomFFT branch
     const int lane = threadIdx.x & 31;
@@ -535,9 +536,9 @@ rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t 
         if (P.mode == kModeLoopback) mv = 60000.0f;
         const float inv = 1.0f / mv;                                   // arm_scale_f32(FFTInput, 1.0f / maxValueFFT, ...)
         // temporal averaging into FFTOutput_mean (:324-328) and the display pass's overflow count (:369-373)
-        uint32_t nerr = 0;
         float* out = spectra + (size_t)ch * spec_ch_stride + (size_t)fi * kFftBins;
         uint16_t* wf = waterfall + (size_t)ch * spec_ch_stride + (size_t)fi * kFftBins;
+        uint16_t* hist = wtf_hist + (size_t)ch * kWtfRows * kFftBins;
 #pragma unroll
         for (int q = 0; q < kFftBins / 32; ++q) {
             const int bin = q * 32 + lane;
@@ -546,16 +547,61 @@ rx_fft_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t 
             if (m < x) m += (x - m) / P.fft_averaging;
             else m -= (m - x) / P.fft_averaging;
             S.fft_mean[bin] = m;
-            out[bin] = m;
+            out[bin] = m;                                             // FFTOutput_mean as FFT_doFFT() leaves it
+        }
+        __syncwarp();
+        uint32_t head = wtf_head[ch];
+        // ---- FFT_printFFT() part that feeds back into the numbers (fft.c:346-379) ----
+        // a retune since the last print shifts the averages and every stored row sideways (FFT_moveWaterfall, :458-504)
+        const int32_t hz = wtf_pending_hz[ch];
+        if (hz != 0) {
+            const int d = (int)(int16_t)(((int)(int16_t)hz / 187) * zoom);    // FFT_HZ_IN_PIXEL = 48000 / 256 in integers (fft.h:23)
+            if (d != 0) {
+                if (lane == 0) {
+                    // FFTOutput_mean is shifted IN PLACE with wrap-around, so wrapped bins read already-moved values
+                    if (d > 0) {
+                        for (int x = 0; x < kFftBins; ++x) S.fft_mean[x] = S.fft_mean[(x + d) & (kFftBins - 1)];
+                    } else {
+                        for (int x = kFftBins - 1; x >= 0; --x) S.fft_mean[x] = S.fft_mean[(x + d) & (kFftBins - 1)];
+                    }
+                }
+                for (int y = 0; y < kWtfRows; ++y) {                 // rows move without wrap, zero filled
+                    uint16_t* row = hist + (size_t)y * kFftBins;
+                    uint16_t v[kFftBins / 32];
+#pragma unroll
+                    for (int q = 0; q < kFftBins / 32; ++q) {
+                        const int nx = q * 32 + lane + d;
+                        v[q] = (nx >= 0 && nx < kFftBins) ? row[nx] : (uint16_t)0;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < kFftBins / 32; ++q) row[q * 32 + lane] = v[q];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) wtf_pending_hz[ch] = 0;
+        }
+        __syncwarp();
+        // rows move down by one (:353-358), then row 0 is drawn from the averages (:361-379)
+        head = (head + kWtfRows - 1) % kWtfRows;
+        uint16_t* row0 = hist + (size_t)head * kFftBins;
+        uint32_t nerr = 0;
+#pragma unroll
+        for (int q = 0; q < kFftBins / 32; ++q) {
+            const int bin = q * 32 + lane;
+            const float m = S.fft_mean[bin];
             // height = (uint16_t)(mean * FFT_MAX_HEIGHT); if (height > FFT_MAX_HEIGHT - 1) maxValueErrors++
             const uint32_t height = (uint32_t)(int32_t)(m * 30.0f) & 0xFFFFu;
             nerr += (height > 29u) ? 1u : 0u;
-            // FFT_printFFT (fft.c:361-379): colour of the column, stored fft-shifted
-            wf[bin ^ 128] = c_fft_colors[height > 29u ? 30u : height];
+            // colour of the column, stored fft-shifted
+            const uint16_t col = c_fft_colors[height > 29u ? 30u : height];
+            wf[bin ^ 128] = col;
+            row0[bin ^ 128] = col;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nerr += __shfl_xor_sync(UA3_FULL_MASK, nerr, o);
         __syncwarp();
+        if (lane == 0) wtf_head[ch] = head;
         if (lane == 0) { S.fft_max_value = mv; S.fft_max_errors = nerr; }
         __syncwarp();
     }
@@ -586,6 +632,12 @@ __global__ void rx_init_state_kernel(RxState* __restrict__ state, uint32_t n) {
 
 cudaError_t rx_launch_init_state(const RxBuffers& b, cudaStream_t st, int* launches) {
     cudaError_t e = cudaMemsetAsync(b.state, 0, sizeof(RxState) * (size_t)b.n_ch, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(b.wtf_hist, 0, sizeof(uint16_t) * (size_t)b.n_ch * kWtfRows * kFftBins, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(b.wtf_head, 0, sizeof(uint32_t) * (size_t)b.n_ch, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(b.wtf_pending_hz, 0, sizeof(int32_t) * (size_t)b.n_ch, st);
     if (e != cudaSuccess) return e;
     UA3_LAUNCH(rx_init_state_kernel, (b.n_ch + 127u) / 128u, 128, 0, st, b.state, b.n_ch);
     if (launches) *launches += 1;
@@ -669,7 +721,7 @@ cudaError_t rx_launch_audio(const RxBuffers& b, uint32_t start, uint32_t n_block
 cudaError_t rx_launch_fft(const RxBuffers& b, uint32_t start, uint32_t n_frames, cudaStream_t st, int* launches) {
     if (!n_frames) return cudaSuccess;
     UA3_LAUNCH(rx_fft_kernel, b.n_ch, 32, 0, st, b.frames, b.ring_mask, b.frame_ch_stride, start, n_frames, b.params,
-               b.state, b.n_ch, b.spectra, b.spec_ch_stride, b.waterfall);
+               b.state, b.n_ch, b.spectra, b.spec_ch_stride, b.waterfall, b.wtf_hist, b.wtf_head, b.wtf_pending_hz);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

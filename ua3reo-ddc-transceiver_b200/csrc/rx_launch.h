@@ -19,7 +19,13 @@ struct RxBuffers {
     float* spectra = nullptr;           // [n_ch][max_fft_frames][256]
     uint16_t* waterfall = nullptr;      // [n_ch][max_fft_frames][256] RGB565 rows, fft-shifted
     uint32_t spec_ch_stride = 0, max_fft_frames = 0;
+    // wtf_buffer[FFT_WTF_HEIGHT][FFT_PRINT_SIZE] (fft.c:29) per channel, kept as a ring: firmware row y is ring row
+    // (wtf_head + y) % 50, so the "shift every row down by one" of fft.c:353-358 is a head decrement
+    uint16_t* wtf_hist = nullptr;       // [n_ch][50][256]
+    uint32_t* wtf_head = nullptr;       // [n_ch]
+    int32_t* wtf_pending_hz = nullptr;  // [n_ch] CurrentVFO()->Freq - currentFFTFreq not yet applied (fft.c:347-351)
 };
+constexpr int kWtfRows = 50;            // FFT_WTF_HEIGHT (fft.h:14)
 
 cudaError_t rx_upload_constants(const float* window, const float* twiddle, const uint16_t* colors, const float* zoom_biquad,
                                 const float* zoom_fir);

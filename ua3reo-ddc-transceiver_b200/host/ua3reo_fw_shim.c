@@ -72,11 +72,13 @@ char CW_Decoder_Text[CWDECODER_STRLEN] = {0};
 /* ---- what the shim publishes beside the firmware's globals (display code and test harnesses read these) ---- */
 float ua3reo_shim_fft_mean[FFT_PRINT_SIZE];       /* FFTOutput_mean (fft.c:27) after the last FFT_doFFT() */
 uint16_t ua3reo_shim_wtf_row0[FFT_PRINT_SIZE];    /* wtf_buffer[0] (fft.c:29) after the last FFT_printFFT() */
+uint16_t ua3reo_shim_wtf_buffer[UA3_WTF_ROWS * FFT_PRINT_SIZE];   /* wtf_buffer (fft.c:29), row 0 newest, after FFT_printFFT() */
 float ua3reo_shim_cw_magnitude = 0.0f;            /* Goertzel magnitude of the last CW block (cw_decoder.c:56-66) */
 
 static ua3reo_ctx *rx_ctx;      /* audio: processRxAudio / processTxAudio */
 static ua3reo_ctx *fft_ctx;     /* panorama: FFT_doFFT */
 static uint16_t latched_notch_fc = 1000;
+static uint32_t shim_fft_freq = 0;       /* currentFFTFreq (fft.c:31) */
 static float smeter_seen_max, smeter_seen_min;
 static ua3reo_rx_settings rx_last, fft_last;
 static ua3reo_tx_settings tx_last;
@@ -308,6 +310,11 @@ void FFT_doFFT(void)
     if (NeedFFTInputBuffer) return;
     ensure_contexts();
     apply_fft(false);
+    if (CurrentVFO()->Freq != shim_fft_freq) {                    /* fft.c:347-351: applied on the device after this frame's averaging */
+        const int32_t diff = (int32_t)(CurrentVFO()->Freq - shim_fft_freq);
+        CHECK(ua3reo_rx_move_waterfall(fft_ctx, 0, 1, &diff));
+        shim_fft_freq = CurrentVFO()->Freq;
+    }
     static uint8_t frames[FFT_SIZE * UA3_FRAME_BYTES];
     memset(frames, 0, sizeof frames);
     for (int i = 0; i < FFT_SIZE; i++) {                          /* FFTInput_I/Q hold the SPEC words (fpga.c:307-339) */
@@ -328,6 +335,7 @@ void FFT_printFFT(void)
 {
     if (!TRX.FFT_Enabled) return;
     if (FFT_need_fft) return;
+    CHECK(ua3reo_rx_read_waterfall_history(fft_ctx, ua3reo_shim_wtf_buffer));
     FFT_need_fft = true;
 }
 void FFT_printWaterfallDMA(void) {}
