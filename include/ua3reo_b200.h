@@ -187,6 +187,22 @@ int ua3reo_rx_read_cw(ua3reo_ctx *ctx, float *dst_host, size_t n_blocks);
  * resets to +2000 / -2000 when the MCU reads them with command 2, stm32_interface.v:172-205 <- fpga.c:222-284), and
  * the number of samples at either rail of the 12-bit range (what the AD9226 flags on its OTR pin). */
 int ua3reo_adc_stats(ua3reo_ctx *ctx, int16_t *adc_min, int16_t *adc_max, uint32_t *n_rail, int reset);
+/* GET PARAMS, command 2 of the wire protocol: the five bytes stm32_interface.v:172-205 returns (flags, ADC_MIN/ADC_MAX
+ * nibbles and low bytes, encoder) built from the tracked ADC extremes, which are reset afterwards as the FPGA does, and
+ * the two values FPGA_fpgadata_getparam() (fpga.c:222-284) decodes from them - TRX_ADC_MINAMPLITUDE sign-extended,
+ * TRX_ADC_MAXAMPLITUDE not (a firmware quirk, kept).  ADC_OTR (bit 0) = a sample reached a rail since the last read;
+ * DAC_OTR (bit 1) = dac_otr as given by the caller (e.g. a change of ua3reo_duc_read_otr()); key/encoder bits are 0.
+ * packet and either amplitude pointer may be NULL. */
+int ua3reo_get_params(ua3reo_ctx *ctx, uint8_t packet[5], int16_t *adc_min_amplitude, int16_t *adc_max_amplitude, int dac_otr);
+/* TRX_DoAutoGain() (trx_manager.c:268-356, called every 100 ms from stm32f4xx_it.c:422): the ATT / preamp decision
+ * state machine driven by TRX_ADC_MAXAMPLITUDE.  Pure host function; `stage` and `wait` are autogain_stage and
+ * autogain_wait_reaction, the four outputs are TRX.Preamp, TRX.ATT, TRX.LPF and TRX.BPF. */
+typedef struct ua3reo_autogain {
+    uint8_t stage, wait;
+    uint8_t preamp, att, lpf, bpf;
+} ua3reo_autogain;
+void ua3reo_autogain_init(ua3reo_autogain *st);
+void ua3reo_autogain_step(ua3reo_autogain *st, int16_t adc_max_amplitude);
 /* TRX_RX_dBm of the 100 ms housekeeping tick (stm32f4xx_it.c:398-409) from the S-meter extremes: pure host function. */
 int16_t ua3reo_smeter_dbm(float sample_max, float sample_min, uint8_t rf_gain);
 /* S-meter accumulators Processor_RX_Audio_Samples_MAX/MIN_value (audio_processor.c:491-501): dst [n_channels][2];

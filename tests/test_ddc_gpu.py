@@ -190,3 +190,27 @@ def test_adc_min_max_tracking(pkg, oracle):
     rx.push(small)
     assert rx.adc_stats() == (5, 5, 0)                   # min(2000, 5), max(-2000, 5)
     rx.close()
+
+
+def test_get_params_packet(pkg, oracle):
+    """Command 2 of the wire protocol (stm32_interface.v:172-205) and its decode by FPGA_fpgadata_getparam() (fpga.c:222-284)."""
+    rx = pkg.Receiver(2, 1 << 14)
+    rx.adc_stats()                                        # arm
+    adc = np.clip(oracle.synth_adc(1 << 14, seed=9) // 4, -400, 700).astype(np.int16)
+    rx.push(adc)
+    pkt, mn, mx = rx.get_params()
+    lo, hi = int(adc.min()), int(adc.max())
+    assert lo < 0 < hi
+    assert pkt[0] == 0                                    # no sample at a rail, no DAC overflow, no keys
+    assert pkt[1] == (((lo & 0xFFF) >> 8) << 4 | ((hi & 0xFFF) >> 8)) and pkt[2] == (lo & 0xFF) and pkt[3] == (hi & 0xFF) and pkt[4] == 0
+    assert (mn, mx) == (lo, hi)
+    assert rx.adc_stats() == (2000, -2000, 0)             # the read reset the extremes (ADC_MINMAX_RESET, k == 203)
+    rx.push(np.full(1 << 12, -7, np.int16))
+    pkt, mn, mx = rx.get_params(dac_otr=True)
+    assert pkt[0] == 2 and mn == -7
+    assert mx == ((-7) & 0xFFF)                           # firmware quirk: the maximum is not sign-extended (fpga.c:270)
+    rail = np.zeros(1 << 12, np.int16); rail[5] = 2047
+    rx.push(rail)
+    pkt, mn, mx = rx.get_params()
+    assert pkt[0] == 1 and (mn, mx) == (0, 2047)          # ADC_OTR
+    rx.close()

@@ -102,6 +102,9 @@ def _bind(lib):
         "ua3reo_rx_read_cw": (c.c_int, [vp, vp, sz]),
         "ua3reo_adc_stats": (c.c_int, [vp, c.POINTER(c.c_int16), c.POINTER(c.c_int16), c.POINTER(u32), c.c_int]),
         "ua3reo_smeter_dbm": (c.c_int16, [c.c_float, c.c_float, c.c_uint8]),
+        "ua3reo_get_params": (c.c_int, [vp, vp, c.POINTER(c.c_int16), c.POINTER(c.c_int16), c.c_int]),
+        "ua3reo_autogain_init": (None, [vp]),
+        "ua3reo_autogain_step": (None, [vp, c.c_int16]),
         "ua3reo_duc_enable": (c.c_int, [vp, u32]),
         "ua3reo_duc_push": (c.c_int, [vp, vp, sz]),
         "ua3reo_duc_read_dac": (c.c_int, [vp, vp, sz]),
@@ -152,6 +155,20 @@ def phrase_from_frequency(freq_hz, lib=None):
     swap = ctypes.c_int(0)
     w = lib.ua3reo_phrase_from_frequency(int(freq_hz), ctypes.byref(swap))
     return int(w), bool(swap.value)
+
+
+class AutoGain(ctypes.Structure):
+    """TRX_DoAutoGain() state (ua3reo_autogain): stage, wait counter and the Preamp / ATT / LPF / BPF decisions."""
+    _fields_ = [(n, ctypes.c_uint8) for n in ("stage", "wait", "preamp", "att", "lpf", "bpf")]
+
+    def __init__(self, lib=None):
+        super().__init__()
+        self._lib = lib or load_library()
+        self._lib.ua3reo_autogain_init(ctypes.byref(self))
+
+    def step(self, adc_max_amplitude):
+        self._lib.ua3reo_autogain_step(ctypes.byref(self), int(adc_max_amplitude))
+        return (self.stage, self.wait, self.preamp, self.att, self.lpf, self.bpf)
 
 
 class Receiver:
@@ -338,6 +355,13 @@ class Receiver:
         mn, mx, nr = ctypes.c_int16(), ctypes.c_int16(), ctypes.c_uint32()
         self._chk(self.lib.ua3reo_adc_stats(self._h, ctypes.byref(mn), ctypes.byref(mx), ctypes.byref(nr), 1 if reset else 0))
         return int(mn.value), int(mx.value), int(nr.value)
+
+    def get_params(self, dac_otr=False):
+        """Command 2 of the wire protocol: (packet uint8[5], TRX_ADC_MINAMPLITUDE, TRX_ADC_MAXAMPLITUDE); resets the extremes."""
+        pkt = np.zeros(5, np.uint8)
+        mn, mx = ctypes.c_int16(), ctypes.c_int16()
+        self._chk(self.lib.ua3reo_get_params(self._h, pkt.ctypes.data, ctypes.byref(mn), ctypes.byref(mx), 1 if dac_otr else 0))
+        return pkt, int(mn.value), int(mx.value)
 
     def read_smeter(self, reset=False):
         out = np.empty((self.n_channels, 2), np.float32)

@@ -741,6 +741,64 @@ int ua3reo_adc_stats(ua3reo_ctx* c, int16_t* adc_min, int16_t* adc_max, uint32_t
     return reset ? adc_stats_reset(c) : UA3_OK;
 }
 
+// The five bytes the FPGA puts on the bus for command 2 (stm32_interface.v:172-205) and what FPGA_fpgadata_getparam()
+// (fpga.c:222-284) makes of them.  ADC_OTR: the AD9226 flag is a pin state; here it reports "a sample sat at either
+// rail since the last read".  Front-panel keys and encoder bits are 0 (no front panel behind this library).
+int ua3reo_get_params(ua3reo_ctx* c, uint8_t packet[5], int16_t* adc_min_amplitude, int16_t* adc_max_amplitude, int dac_otr) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    int16_t mn = 0, mx = 0;
+    uint32_t rail = 0;
+    const int rc = ua3reo_adc_stats(c, &mn, &mx, &rail, /*reset=*/1);      // ADC_MINMAX_RESET=1 at k==203
+    if (rc != UA3_OK) return rc;
+    const uint32_t min12 = (uint32_t)mn & 0xFFFu, max12 = (uint32_t)mx & 0xFFFu;
+    uint8_t b[5];
+    b[0] = (uint8_t)((rail ? 1u : 0u) | (dac_otr ? 2u : 0u));
+    b[1] = (uint8_t)(((min12 >> 8) << 4) | (max12 >> 8));
+    b[2] = (uint8_t)(min12 & 0xFFu);
+    b[3] = (uint8_t)(max12 & 0xFFu);
+    b[4] = 0;
+    if (packet) std::memcpy(packet, b, 5);
+    // decode as the firmware does: the minimum is sign-extended through <<4, /16; the maximum is NOT (fpga.c:247-270)
+    int16_t dmin = 0, dmax = 0;
+    dmin = (int16_t)(dmin | ((b[1] & 0xF0) << 4));
+    dmax = (int16_t)(dmax | ((b[1] & 0x0F) << 8));
+    dmin = (int16_t)(dmin | b[2]);
+    dmin = (int16_t)(dmin << 4);
+    dmin = (int16_t)(dmin / 16);
+    dmax = (int16_t)(dmax | b[3]);
+    if (adc_min_amplitude) *adc_min_amplitude = dmin;
+    if (adc_max_amplitude) *adc_max_amplitude = dmax;
+    return UA3_OK;
+}
+
+// TRX_DoAutoGain() (trx_manager.c:268-356): one call of the input-stage state machine (stm32f4xx_it.c:422).
+void ua3reo_autogain_init(ua3reo_autogain* st) { if (st) std::memset(st, 0, sizeof *st); }
+
+void ua3reo_autogain_step(ua3reo_autogain* st, int16_t adc_max_amplitude) {
+    if (!st) return;
+    const double kLimit = 1100;                                   // AUTOGAIN_MAX_AMPLITUDE (settings.h:25)
+    const double att = std::pow(10.0, 12 / 20.0);                 // db2rateV(ATT_DB)         (functions.c:262-265, settings.h:23)
+    const double pre = std::pow(10.0, 20 / 20.0);                 // db2rateV(PREAMP_GAIN_DB) (settings.h:24)
+    const uint8_t kWait = 7;                                      // AUTOGAIN_CORRECTOR_WAITSTEP (trx_manager.h:9)
+    const double a = (double)adc_max_amplitude;
+    st->lpf = 1; st->bpf = 1;
+    auto settle = [&](bool can_raise) {
+        if (can_raise) st->wait++; else st->wait = 0;
+        if (st->wait >= kWait) { st->stage++; st->wait = 0; }
+    };
+    switch (st->stage) {
+        case 0: st->preamp = 0; st->att = 1; st->stage++; st->wait = 0; break;               // -12 dB
+        case 1: settle(a * att <= kLimit); break;
+        case 2: st->preamp = 0; st->att = 0; st->stage++; st->wait = 0; break;               // 0 dB
+        case 3: if (a > kLimit) st->stage -= 3; settle(a * pre / att <= kLimit); break;
+        case 4: st->preamp = 1; st->att = 1; st->stage++; st->wait = 0; break;               // +8 dB
+        case 5: if (a > kLimit) st->stage -= 3; settle(a * att <= kLimit); break;
+        case 6: st->preamp = 1; st->att = 0; st->stage++; st->wait = 0; break;               // +20 dB
+        case 7: if (a > kLimit) st->stage -= 3; break;
+        default: st->stage = 0; break;
+    }
+}
+
 int16_t ua3reo_smeter_dbm(float sample_max, float sample_min, uint8_t rf_gain) {
     // stm32f4xx_it.c:398-407, settings.h:11,19-21 (ADC_BITS 12, FPGA_BUS_BITS 16, ADC_VREF 1.0, ratio 4, calibration 0.2)
     float vpp = (sample_max / (float)rf_gain) - (sample_min / (float)rf_gain);
