@@ -259,8 +259,9 @@ int ua3reo_tx_feed_duc(ua3reo_ctx *ctx);
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline):
  * after ua3reo_profile_begin(ctx, max_blocks) each processed ADC block records an event before and
  * after every kernel; ua3reo_profile_end() waits for the stream and sums the elapsed times per
- * kernel over the recorded blocks.  kernel_ms[0..4] = front (NCO+mixer+CIC integrators), cic combs,
- * compensator FIR, Hilbert+delay+frame pack, state rotate; [5..6] = rx_audio, rx_fft when the STM32 stage is enabled. */
+ * kernel over the recorded blocks.  kernel_ms[0..4], in launch order = ADC widening (int16 -> int32 << 9), front
+ * (NCO+mixer+CIC integrators), cic combs + compensator FIR, Hilbert+delay+frame pack, state rotate; [5..6] = rx_audio,
+ * rx_fft when the STM32 stage is enabled. */
 #define UA3_DDC_KERNELS 5u
 #define UA3_PROFILED_KERNELS 7u
 int ua3reo_profile_begin(ua3reo_ctx *ctx, uint32_t max_blocks);

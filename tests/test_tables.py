@@ -48,8 +48,18 @@ def test_nco_rom_closed_forms(ddc_tables):
     k = np.arange(2048)
     assert np.array_equal(ddc_tables["UA3_NCO_SIN_C"], np.round(8191 * np.sin(2 * np.pi * k / 2048)).astype(int))
     assert np.array_equal(ddc_tables["UA3_NCO_COS_C"], np.round(8191 * np.cos(2 * np.pi * k / 2048)).astype(int))
-    # the front kernel computes the fine-sine ROM arithmetically (ddc_front.cuh: kSinFMul)
+    # the kernels compute the fine-sine ROM arithmetically, in place on the left-aligned phase word
+    # (ddc_front.cuh: nco_fine_level, kSinFMul / kSinFBias / kSinFShift)
     assert np.array_equal(ddc_tables["UA3_NCO_SIN_F"], (k * 6433 + (1 << 18)) >> 19)
+    assert np.array_equal(ddc_tables["UA3_NCO_SIN_F"], (k * 201 + 8224) >> 14)
+    phase = np.arange(1 << 22, dtype=np.uint64)
+    P = (phase << np.uint64(10)) & np.uint64(0xFFFFFFFF)
+    t = (P & np.uint64(0x1FFC00)) * np.uint64(201) + np.uint64(8224 << 10)
+    assert int(t.max()) < (1 << 32)                                      # no 32-bit overflow in the kernel's form
+    assert np.array_equal((t >> np.uint64(24)).astype(np.int64), ddc_tables["UA3_NCO_SIN_F"][(phase & np.uint64(0x7FF)).astype(np.int64)])
+    # ChunkState bounds of ddc_front.cuh: the two lowest CIC stages of a 512-sample chunk fit 32 bits
+    xmax = (2048 * 2047) >> 8
+    assert xmax == 16376 and 512 * xmax < (1 << 23) and (512 * 511 // 2) * xmax < (1 << 31)
     assert set(ddc_tables["UA3_NCO_COS_F"].tolist()) == {8191}
 
 

@@ -439,7 +439,7 @@ class Receiver:
         ms = (ctypes.c_double * 7)()
         nb = ctypes.c_uint32(0)
         self._chk(self.lib.ua3reo_profile_end(self._h, ms, 7, ctypes.byref(nb)))
-        names = ["front", "ciccomp", "unused", "hilb", "rotate", "rx_audio", "rx_fft"]
+        names = ["adc_expand", "front", "ciccomp", "hilb", "rotate", "rx_audio", "rx_fft"]
         return {k: float(v) for k, v in zip(names, ms)}, int(nb.value)
 
     def launch_count(self):

@@ -82,8 +82,9 @@ ddc_front_kernel(const int16_t* __restrict__ adc, uint32_t n_chunks, const uint3
 // launch with TMA bulk copies), 32 warps = 8 channel tiles x 4 chunks; the next tile's raw ADC samples are
 // fetched by a TMA bulk copy while the current tile computes.
 // ------------------------------------------------------------------------------------------------
-// big table + pre-shifted int32 tile + raw int16 tile + 2 mbarriers
-constexpr size_t kBtSmemBytes = (size_t)kBigTabWords * 4 + (size_t)kBtTG * kCicR * 6 + 64;
+// big table + two pre-shifted int32 ADC tiles (double buffer) + 3 mbarriers + 2 release counters
+constexpr size_t kBtAdcTileBytes = (size_t)kBtTG * kCicR * 4;
+constexpr size_t kBtSmemBytes = (size_t)kBigTabWords * 4 + 2 * kBtAdcTileBytes + 64;
 
 #if !defined(UA3_HOST_EMU)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -104,45 +105,68 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 #endif
 
+// int16 ADC block -> int32, pre-shifted left by 9 (see nco_mix): done once per block so that the persistent front
+// kernel can pull ready-to-use tiles with TMA and never touches the raw samples.
+__global__ void __launch_bounds__(256)
+adc_expand_kernel(const int16_t* __restrict__ adc, uint32_t n8, int32_t* __restrict__ adc9) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n8) return;
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(adc) + v);
+    const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+    I4 lo, hi;
+    lo.x = (int32_t)(int16_t)(ws[0] & 0xFFFFu) << 9; lo.y = ((int32_t)ws[0] >> 16) << 9;
+    lo.z = (int32_t)(int16_t)(ws[1] & 0xFFFFu) << 9; lo.w = ((int32_t)ws[1] >> 16) << 9;
+    hi.x = (int32_t)(int16_t)(ws[2] & 0xFFFFu) << 9; hi.y = ((int32_t)ws[2] >> 16) << 9;
+    hi.z = (int32_t)(int16_t)(ws[3] & 0xFFFFu) << 9; hi.w = ((int32_t)ws[3] >> 16) << 9;
+    I4* dst = reinterpret_cast<I4*>(adc9);
+    dst[2 * v] = lo;
+    dst[2 * v + 1] = hi;
+}
+
 __global__ void __launch_bounds__(kBtThreads, 1)
-ddc_front_bt_kernel(const int16_t* __restrict__ adc, uint32_t n_chunks, const uint32_t* __restrict__ big_tab,
-                    const uint32_t* __restrict__ fcw, const uint32_t* __restrict__ phase, uint32_t n_ch_pad,
-                    uint64_t* __restrict__ L, uint32_t l_ch_stride) {
+ddc_front_bt_kernel(const int16_t* __restrict__ adc, const int32_t* __restrict__ adc9, uint32_t n_chunks,
+                    const uint32_t* __restrict__ big_tab, const uint32_t* __restrict__ fcw,
+                    const uint32_t* __restrict__ phase, uint32_t n_ch_pad, uint64_t* __restrict__ L, uint32_t l_ch_stride) {
 #if defined(UA3_HOST_EMU)
     static uint8_t s_dyn[kBtSmemBytes] __attribute__((aligned(128)));
 #else
     extern __shared__ __align__(128) uint8_t s_dyn[];
 #endif
     uint32_t* s_bt = reinterpret_cast<uint32_t*>(s_dyn);                                    // 53248 words
-    I4* s_adc = reinterpret_cast<I4*>(s_dyn + (size_t)kBigTabWords * 4);                    // kBtTG * 512 int32
-    int16_t* s_raw = reinterpret_cast<int16_t*>(s_dyn + (size_t)kBigTabWords * 4 + (size_t)kBtTG * kCicR * 4);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dyn + (size_t)kBigTabWords * 4 + (size_t)kBtTG * kCicR * 6);
+    I4* s_adc = reinterpret_cast<I4*>(s_dyn + (size_t)kBigTabWords * 4);                    // 2 x kBtTG x 512 int32
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_dyn + (size_t)kBigTabWords * 4 + 2 * kBtAdcTileBytes);
+    uint32_t* s_done = reinterpret_cast<uint32_t*>(s_bar + 3);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t n_ctiles = n_ch_pad >> 5;
     const uint32_t n_cg = (n_ctiles + kBtCG - 1) / kBtCG, n_tg = (n_chunks + kBtTG - 1) / kBtTG;
     const uint32_t n_tiles = n_cg * n_tg;
+    const uint32_t wc = (uint32_t)warp % kBtCG, wt = (uint32_t)warp / kBtCG;
 
 #if !defined(UA3_HOST_EMU)
-    // bar[0]: table; bar[1]: raw ADC tile
+    // bar[0]: table; bar[1], bar[2]: ADC tile buffers 0 / 1 ("full").  A buffer is released by counting the warps
+    // that are done with it; the LAST warp to finish refills it for the tile two steps ahead, so no warp ever
+    // waits for the others at a CTA-wide barrier - fast warps run up to two tiles ahead of slow ones.
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar[2], 1);
+        s_done[0] = s_done[1] = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue_raw = [&](uint32_t tile) {       // thread 0: fetch the tile's raw int16 samples
-        const uint32_t tg = tile / n_cg;
-        const uint32_t chunk0 = tg * kBtTG;
-        const uint32_t bytes = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR * 2u;
-        mbar_expect_tx(&s_bar[1], bytes);
-        tma_bulk_g2s(s_raw, adc + (size_t)chunk0 * kCicR, bytes, &s_bar[1]);
+    auto issue_tile = [&](uint32_t tile, uint32_t buf) {       // one thread: fetch the tile's pre-shifted samples
+        const uint32_t chunk0 = (tile / n_cg) * kBtTG;
+        const uint32_t bytes = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR * 4u;
+        mbar_expect_tx(&s_bar[1 + buf], bytes);
+        tma_bulk_g2s(reinterpret_cast<uint8_t*>(s_adc) + buf * kBtAdcTileBytes, adc9 + (size_t)chunk0 * kCicR, bytes, &s_bar[1 + buf]);
     };
     if (tid == 0) {
         mbar_expect_tx(&s_bar[0], (uint32_t)kBigTabWords * 4u);
         for (uint32_t off = 0; off < (uint32_t)kBigTabWords * 4u; off += 16384u)
             tma_bulk_g2s(s_dyn + off, reinterpret_cast<const uint8_t*>(big_tab) + off, 16384u, &s_bar[0]);
-        if (blockIdx.x < n_tiles) issue_raw(blockIdx.x);
+        if (blockIdx.x < n_tiles) issue_tile(blockIdx.x, 0);
+        if (blockIdx.x + gridDim.x < n_tiles) issue_tile(blockIdx.x + gridDim.x, 1);
     }
     mbar_wait(&s_bar[0], 0);
 #else
@@ -150,50 +174,46 @@ ddc_front_bt_kernel(const int16_t* __restrict__ adc, uint32_t n_chunks, const ui
     __syncthreads();
 #endif
 
-    uint32_t raw_parity = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const uint32_t cg = tile % n_cg, tg = tile / n_cg;     // channel group fastest: neighbours share the ADC tile in L2
         const uint32_t chunk0 = tg * kBtTG;
-        const uint32_t n_valid = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR;
-        __syncthreads();                                       // previous tile's compute is done with s_adc
+        const uint32_t buf = it & 1u;
 #if !defined(UA3_HOST_EMU)
-        mbar_wait(&s_bar[1], raw_parity);
-        raw_parity ^= 1u;
+        mbar_wait(&s_bar[1 + buf], (it >> 1) & 1u);
 #else
-        for (uint32_t v = tid; v < n_valid; v += kBtThreads) s_raw[v] = adc[(size_t)chunk0 * kCicR + v];
-        __syncthreads();
-#endif
-        {   // int16 -> int32 << 9, 8 samples per thread step
-            const uint4* src = reinterpret_cast<const uint4*>(s_raw);
-            for (uint32_t v = tid; v < n_valid / 8; v += kBtThreads) {
-                const uint4 q = src[v];
-                const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
-                I4 lo, hi;
-                lo.x = (int32_t)(int16_t)(ws[0] & 0xFFFFu) << 9; lo.y = ((int32_t)ws[0] >> 16) << 9;
-                lo.z = (int32_t)(int16_t)(ws[1] & 0xFFFFu) << 9; lo.w = ((int32_t)ws[1] >> 16) << 9;
-                hi.x = (int32_t)(int16_t)(ws[2] & 0xFFFFu) << 9; hi.y = ((int32_t)ws[2] >> 16) << 9;
-                hi.z = (int32_t)(int16_t)(ws[3] & 0xFFFFu) << 9; hi.w = ((int32_t)ws[3] >> 16) << 9;
-                s_adc[2 * v] = lo;
-                s_adc[2 * v + 1] = hi;
-            }
+        {   // emulation: plain staging of the raw samples behind CTA-wide barriers
+            const uint32_t n_valid = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR;
+            __syncthreads();
+            int32_t* dst = reinterpret_cast<int32_t*>(s_adc) + buf * (kBtTG * kCicR);
+            for (uint32_t v = tid; v < n_valid; v += kBtThreads) dst[v] = (int32_t)adc[(size_t)chunk0 * kCicR + v] << 9;
+            __syncthreads();
         }
-        __syncthreads();                                       // s_adc complete, s_raw free again
-#if !defined(UA3_HOST_EMU)
-        if (tid == 0 && tile + gridDim.x < n_tiles) issue_raw(tile + gridDim.x);   // overlaps with the compute below
 #endif
-        const uint32_t wc = (uint32_t)warp % kBtCG, wt = (uint32_t)warp / kBtCG;
         const uint32_t ctile = cg * kBtCG + wc, chunk = chunk0 + wt;
         if (ctile < n_ctiles && chunk < n_chunks) {
             const uint32_t ch = (ctile << 5) + lane;
             const uint32_t F = fcw[ch] << 10;
             const uint32_t P0 = (phase[ch] << 10) + F * (chunk * (uint32_t)kCicR);
             uint64_t out[10];
-            front_chunk_bt(s_bt, s_adc + wt * (kCicR / 4), P0, F, out);
+            front_chunk_bt(s_bt, s_adc + buf * (kBtTG * kCicR / 4) + wt * (kCicR / 4), P0, F, out);
             uint64_t* dst = L + (size_t)ch * l_ch_stride + (size_t)(kLHalo + chunk) * kLRec;
             ulonglong2* d2 = reinterpret_cast<ulonglong2*>(dst);
 #pragma unroll
             for (int k = 0; k < 5; ++k) d2[k] = make_ulonglong2(out[2 * k], out[2 * k + 1]);
         }
+#if !defined(UA3_HOST_EMU)
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();                                         // this warp's reads of the buffer are done
+            if (atomicAdd(&s_done[buf], 1u) == (uint32_t)kBtWarps - 1u) {  // last warp out refills it
+                atomicExch(&s_done[buf], 0u);
+                __threadfence_block();
+                const uint32_t next = tile + 2u * gridDim.x;
+                if (next < n_tiles) issue_tile(next, buf);
+            }
+        }
+#endif
     }
 }
 
@@ -363,7 +383,7 @@ void build_cic_weights(uint64_t G[25]) {
 void build_nco_big_table(uint32_t* tab /* kBigTabWords */) {
     for (int k = 0; k < 2048; ++k)
         for (int sf = 0; sf < kSfLevels; ++sf)
-            tab[k * kSfLevels + sf] = nco_bigtab_entry(UA3_NCO_SIN_C[k], UA3_NCO_COS_C[k], sf);
+            tab[nco_bigtab_index((uint32_t)k, (uint32_t)sf)] = nco_bigtab_entry(UA3_NCO_SIN_C[k], UA3_NCO_COS_C[k], sf);
 }
 
 cudaError_t ddc_prepare_kernels() {
@@ -410,18 +430,24 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
     if (big) {
         const uint32_t n_tiles = (((b.n_ch_pad >> 5) + kBtCG - 1) / kBtCG) * ((n_chunks + kBtTG - 1) / kBtTG);
         const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count);
-        UA3_LAUNCH(ddc_front_bt_kernel, grid, kBtThreads, kBtSmemBytes, st, adc_dev, n_chunks, b.big_tab, b.fcw, b.phase,
+#if !defined(UA3_HOST_EMU)
+        const uint32_t n8 = n_chunks * (uint32_t)kCicR / 8u;
+        UA3_LAUNCH(adc_expand_kernel, (n8 + 255u) / 256u, 256, 0, st, adc_dev, n8, b.adc9);
+        if (launches) *launches += 1;
+#endif
+        if (ev) cudaEventRecord(ev[1], st);
+        UA3_LAUNCH(ddc_front_bt_kernel, grid, kBtThreads, kBtSmemBytes, st, adc_dev, b.adc9, n_chunks, b.big_tab, b.fcw, b.phase,
                    b.n_ch_pad, b.L, b.l_ch_stride);
     } else {
         const uint32_t n_tiles = ((n_chunks + kFrontWarps - 1) / kFrontWarps) * (b.n_ch_pad >> 5);
         const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count * 3);
+        if (ev) cudaEventRecord(ev[1], st);
         UA3_LAUNCH(ddc_front_kernel, grid, kFrontThreads, 0, st, adc_dev, n_chunks, b.nco_tab, b.fcw, b.phase, b.n_ch_pad,
                    b.L, b.l_ch_stride);
     }
-    if (ev) cudaEventRecord(ev[1], st);
+    if (ev) cudaEventRecord(ev[2], st);
     UA3_LAUNCH(ddc_ciccomp_kernel, dim3(b.n_ch, (n_frames + kCcFrames - 1) / kCcFrames), 256, 0, st, b.L, b.l_ch_stride, n_frames,
                b.YI, b.yi_stride, b.YQ, b.yq_stride);
-    if (ev) cudaEventRecord(ev[2], st);
     if (ev) cudaEventRecord(ev[3], st);
     UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + 255) / 256), 256, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
                n_frames, b.frames, b.frame_ch_stride, ring_start, b.ring_mask);

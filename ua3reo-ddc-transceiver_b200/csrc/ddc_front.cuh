@@ -15,10 +15,18 @@
 
 namespace ua3 {
 
-// NCO fine-sine ROM in closed form: UA3_NCO_SIN_F[j] == (j * 6433 + 2^18) >> 19 for all j < 2048
-// (checked exhaustively in tests/test_tables.py); cos_f ROM is the constant 8191.
-constexpr int32_t kSinFMul = 6433;
+// NCO fine-sine ROM in closed form: UA3_NCO_SIN_F[j] == (j * 201 + 8224) >> 14 for all j < 2048 (checked
+// exhaustively in tests/test_tables.py; (j * 6433 + 2^18) >> 19 is the same function); cos_f ROM is the constant
+// 8191.  The small multiplier lets the kernels apply it to the phase field IN PLACE: with the 22-bit phase
+// left-aligned in 32 bits, (P & 0x1FFC00) = j << 10 and (j << 10) * 201 + (8224 << 10) stays below 2^32, so
+// sf = that >> 24 - one mask, one multiply-add, one shift.
+constexpr uint32_t kSinFMul = 201u;
+constexpr uint32_t kSinFBias = 8224u;
+constexpr int kSinFShift = 14;
 constexpr int32_t kCosF = 8191;
+UA3_HD uint32_t nco_fine_level(uint32_t P) {
+    return ((P & 0x1FFC00u) * kSinFMul + (kSinFBias << 10)) >> (kSinFShift + 10);
+}
 
 // Packed coarse ROM word: sin_c in the high half, cos_c in the low half (both s14, sign-extended to 16).
 UA3_HD uint32_t nco_pack(int32_t sin_c, int32_t cos_c) {
@@ -32,8 +40,7 @@ UA3_HD void nco_mix(const uint32_t* __restrict__ tab, uint32_t P, int32_t a9, in
     const uint32_t w = tab[P >> 21];                        // coarse address = phase[21:11]
     const int32_t sc = (int32_t)w >> 16;
     const int32_t cc = (int32_t)(int16_t)(w & 0xFFFFu);
-    const int32_t j = (int32_t)((P >> 10) & 0x7FFu);        // fine address = phase[10:0]
-    const int32_t sf = (j * kSinFMul + (1 << 18)) >> 19;
+    const int32_t sf = (int32_t)nco_fine_level(P);          // fine-sine ROM value of phase[10:0]
     // 28-bit angle-sum products + round-half-up to 14 bits + nco_shift's [13:2]  ==  (x + 2^12) >> 15
     const int32_t s12 = (sc * kCosF + sf * cc + 4096) >> 15;
     const int32_t c12 = (cc * kCosF - sc * sf + 4096) >> 15;
@@ -41,14 +48,24 @@ UA3_HD void nco_mix(const uint32_t* __restrict__ tab, uint32_t P, int32_t a9, in
     xq = (int32_t)((uint32_t)a9 * (uint32_t)c12) >> 17;     // mixer Q = ADC * cos
 }
 
-// Fold a 16-sample partial state (32-bit, from zero) into the 64-bit chunk state: S = A16*S + l.
-// A16[r][c] = C(16, r-c): the cascade's own response to its state over 16 clocks.
-UA3_HD void fold16(uint64_t S[5], int32_t l1, int32_t l2, int32_t l3, int32_t l4, int32_t l5) {
-    S[4] += 16u * S[3] + 120u * S[2] + 560u * S[1] + 1820u * S[0] + (uint64_t)(int64_t)l5;
-    S[3] += 16u * S[2] + 120u * S[1] + 560u * S[0] + (uint64_t)(int64_t)l4;
-    S[2] += 16u * S[1] + 120u * S[0] + (uint64_t)(int64_t)l3;
-    S[1] += 16u * S[0] + (uint64_t)(int64_t)l2;
-    S[0] += (uint64_t)(int64_t)l1;
+// Fold a 16-sample partial state (32-bit, from zero) into the chunk state: S = A16*S + l, A16[r][c] = C(16, r-c)
+// (the cascade's own response to its state over 16 clocks).  The two lowest stages of the chunk state fit 32 bits:
+// over one 512-sample chunk from zero |S0| <= 512 * 16376 < 2^23 and |S1| <= C(512,2) * 16376 = 2 142 242 816 < 2^31
+// (|x| <= 2048 * 2047 >> 8 = 16376), so their products with the binomials are single 32x32->64 multiply-adds.
+struct ChunkState {
+    int32_t s0 = 0, s1 = 0;
+    uint64_t s2 = 0, s3 = 0, s4 = 0;
+};
+UA3_HD void fold16(ChunkState& S, int32_t l1, int32_t l2, int32_t l3, int32_t l4, int32_t l5) {
+    const int64_t a0 = S.s0, a1 = S.s1;
+    S.s4 += 16u * S.s3 + 120u * S.s2 + (uint64_t)(560 * a1 + 1820 * a0 + (int64_t)l5);
+    S.s3 += 16u * S.s2 + (uint64_t)(120 * a1 + 560 * a0 + (int64_t)l4);
+    S.s2 += (uint64_t)(16 * a1 + 120 * a0 + (int64_t)l3);
+    S.s1 += 16 * S.s0 + l2;
+    S.s0 += l1;
+}
+UA3_HD void chunk_state_out(const ChunkState& S, uint64_t out[5]) {
+    out[0] = (uint64_t)(int64_t)S.s0; out[1] = (uint64_t)(int64_t)S.s1; out[2] = S.s2; out[3] = S.s3; out[4] = S.s4;
 }
 
 // Whole chunk for one channel.  adc9: 512 pre-shifted samples (shared memory on the device, read
@@ -57,7 +74,7 @@ UA3_HD void fold16(uint64_t S[5], int32_t l1, int32_t l2, int32_t l3, int32_t l4
 // out[0..4] = I-rail partial states, out[5..9] = Q-rail.
 UA3_HD void front_chunk(const uint32_t* __restrict__ tab, const I4* __restrict__ adc9, uint32_t P0, uint32_t F,
                         uint64_t out[10]) {
-    uint64_t SI[5] = {0, 0, 0, 0, 0}, SQ[5] = {0, 0, 0, 0, 0};
+    ChunkState SI, SQ;
     uint32_t P = P0;
 #pragma unroll 1
     for (int sb = 0; sb < kCicR / kSub; ++sb) {
@@ -80,8 +97,8 @@ UA3_HD void front_chunk(const uint32_t* __restrict__ tab, const I4* __restrict__
         fold16(SI, i1, i2, i3, i4, i5);
         fold16(SQ, q1, q2, q3, q4, q5);
     }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) { out[k] = SI[k]; out[5 + k] = SQ[k]; }
+    chunk_state_out(SI, out);
+    chunk_state_out(SQ, out + 5);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -94,6 +111,8 @@ UA3_HD void front_chunk(const uint32_t* __restrict__ tab, const I4* __restrict__
 constexpr int kSfLevels = 26;
 constexpr int kBigTabWords = 2048 * kSfLevels;
 
+UA3_HD uint32_t nco_bigtab_index(uint32_t k, uint32_t sf) { return k * kSfLevels + sf; }
+
 UA3_HD uint32_t nco_bigtab_entry(int32_t sc, int32_t cc, int32_t sf) {
     const int32_t s12 = (sc * kCosF + sf * cc + 4096) >> 15;
     const int32_t c12 = (cc * kCosF - sc * sf + 4096) >> 15;
@@ -101,10 +120,7 @@ UA3_HD uint32_t nco_bigtab_entry(int32_t sc, int32_t cc, int32_t sf) {
 }
 
 UA3_HD void nco_mix_bt(const uint32_t* __restrict__ bt, uint32_t P, int32_t a9, int32_t& xi, int32_t& xq) {
-    const uint32_t k = P >> 21;
-    const int32_t j = (int32_t)((P >> 10) & 0x7FFu);
-    const uint32_t sf = (uint32_t)((j * kSinFMul + (1 << 18)) >> 19);
-    const uint32_t w = bt[k * kSfLevels + sf];
+    const uint32_t w = bt[nco_bigtab_index(P >> 21, nco_fine_level(P))];
     const int32_t s12 = (int32_t)w >> 16;
     const int32_t c12 = (int32_t)(int16_t)(w & 0xFFFFu);
     xi = (int32_t)((uint32_t)a9 * (uint32_t)s12) >> 17;
@@ -113,7 +129,7 @@ UA3_HD void nco_mix_bt(const uint32_t* __restrict__ bt, uint32_t P, int32_t a9, 
 
 UA3_HD void front_chunk_bt(const uint32_t* __restrict__ bt, const I4* __restrict__ adc9, uint32_t P0, uint32_t F,
                            uint64_t out[10]) {
-    uint64_t SI[5] = {0, 0, 0, 0, 0}, SQ[5] = {0, 0, 0, 0, 0};
+    ChunkState SI, SQ;
     uint32_t P = P0;
 #pragma unroll 1
     for (int sb = 0; sb < kCicR / kSub; ++sb) {
@@ -135,8 +151,8 @@ UA3_HD void front_chunk_bt(const uint32_t* __restrict__ bt, const I4* __restrict
         fold16(SI, i1, i2, i3, i4, i5);
         fold16(SQ, q1, q2, q3, q4, q5);
     }
-#pragma unroll
-    for (int k = 0; k < 5; ++k) { out[k] = SI[k]; out[5 + k] = SQ[k]; }
+    chunk_state_out(SI, out);
+    chunk_state_out(SQ, out + 5);
 }
 
 }  // namespace ua3

@@ -10,6 +10,7 @@ struct DdcBuffers {
     uint32_t max_chunks = 0, max_frames = 0;
     uint32_t* nco_tab = nullptr;   // [2048] packed coarse ROM
     uint32_t* big_tab = nullptr;   // [2048 * 26] packed (sin12, cos12) by (coarse address, fine-sine value)
+    int32_t* adc9 = nullptr;       // [max_block] the current ADC block widened to int32 and pre-shifted << 9 (adc_expand_kernel)
     int front_variant = 0;         // 0 auto, 1 force the 8 KB-table kernel, 2 force the big-table kernel
     uint32_t* fcw = nullptr;       // [n_ch_pad] 22-bit tuning words
     uint32_t* phase = nullptr;     // [n_ch_pad] 22-bit phase at the start of the next block
@@ -30,7 +31,7 @@ void build_nco_big_table(uint32_t* tab);
 cudaError_t ddc_prepare_kernels();
 constexpr int kNcoBigTabWords = 2048 * 26;
 cudaError_t ddc_upload_constants();
-constexpr int kDdcKernels = 5;   // profile slots: front, cic+comp, (unused), hilb, rotate
+constexpr int kDdcKernels = 5;   // profile slots in launch order: adc_expand, front, cic+comp, hilb, rotate
 // ev: optional array of kDdcKernels + 1 events recorded before/after each kernel (profiling mode)
 // ring_start: ring index that receives the block's first frame
 cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, uint32_t ring_start,

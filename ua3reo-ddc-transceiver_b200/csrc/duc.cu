@@ -23,8 +23,7 @@ UA3_D int32_t nco_sin14(const uint32_t* __restrict__ tab, uint32_t P) {
     const uint32_t w = tab[P >> 21];
     const int32_t sc = (int32_t)w >> 16;
     const int32_t cc = (int32_t)(int16_t)(w & 0xFFFFu);
-    const int32_t j = (int32_t)((P >> 10) & 0x7FFu);
-    const int32_t sf = (j * kSinFMul + (1 << 18)) >> 19;
+    const int32_t sf = (int32_t)nco_fine_level(P);
     return (sc * kCosF + sf * cc + 4096) >> 13;
 }
 

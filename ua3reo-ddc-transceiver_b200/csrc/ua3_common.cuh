@@ -44,7 +44,10 @@ constexpr int kFrontThreads = kFrontWarps * 32;
 constexpr int kSub = 16;                           // 32-bit sub-block length (see ddc_front.cuh)
 // big-table front kernel: one persistent CTA per SM, 32 warps = 8 channel tiles x 4 chunks per tile
 constexpr int kBtCG = 8;                           // channel tiles (of 32 channels) per CTA tile
-constexpr int kBtTG = 4;                           // 512-sample chunks per CTA tile
+#ifndef UA3_BT_TG
+#define UA3_BT_TG 4
+#endif
+constexpr int kBtTG = UA3_BT_TG;                   // 512-sample chunks per CTA tile
 constexpr int kBtWarps = kBtCG * kBtTG;
 constexpr int kBtThreads = kBtWarps * 32;
 
