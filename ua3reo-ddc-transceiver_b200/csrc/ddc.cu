@@ -382,8 +382,9 @@ void build_cic_weights(uint64_t G[25]) {
 
 void build_nco_big_table(uint32_t* tab /* kBigTabWords */) {
     for (int k = 0; k < 2048; ++k)
-        for (int sf = 0; sf < kSfLevels; ++sf)
+        for (int sf = 0; sf < kSfLevels; ++sf) {
             tab[nco_bigtab_index((uint32_t)k, (uint32_t)sf)] = nco_bigtab_entry(UA3_NCO_SIN_C[k], UA3_NCO_COS_C[k], sf);
+        }
 }
 
 cudaError_t ddc_prepare_kernels() {
