@@ -218,56 +218,117 @@ ddc_front_bt_kernel(const int16_t* __restrict__ adc, const int32_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
-// cic combs + compensator FIR, fused: CTA = (channel, tile of 128 frames).  The tile's chunk records (256 chunks
-// plus the 68-chunk halo, both rails, 80 B each) are staged once in shared memory with 16-byte coalesced loads;
-// the 96 kHz CIC outputs live only in shared memory.
+// cic combs + compensator FIR, fused: CTA = (channel, tile of 128 frames).
+//   stage  : the tile's chunk records (256 chunks + 68 halo, both rails, 80 B each = 25.9 KB) arrive in shared memory
+//            with ONE TMA bulk copy, in the order the front kernel wrote them (no transposition, no staging code).
+//   combs  : run-based.  With S_m = A512 S_{m-1} + L_m and z_m = (S_m)[stage 5] the five combs are the 5th backward
+//            difference of z, which annihilates the (degree <= 4 polynomial) response to whatever state preceded a run.
+//            A thread therefore starts from S = 0 four records before its run of kCcRun outputs and steps the
+//            recurrence - 10 multiply-adds by the 32-bit binomials C(512, 1..4) plus five 64-bit subtractions per
+//            output instead of the 25 64x64-bit products of the direct form (ddc_back.cuh: cic_combine, which the
+//            tests keep as the cross-check).  The 96 kHz CIC outputs live only in shared memory.
+//   FIR    : one thread per (rail, pair of frames): the two 65-tap windows overlap in 63 samples, which are read once
+//            as 16-byte vectors of widened samples; 32-bit wrap-around accumulators (only the low 31 bits are kept by
+//            rx_ciccomp.vhd:616).
 // ------------------------------------------------------------------------------------------------
 constexpr int kCcFrames = 128;                         // frames per CTA tile
 constexpr int kCcChunks = 2 * kCcFrames;               // chunks per tile
 constexpr int kCcRecs = kCcChunks + kLHalo;            // records staged
+constexpr int kCcOut = kCcChunks + kUHalo;             // CIC outputs per rail and tile
+constexpr int kCcRun = 11;                             // outputs per run; odd, so that the strided 64-bit record reads of a half warp fall into distinct banks
+constexpr int kCcWarm = kLHalo - kUHalo;               // 4 records of run-in
+constexpr int kCcThreads = 128;
+constexpr int kCcUPitch = kCcOut + 8;                  // int32 samples per rail, zero padded for the vector reads
+static_assert(2 * ((kCcOut + kCcRun - 1) / kCcRun) <= kCcThreads, "one thread per (rail, run)");
+static_assert(2 * (kCcFrames / 2) <= kCcThreads, "one thread per (rail, frame pair)");
+static_assert((kCcRecs * kLRec * 8) % 16 == 0, "TMA bulk size");
 
-constexpr int kCcPitch = kCcRecs + 1;                  // odd pitch: the transposing stores spread over the banks
-
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCcThreads)
 ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_t n_frames, int16_t* __restrict__ YI,
                    uint32_t yi_stride, int16_t* __restrict__ YQ, uint32_t yq_stride) {
-    // field-major (structure of arrays): s_l[field][record], field = rail * 5 + stage.  Threads that work on
-    // neighbouring chunks then read neighbouring 8-byte words: conflict-free 64-bit shared loads.
-    __shared__ __align__(16) uint64_t s_l[kLRec * kCcPitch];         // 10 x 325 x 8 B = 26 KB
-    __shared__ int16_t s_u[2][kCcChunks + kUHalo + 2];
+    __shared__ __align__(128) uint64_t s_rec[kCcRecs * kLRec];       // 324 x 10 x 8 B, record-major as in global memory
+    __shared__ __align__(16) int32_t s_u[2][kCcUPitch];
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t tid = threadIdx.x;
     const uint32_t ch = blockIdx.x;
     const uint32_t k0 = blockIdx.y * kCcFrames;                      // first frame of the tile
     const uint32_t nk = min((uint32_t)kCcFrames, n_frames - k0);
     const uint32_t n_rec = 2 * nk + kLHalo;
     // record index (array, halo included) of the tile's first staged record: chunk 2*k0 - 68 -> array index 2*k0
     const uint64_t* src = L + (size_t)ch * l_ch_stride + (size_t)(2 * k0) * kLRec;
-    {
-        const ulonglong2* s2 = reinterpret_cast<const ulonglong2*>(src);
-        for (uint32_t i = threadIdx.x; i < n_rec * (kLRec / 2); i += 256) {
-            const ulonglong2 v = s2[i];                               // coalesced 16-byte loads of the record stream
-            const uint32_t rec = i / (kLRec / 2), f = 2 * (i % (kLRec / 2));
-            s_l[f * kCcPitch + rec] = v.x;
-            s_l[(f + 1) * kCcPitch + rec] = v.y;
+#if !defined(UA3_HOST_EMU)
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&s_bar, n_rec * kLRec * 8u);
+        tma_bulk_g2s(s_rec, src, n_rec * kLRec * 8u, &s_bar);
+    }
+#else
+    for (uint32_t i = tid; i < n_rec * kLRec; i += kCcThreads) s_rec[i] = src[i];
+#endif
+    for (uint32_t i = tid; i < 2 * kCcUPitch; i += kCcThreads) (&s_u[0][0])[i] = 0;
+    __syncthreads();                                                 // barrier initialised / emulation copy done
+#if !defined(UA3_HOST_EMU)
+    mbar_wait(&s_bar, 0);
+#endif
+    // ---- combs: CIC outputs u'[c] for chunks c = 2*k0 - 64 .. 2*k0 + 2*nk - 1  ->  s_u[rail][0 .. 64 + 2*nk) ----
+    const uint32_t n_out = 2 * nk + kUHalo;
+    const uint32_t n_runs = (n_out + kCcRun - 1) / kCcRun;
+    if (tid < 2 * n_runs) {
+        const uint32_t rail = tid / n_runs, m0 = (tid % n_runs) * kCcRun;      // staged record of output m is m + kCcWarm
+        const uint64_t* rec = s_rec + (size_t)m0 * kLRec + rail * 5;
+        uint64_t S0 = 0, S1 = 0, S2 = 0, S3 = 0, S4 = 0;
+        uint64_t d0 = 0, d1 = 0, d2 = 0, d3 = 0, d4 = 0;                       // comb delay registers (rx_cic.vhd:293-404)
+        const uint32_t steps = min((uint32_t)(kCcRun + kCcWarm), n_rec - m0);
+#pragma unroll 3
+        for (uint32_t j = 0; j < steps; ++j, rec += kLRec) {
+            // S <- A512 S + L, A512[r][c] = C(512, r - c): 512, 130816, 22238720, 2829877120
+            S4 += 512u * S3 + 130816u * S2 + 22238720u * S1 + 2829877120u * S0 + rec[4];
+            S3 += 512u * S2 + 130816u * S1 + 22238720u * S0 + rec[3];
+            S2 += 512u * S1 + 130816u * S0 + rec[2];
+            S1 += 512u * S0 + rec[1];
+            S0 += rec[0];
+            uint64_t y = S4, t;
+            t = y - d0; d0 = y; y = t;
+            t = y - d1; d1 = y; y = t;
+            t = y - d2; d2 = y; y = t;
+            t = y - d3; d3 = y; y = t;
+            t = y - d4; d4 = y; y = t;
+            if (j >= (uint32_t)kCcWarm)                              // output_typeconvert <= section_out10(59 DOWNTO 44)
+                s_u[rail][m0 + j - kCcWarm] = (int32_t)(int16_t)(uint16_t)(y >> 44);
         }
     }
     __syncthreads();
-    // CIC outputs u'[c] for chunks c = 2*k0 - 64 .. 2*k0 + 2*nk - 1  ->  s_u[rail][0 .. 64 + 2*nk)
-    for (uint32_t i = threadIdx.x; i < 2 * (2 * nk + kUHalo); i += 256) {
-        const uint32_t rail = i / (2 * nk + kUHalo), m = i % (2 * nk + kUHalo);   // consecutive threads: consecutive chunks
-        const uint64_t* base = s_l + (size_t)(rail * 5) * kCcPitch + (m + 4);
-        uint64_t acc = 0;
+    // ---- compensator: frames k0 + 2g, k0 + 2g + 1 of one rail per thread (rx_ciccomp.vhd:339-616) ----
+    const uint32_t n_pairs = (nk + 1) / 2;
+    if (tid < 2 * n_pairs) {
+        const uint32_t rail = tid / n_pairs, g = tid % n_pairs;
+        const I4* w4 = reinterpret_cast<const I4*>(&s_u[rail][4 * g]);       // window of frame k: s_u[2k .. 2k + 64]
+        int32_t a0 = 0, a1 = 0;
 #pragma unroll
-        for (int p = 0; p < 5; ++p)
+        for (int v = 0; v < 17; ++v) {
+            const I4 q = w4[v];
+            const int32_t x[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int k = 0; k < 5; ++k) acc += c_cic_g[p * 5 + k] * base[(size_t)k * kCcPitch - p];
-        s_u[rail][m] = (int16_t)(uint16_t)(acc >> 44);                // output_typeconvert <= section_out10(59 DOWNTO 44)
-    }
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 2 * nk; i += 256) {
-        const uint32_t rail = i / nk, k = i % nk;
-        const int16_t y = comp_fir(s_u[rail], c_comp_h, (int)k);
-        if (rail == 0) YI[(size_t)ch * yi_stride + kYIHalo + k0 + k] = y;
-        else           YQ[(size_t)ch * yq_stride + kYQHalo + k0 + k] = y;
+            for (int e = 0; e < 4; ++e) {
+                const int i = 4 * v + e;                             // window position; tap j multiplies position 64 - j
+                if (i <= 64) a0 += (int32_t)c_comp_h[64 - i] * x[e];
+                if (i >= 2 && i <= 66) a1 += (int32_t)c_comp_h[66 - i] * x[e];
+            }
+        }
+        const int32_t accs[2] = {a0, a1};
+#pragma unroll
+        for (int f = 0; f < 2; ++f) {
+            const uint32_t k = 2 * g + f;
+            if (k < nk) {
+                // rx_ciccomp.vhd:616: low 31 bits + 0x3FFF + bit15, wrap at 31 bits, >> 15, keep 16 bits
+                const uint32_t a31 = (uint32_t)accs[f] & 0x7FFFFFFFu;
+                const uint32_t r31 = (a31 + 0x3FFFu + (((uint32_t)accs[f] >> 15) & 1u)) & 0x7FFFFFFFu;
+                const int16_t y = (int16_t)((int32_t)(r31 << 1) >> 16);
+                if (rail == 0) YI[(size_t)ch * yi_stride + kYIHalo + k0 + k] = y;
+                else           YQ[(size_t)ch * yq_stride + kYQHalo + k0 + k] = y;
+            }
+        }
     }
 }
 
@@ -447,7 +508,7 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
                    b.L, b.l_ch_stride);
     }
     if (ev) cudaEventRecord(ev[2], st);
-    UA3_LAUNCH(ddc_ciccomp_kernel, dim3(b.n_ch, (n_frames + kCcFrames - 1) / kCcFrames), 256, 0, st, b.L, b.l_ch_stride, n_frames,
+    UA3_LAUNCH(ddc_ciccomp_kernel, dim3(b.n_ch, (n_frames + kCcFrames - 1) / kCcFrames), kCcThreads, 0, st, b.L, b.l_ch_stride, n_frames,
                b.YI, b.yi_stride, b.YQ, b.yq_stride);
     if (ev) cudaEventRecord(ev[3], st);
     UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + 255) / 256), 256, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
