@@ -338,41 +338,64 @@ ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_
 // rx_hilb.vhd:903 rounds every product: pr = (p + p[1]) >> 1 (convergent).  Because 2*pr = p + adj with
 // adj = +1 if p mod 4 == 3, -1 if p mod 4 == 1, 0 otherwise, the 256-tap sum is exactly
 //     sum pr = ( sum p + 2 * #{p mod 4 == 3} - #{p odd} ) / 2,
-// and p mod 4 depends only on the two low bits of coefficient and sample.  The kernel therefore does one plain
-// IMAD per tap (two 32-bit half sums, each provably < 2^31) and gets the rounding term from 256-bit popcounts over
-// bit planes of the samples (built with warp ballots) against bit planes of the coefficients.
-__global__ void __launch_bounds__(256)
+// and p mod 4 depends only on the two low bits of coefficient and sample: the rounding term comes from 256-bit
+// popcounts over bit planes of the samples (built with warp ballots) against bit planes of the coefficients.
+// The plain sum uses the antisymmetry of the coefficient set, c[t] = -c[255 - t] (checked in tests/test_tables.py):
+//     sum p = sum_{t<128} c[t] * (y[k - t] - y[k - 255 + t]),
+// one subtraction (either integer pipe) and one IMAD per PAIR of taps, in 32-bit wrap-around arithmetic - only the
+// low 31 bits of the doubled sum survive rx_hilb.vhd:935.  A thread produces 4 consecutive frames from a register
+// window of widened samples read as 16-byte vectors (2 vector loads per 32 multiply-adds).
+constexpr int kHbFrames = 256;                        // frames per CTA tile
+constexpr int kHbPer = 4;                             // frames per thread
+constexpr int kHbThreads = kHbFrames / kHbPer;        // 64
+constexpr int kHbWin = 528;                           // widened window: 511 samples + zero padding for the vector reads
+
+__global__ void __launch_bounds__(kHbThreads)
 ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_t* __restrict__ YQ, uint32_t yq_stride,
                 uint32_t n_frames, uint64_t* __restrict__ frames, uint32_t frame_ch_stride, uint32_t ring_start,
                 uint32_t ring_mask) {
-    __shared__ int16_t s_y[512];                  // window: s_y[i] = yI[k0 - 255 + i], zero padded
-    __shared__ uint32_t s_b0[17], s_b1[17];       // bit planes of the window, 32 samples per word
+    __shared__ __align__(16) int32_t s_y[kHbWin];  // window: s_y[i] = yI[k0 - 255 + i], zero padded
+    __shared__ uint32_t s_b0[18], s_b1[18];        // bit planes of the window, 32 samples per word
     const uint32_t ch = blockIdx.x;
-    const uint32_t k0 = blockIdx.y * 256;
-    const uint32_t nk = min(256u, n_frames - k0);
+    const uint32_t k0 = blockIdx.y * kHbFrames;
+    const uint32_t nk = min((uint32_t)kHbFrames, n_frames - k0);
     const uint32_t tid = threadIdx.x;
     const int16_t* src = YI + (size_t)ch * yi_stride + k0;
-    for (uint32_t i = tid; i < 512; i += 256) s_y[i] = (i < nk + kYIHalo) ? src[i] : (int16_t)0;
-    if (tid == 0) { s_b0[16] = 0; s_b1[16] = 0; }
-    __syncthreads();
-    for (uint32_t i = tid; i < 512; i += 256) {    // every warp: 32 consecutive samples -> one word per plane
-        const int32_t v = s_y[i];
+    for (uint32_t i = tid; i < 512; i += kHbThreads) {     // every warp: 32 consecutive samples -> one word per plane
+        const int32_t v = (i < nk + kYIHalo) ? (int32_t)src[i] : 0;
+        s_y[i] = v;
         const uint32_t w0 = __ballot_sync(0xffffffffu, v & 1), w1 = __ballot_sync(0xffffffffu, v & 2);
         if ((tid & 31) == 0) { s_b0[i >> 5] = w0; s_b1[i >> 5] = w1; }
     }
+    if (tid < kHbWin - 512) s_y[512 + tid] = 0;
+    if (tid < 2) { s_b0[16 + tid] = 0; s_b1[16 + tid] = 0; }
     __syncthreads();
-    if (tid < nk) {
-        const uint32_t k = k0 + tid;
-        // ---- sum of the raw products, taps 0..127 and 128..255 in separate 32-bit accumulators ----
-        const int16_t* w = s_y + tid;             // w[255 - t] = yI[k - t]
-        int32_t s1 = 0, s2 = 0;
-#pragma unroll 16
-        for (int t = 0; t < 128; ++t) {
-            s1 += c_hilb_c32[t] * (int32_t)w[255 - t];
-            s2 += c_hilb_c32[128 + t] * (int32_t)w[127 - t];
-        }
-        // ---- rounding term: u = 255 - t runs over the window from bit `tid` on ----
-        const uint32_t wsel = tid >> 5, sh = tid & 31;
+    const uint32_t kt = kHbPer * tid;              // first frame of this thread, tile-relative
+    if (kt >= nk) return;
+    // ---- plain sums: acc[o] = sum_{t<128} c[t] * (s_y[kt+o+255-t] - s_y[kt+o+t]) ----
+    const I4* lv = reinterpret_cast<const I4*>(s_y + kt);            // left stream : s_y[kt + 4v ..]
+    const I4* rv = reinterpret_cast<const I4*>(s_y + kt + 128);      // right stream: s_y[kt + 128 + 4u ..]
+    uint32_t acc[kHbPer] = {0, 0, 0, 0};
+    I4 l0 = lv[0], r1 = rv[32];
+#pragma unroll
+    for (int v = 0; v < 32; ++v) {
+        const I4 l1 = lv[v + 1], r0 = rv[31 - v];
+        const int32_t lw[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};     // s_y[kt + 4v + 0..7]
+        const int32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};     // s_y[kt + 128 + 4(31-v) + 0..7]
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int o = 0; o < kHbPer; ++o)
+                acc[o] += (uint32_t)c_hilb_c32[4 * v + e] * (uint32_t)(rw[3 + o - e] - lw[o + e]);
+        l0 = l1; r1 = r0;
+    }
+    const int16_t* qsrc = YQ + (size_t)ch * yq_stride + k0 + kt;     // qsrc[kYQHalo + o] = yQ[k], qsrc[o] = yQ[k - 130]
+    uint64_t* dst = frames + (size_t)ch * frame_ch_stride;
+#pragma unroll
+    for (int o = 0; o < kHbPer; ++o) {
+        if (kt + o >= nk) break;
+        // ---- rounding term: u = 255 - t runs over the window from bit kt + o on ----
+        const uint32_t wsel = (kt + o) >> 5, sh = (kt + o) & 31;
         uint32_t n_odd = 0, n_three = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -383,15 +406,14 @@ ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_
             n_odd += __popc(q0);
             n_three += __popc(q0 & q1);
         }
-        const int64_t twice = (int64_t)s1 + (int64_t)s2 + 2 * (int64_t)n_three - (int64_t)n_odd;
-        const int32_t acc = (int32_t)(twice >> 1);                       // exact: the sum is even
+        const uint32_t twice = acc[o] + 2u * n_three - n_odd;        // mod 2^32; even, so >> 1 is exact on bits 1..31
+        const uint32_t a = twice >> 1;                               // low 31 bits of the HDL accumulator
         // rx_hilb.vhd:935: low 30 bits + 0x1FFF + bit14, wrap at 30 bits, >> 14, keep 16 bits
-        const uint32_t a30 = (uint32_t)acc & 0x3FFFFFFFu;
-        const uint32_t r30 = (a30 + 0x1FFFu + (((uint32_t)acc >> 14) & 1u)) & 0x3FFFFFFFu;
+        const uint32_t a30 = a & 0x3FFFFFFFu;
+        const uint32_t r30 = (a30 + 0x1FFFu + ((a >> 14) & 1u)) & 0x3FFFFFFFu;
         const int16_t vi = (int16_t)((int32_t)(r30 << 2) >> 16);
-        const int16_t yi = s_y[kYIHalo + tid];
-        const int16_t* q = YQ + (size_t)ch * yq_stride + k;   // q[kYQHalo] = yQ[k], q[0] = yQ[k-130]
-        frames[(size_t)ch * frame_ch_stride + ((ring_start + k) & ring_mask)] = frame_pack(q[kYQHalo], yi, q[0], vi);
+        const int16_t yi = (int16_t)s_y[kYIHalo + kt + o];
+        dst[(ring_start + k0 + kt + o) & ring_mask] = frame_pack(qsrc[kYQHalo + o], yi, qsrc[o], vi);
     }
 }
 
@@ -511,7 +533,7 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
     UA3_LAUNCH(ddc_ciccomp_kernel, dim3(b.n_ch, (n_frames + kCcFrames - 1) / kCcFrames), kCcThreads, 0, st, b.L, b.l_ch_stride, n_frames,
                b.YI, b.yi_stride, b.YQ, b.yq_stride);
     if (ev) cudaEventRecord(ev[3], st);
-    UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + 255) / 256), 256, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
+    UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + kHbFrames - 1) / kHbFrames), kHbThreads, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
                n_frames, b.frames, b.frame_ch_stride, ring_start, b.ring_mask);
     if (ev) cudaEventRecord(ev[4], st);
     UA3_LAUNCH(ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.YI, b.yi_stride,
