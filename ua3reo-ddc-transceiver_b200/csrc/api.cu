@@ -172,6 +172,7 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     UA3_TRY(dev_alloc(c, &b.nco_tab, 2048));
     UA3_TRY(dev_alloc(c, &b.big_tab, (size_t)kNcoBigTabWords));
     UA3_TRY(dev_alloc(c, &b.adc9, (size_t)max_block_samples + 8));
+    UA3_TRY(dev_alloc(c, &b.tile_counter, (size_t)4));
     UA3_TRY(ddc_prepare_kernels());
     {
         std::vector<uint32_t> bt((size_t)kNcoBigTabWords);

@@ -84,7 +84,7 @@ ddc_front_kernel(const int16_t* __restrict__ adc, uint32_t n_chunks, const uint3
 // ------------------------------------------------------------------------------------------------
 // big table + two pre-shifted int32 ADC tiles (double buffer) + 3 mbarriers + 2 release counters
 constexpr size_t kBtAdcTileBytes = (size_t)kBtTG * kCicR * 4;
-constexpr size_t kBtSmemBytes = (size_t)kBigTabWords * 4 + 2 * kBtAdcTileBytes + 64;
+constexpr size_t kBtSmemBytes = (size_t)kBigTabWords * 4 + 2 * kBtAdcTileBytes + 64;   // 3 barriers (24 B) + 2 counters + 2 tile slots
 
 #if !defined(UA3_HOST_EMU)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,8 +108,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 // int16 ADC block -> int32, pre-shifted left by 9 (see nco_mix): done once per block so that the persistent front
 // kernel can pull ready-to-use tiles with TMA and never touches the raw samples.
 __global__ void __launch_bounds__(256)
-adc_expand_kernel(const int16_t* __restrict__ adc, uint32_t n8, int32_t* __restrict__ adc9) {
+adc_expand_kernel(const int16_t* __restrict__ adc, uint32_t n8, int32_t* __restrict__ adc9, uint32_t* __restrict__ tile_counter) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0) *tile_counter = 0;                 // the front kernel that follows hands out tiles from this counter
     if (v >= n8) return;
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(adc) + v);
     const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
@@ -126,7 +127,8 @@ adc_expand_kernel(const int16_t* __restrict__ adc, uint32_t n8, int32_t* __restr
 __global__ void __launch_bounds__(kBtThreads, 1)
 ddc_front_bt_kernel(const int16_t* __restrict__ adc, const int32_t* __restrict__ adc9, uint32_t n_chunks,
                     const uint32_t* __restrict__ big_tab, const uint32_t* __restrict__ fcw,
-                    const uint32_t* __restrict__ phase, uint32_t n_ch_pad, uint64_t* __restrict__ L, uint32_t l_ch_stride) {
+                    const uint32_t* __restrict__ phase, uint32_t n_ch_pad, uint64_t* __restrict__ L, uint32_t l_ch_stride,
+                    uint32_t* __restrict__ tile_counter) {
 #if defined(UA3_HOST_EMU)
     static uint8_t s_dyn[kBtSmemBytes] __attribute__((aligned(128)));
 #else
@@ -145,8 +147,12 @@ ddc_front_bt_kernel(const int16_t* __restrict__ adc, const int32_t* __restrict__
 
 #if !defined(UA3_HOST_EMU)
     // bar[0]: table; bar[1], bar[2]: ADC tile buffers 0 / 1 ("full").  A buffer is released by counting the warps
-    // that are done with it; the LAST warp to finish refills it for the tile two steps ahead, so no warp ever
-    // waits for the others at a CTA-wide barrier - fast warps run up to two tiles ahead of slow ones.
+    // that are done with it; the LAST warp to finish takes the next tile from a global counter and refills the
+    // buffer for the step two ahead, so no warp ever waits for the others at a CTA-wide barrier - fast warps run up to
+    // two tiles ahead of slow ones - and a CTA that starts late or shares its SM (an NCCL kernel, another stream)
+    // simply takes fewer tiles.
+    uint32_t* s_tile = s_done + 2;                              // tile index held by each buffer
+    constexpr uint32_t kNoTile = 0xFFFFFFFFu;
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -155,41 +161,35 @@ ddc_front_bt_kernel(const int16_t* __restrict__ adc, const int32_t* __restrict__
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue_tile = [&](uint32_t tile, uint32_t buf) {       // one thread: fetch the tile's pre-shifted samples
-        const uint32_t chunk0 = (tile / n_cg) * kBtTG;
-        const uint32_t bytes = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR * 4u;
-        mbar_expect_tx(&s_bar[1 + buf], bytes);
-        tma_bulk_g2s(reinterpret_cast<uint8_t*>(s_adc) + buf * kBtAdcTileBytes, adc9 + (size_t)chunk0 * kCicR, bytes, &s_bar[1 + buf]);
+    auto fill = [&](uint32_t buf) {                            // one thread: claim a tile and fetch its pre-shifted samples
+        const uint32_t tile = atomicAdd(tile_counter, 1u);
+        if (tile < n_tiles) {
+            const uint32_t chunk0 = (tile / n_cg) * kBtTG;
+            const uint32_t bytes = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR * 4u;
+            s_tile[buf] = tile;
+            mbar_expect_tx(&s_bar[1 + buf], bytes);
+            tma_bulk_g2s(reinterpret_cast<uint8_t*>(s_adc) + buf * kBtAdcTileBytes, adc9 + (size_t)chunk0 * kCicR, bytes, &s_bar[1 + buf]);
+        } else {
+            s_tile[buf] = kNoTile;                              // out of work: complete the phase with a plain arrive
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_bar[1 + buf])) : "memory");
+        }
     };
     if (tid == 0) {
         mbar_expect_tx(&s_bar[0], (uint32_t)kBigTabWords * 4u);
         for (uint32_t off = 0; off < (uint32_t)kBigTabWords * 4u; off += 16384u)
             tma_bulk_g2s(s_dyn + off, reinterpret_cast<const uint8_t*>(big_tab) + off, 16384u, &s_bar[0]);
-        if (blockIdx.x < n_tiles) issue_tile(blockIdx.x, 0);
-        if (blockIdx.x + gridDim.x < n_tiles) issue_tile(blockIdx.x + gridDim.x, 1);
+        fill(0);
+        fill(1);
     }
     mbar_wait(&s_bar[0], 0);
-#else
-    for (int i = tid; i < kBigTabWords; i += kBtThreads) s_bt[i] = big_tab[i];
-    __syncthreads();
-#endif
 
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t buf = it & 1u;
+        mbar_wait(&s_bar[1 + buf], (it >> 1) & 1u);
+        const uint32_t tile = s_tile[buf];
+        if (tile == kNoTile) break;
         const uint32_t cg = tile % n_cg, tg = tile / n_cg;     // channel group fastest: neighbours share the ADC tile in L2
         const uint32_t chunk0 = tg * kBtTG;
-        const uint32_t buf = it & 1u;
-#if !defined(UA3_HOST_EMU)
-        mbar_wait(&s_bar[1 + buf], (it >> 1) & 1u);
-#else
-        {   // emulation: plain staging of the raw samples behind CTA-wide barriers
-            const uint32_t n_valid = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR;
-            __syncthreads();
-            int32_t* dst = reinterpret_cast<int32_t*>(s_adc) + buf * (kBtTG * kCicR);
-            for (uint32_t v = tid; v < n_valid; v += kBtThreads) dst[v] = (int32_t)adc[(size_t)chunk0 * kCicR + v] << 9;
-            __syncthreads();
-        }
-#endif
         const uint32_t ctile = cg * kBtCG + wc, chunk = chunk0 + wt;
         if (ctile < n_ctiles && chunk < n_chunks) {
             const uint32_t ch = (ctile << 5) + lane;
@@ -202,19 +202,41 @@ ddc_front_bt_kernel(const int16_t* __restrict__ adc, const int32_t* __restrict__
 #pragma unroll
             for (int k = 0; k < 5; ++k) d2[k] = make_ulonglong2(out[2 * k], out[2 * k + 1]);
         }
-#if !defined(UA3_HOST_EMU)
         __syncwarp();
         if (lane == 0) {
-            __threadfence_block();                                         // this warp's reads of the buffer are done
+            __threadfence_block();                                         // this warp's reads of the buffer (and of s_tile) are done
             if (atomicAdd(&s_done[buf], 1u) == (uint32_t)kBtWarps - 1u) {  // last warp out refills it
                 atomicExch(&s_done[buf], 0u);
                 __threadfence_block();
-                const uint32_t next = tile + 2u * gridDim.x;
-                if (next < n_tiles) issue_tile(next, buf);
+                fill(buf);
             }
         }
-#endif
     }
+#else
+    // emulation: static tile order, plain staging of the raw samples behind CTA-wide barriers
+    for (int i = tid; i < kBigTabWords; i += kBtThreads) s_bt[i] = big_tab[i];
+    __syncthreads();
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t cg = tile % n_cg, tg = tile / n_cg;
+        const uint32_t chunk0 = tg * kBtTG;
+        const uint32_t n_valid = min((uint32_t)kBtTG, n_chunks - chunk0) * kCicR;
+        __syncthreads();
+        int32_t* stage = reinterpret_cast<int32_t*>(s_adc);
+        for (uint32_t v = tid; v < n_valid; v += kBtThreads) stage[v] = (int32_t)adc[(size_t)chunk0 * kCicR + v] << 9;
+        __syncthreads();
+        const uint32_t ctile = cg * kBtCG + wc, chunk = chunk0 + wt;
+        if (ctile < n_ctiles && chunk < n_chunks) {
+            const uint32_t ch = (ctile << 5) + lane;
+            const uint32_t F = fcw[ch] << 10;
+            const uint32_t P0 = (phase[ch] << 10) + F * (chunk * (uint32_t)kCicR);
+            uint64_t out[10];
+            front_chunk_bt(s_bt, s_adc + wt * (kCicR / 4), P0, F, out);
+            uint64_t* dst = L + (size_t)ch * l_ch_stride + (size_t)(kLHalo + chunk) * kLRec;
+            for (int k = 0; k < 10; ++k) dst[k] = out[k];
+        }
+    }
+    (void)adc9; (void)tile_counter; (void)s_bar; (void)s_done;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -516,12 +538,12 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
         const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count);
 #if !defined(UA3_HOST_EMU)
         const uint32_t n8 = n_chunks * (uint32_t)kCicR / 8u;
-        UA3_LAUNCH(adc_expand_kernel, (n8 + 255u) / 256u, 256, 0, st, adc_dev, n8, b.adc9);
+        UA3_LAUNCH(adc_expand_kernel, (n8 + 255u) / 256u, 256, 0, st, adc_dev, n8, b.adc9, b.tile_counter);
         if (launches) *launches += 1;
 #endif
         if (ev) cudaEventRecord(ev[1], st);
         UA3_LAUNCH(ddc_front_bt_kernel, grid, kBtThreads, kBtSmemBytes, st, adc_dev, b.adc9, n_chunks, b.big_tab, b.fcw, b.phase,
-                   b.n_ch_pad, b.L, b.l_ch_stride);
+                   b.n_ch_pad, b.L, b.l_ch_stride, b.tile_counter);
     } else {
         const uint32_t n_tiles = ((n_chunks + kFrontWarps - 1) / kFrontWarps) * (b.n_ch_pad >> 5);
         const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count * 3);

@@ -10,6 +10,7 @@ struct DdcBuffers {
     uint32_t max_chunks = 0, max_frames = 0;
     uint32_t* nco_tab = nullptr;   // [2048] packed coarse ROM
     uint32_t* big_tab = nullptr;   // [2048 * 26] packed (sin12, cos12) by (coarse address, fine-sine value)
+    uint32_t* tile_counter = nullptr;   // work counter of the persistent front kernel (zeroed by adc_expand_kernel)
     int32_t* adc9 = nullptr;       // [max_block] the current ADC block widened to int32 and pre-shifted << 9 (adc_expand_kernel)
     int front_variant = 0;         // 0 auto, 1 force the 8 KB-table kernel, 2 force the big-table kernel
     uint32_t* fcw = nullptr;       // [n_ch_pad] 22-bit tuning words
