@@ -162,6 +162,11 @@ int ua3reo_rx_set_notch(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const uint1
  * [n_channels][n_blocks][384]; n_blocks must equal *audio_blocks of ua3reo_rx_counts(). */
 int ua3reo_rx_counts(ua3reo_ctx *ctx, size_t *audio_blocks, size_t *fft_frames);
 int ua3reo_rx_read_audio(ua3reo_ctx *ctx, int32_t *dst_host, size_t n_blocks);
+/* Pipelined variants: the copy is enqueued behind the STM32 stage of the last push (which runs on its own stream, one
+ * push behind the DDC) and the call returns immediately; dst should be pinned host memory and is valid after
+ * ua3reo_sync().  The next push's DDC kernels overlap both the stage and the copy. */
+int ua3reo_rx_read_audio_async(ua3reo_ctx *ctx, int32_t *dst_host, size_t n_blocks);
+int ua3reo_rx_read_spectra_async(ua3reo_ctx *ctx, float *dst_host, size_t n_frames);
 /* The same audio as processRxAudio() hands to the USB audio class (audio_processor.c:415-432): volume undone,
  * int16, L/R interleaved.  dst is [n_channels][n_blocks][384] int16. */
 int ua3reo_rx_read_audio_usb(ua3reo_ctx *ctx, int16_t *dst_host, size_t n_blocks);

@@ -148,6 +148,49 @@ def test_live_against_host_built_firmware(pkg, oracle):
     rx0.close()
 
 
+def test_pipelined_stage_and_async_reads(pkg, oracle):
+    """The STM32 stage runs on its own stream one push behind the DDC; results read with the *_async calls while the next
+    push is already running must equal the synchronous reads of an identical receiver."""
+    import torch
+    cases = [dict(mode=1, dnr=1), dict(mode=0, notch=1, notch_fc=1300), dict(mode=10, filter_width=6000), dict(mode=8, filter_width=15000),
+             dict(mode=4, filter_width=500, cw_decoder=1), dict(mode=1, fft_zoom=4)] * 20          # 120 channels: two rx_audio CTAs
+    n_blk, block = 6, 1024 * 192 * 2
+    adc = oracle.synth_adc(n_blk * block, seed=21)
+    fcw = [605867 + 997 * i for i in range(len(cases))]
+
+    def make():
+        rx = pkg.Receiver(len(cases), block)
+        rx.set_fcw(fcw)
+        rx.rx_enable(True)
+        rx.rx_set([rx.rx_defaults(**c) for c in cases])
+        return rx
+
+    ref = make()
+    want_a, want_s = [], []
+    for b in range(n_blk):
+        ref.push(adc[b * block:(b + 1) * block])
+        want_a.append(ref.read_audio()); want_s.append(ref.read_spectra())
+    ref.close()
+
+    rx = make()
+    dev = torch.from_numpy(adc.reshape(n_blk, block)).cuda()
+    got_a = [torch.empty((len(cases), 2, 384), dtype=torch.int32).pin_memory() for _ in range(n_blk)]
+    got_s = [torch.empty((len(cases), 1, 256), dtype=torch.float32).pin_memory() for _ in range(n_blk)]
+    counts = []
+    for b in range(n_blk):                       # no host synchronisation inside the loop
+        rx.push(dev[b])
+        na = rx.read_audio_async(got_a[b]); ns = rx.read_spectra_async(got_s[b])
+        counts.append((na, ns))
+    rx.sync()
+    rx.close()
+    for b in range(n_blk):
+        na, ns = counts[b]
+        assert (na, ns) == (want_a[b].shape[1], want_s[b].shape[1]) and na == 2
+        assert np.array_equal(got_a[b].numpy()[:, :na], want_a[b]), "block %d audio" % b
+        if ns:
+            assert np.array_equal(got_s[b].numpy()[:, :ns], want_s[b]), "block %d spectra" % b
+
+
 def test_rejects_settings_without_firmware_table(pkg):
     rx = pkg.Receiver(2, 1024)
     rx.rx_enable(True)

@@ -97,6 +97,8 @@ def _bind(lib):
         "ua3reo_rx_read_audio_usb": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_smeter": (c.c_int, [vp, vp, c.c_int]),
         "ua3reo_rx_read_waterfall": (c.c_int, [vp, vp, sz]),
+        "ua3reo_rx_read_audio_async": (c.c_int, [vp, vp, sz]),
+        "ua3reo_rx_read_spectra_async": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_waterfall_history": (c.c_int, [vp, vp]),
         "ua3reo_rx_move_waterfall": (c.c_int, [vp, u32, u32, vp]),
         "ua3reo_rx_read_cw": (c.c_int, [vp, vp, sz]),
@@ -329,6 +331,20 @@ class Receiver:
         out = np.empty((self.n_channels, nf, FFT_BINS), np.uint16)
         self._chk(self.lib.ua3reo_rx_read_waterfall(self._h, out.ctypes.data, nf))
         return out
+
+    def read_audio_async(self, out):
+        """Enqueue the copy of the last push's audio into `out` (pinned torch/numpy int32 [n_ch, blocks, 384]); valid after sync()."""
+        nb, _ = self.rx_counts()
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        self._chk(self.lib.ua3reo_rx_read_audio_async(self._h, ptr, nb))
+        return nb
+
+    def read_spectra_async(self, out):
+        """Enqueue the copy of the last push's spectra into `out` (pinned float32 [n_ch, frames, 256]); valid after sync()."""
+        _, nf = self.rx_counts()
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        self._chk(self.lib.ua3reo_rx_read_spectra_async(self._h, ptr, nf))
+        return nf
 
     def read_waterfall_history(self):
         """uint16 [n_channels, 50, 256]: the firmware's wtf_buffer per channel, row 0 the newest."""

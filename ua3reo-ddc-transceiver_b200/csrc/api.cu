@@ -62,7 +62,22 @@ struct ua3reo_ctx {
     // frame ring bookkeeping (monotonic frame counters; ring index = counter & ring_mask)
     uint64_t w_pos = 0;                 // frames written so far
     uint64_t a_pos = 0, f_pos = 0;      // frames consumed by the audio / FFT stage
-    // STM32 stage
+    // STM32 stage.  Its kernels run on their own high-priority stream, one push behind the DDC: rx_audio is latency
+    // bound and packed into a few whole SMs (rx.cu), so it overlaps the next push's persistent front kernel, which
+    // takes its tiles from a counter and simply runs on the SMs that are left.
+    cudaStream_t rx_stream = nullptr;
+    cudaEvent_t ev_frames = nullptr;               // the frames (and every earlier operation of `stream`) of the push are done
+    cudaEvent_t ev_rx_done[2] = {nullptr, nullptr};   // STM32 stage of push k (k & 1) has finished
+    bool rx_done_valid[2] = {false, false};
+    // results are double buffered (set k & 1 belongs to push k) so that the pipelined reads of push k, which run on
+    // copy_stream, overlap the STM32 kernels of push k+1
+    int32_t* rx_audio2[2] = {nullptr, nullptr};
+    float* rx_cw2[2] = {nullptr, nullptr};
+    float* rx_spec2[2] = {nullptr, nullptr};
+    uint16_t* rx_wf2[2] = {nullptr, nullptr};
+    cudaEvent_t ev_rxcopy[2] = {nullptr, nullptr};    // pipelined reads of result set i have finished
+    bool rxcopy_pending[2] = {false, false};
+    int rx_last_slot = 0;
     bool rx_on = false, rx_alloc = false;
     RxBuffers rx;
     std::vector<ua3reo_rx_settings> h_set;
@@ -113,6 +128,10 @@ static int ctx_free(ua3reo_ctx* c) {
     if (!c) return UA3_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->rx_stream) { cudaStreamSynchronize(c->rx_stream); cudaStreamDestroy(c->rx_stream); }
+    if (c->ev_frames) cudaEventDestroy(c->ev_frames);
+    for (int i = 0; i < 2; ++i) if (c->ev_rx_done[i]) cudaEventDestroy(c->ev_rx_done[i]);
+    for (int i = 0; i < 2; ++i) if (c->ev_rxcopy[i]) cudaEventDestroy(c->ev_rxcopy[i]);
     for (void* p : c->allocs) cudaFree(p);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
@@ -153,6 +172,14 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        int prio_lo = 0, prio_hi = 0;
+        e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->rx_stream, cudaStreamNonBlocking, prio_hi);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_frames, cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_rx_done[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_rxcopy[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_stage_free[i], cudaEventDisableTiming);
     if (e != cudaSuccess) { ctx_free(c); return fail(UA3_E_CUDA, "stream/event creation", e); }
@@ -206,9 +233,12 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
 
 int ua3reo_destroy(ua3reo_ctx* ctx) { return ctx_free(ctx); }
 
+static int rx_quiesce(ua3reo_ctx* c);
+
 int ua3reo_reset(ua3reo_ctx* c) {
     if (!c) return fail(UA3_E_INVAL, "null context");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     const DdcBuffers& b = c->b;
     UA3_CUDA(cudaMemsetAsync(b.phase, 0, sizeof(uint32_t) * c->n_ch_pad, c->stream));
     UA3_CUDA(cudaMemsetAsync(b.L, 0, sizeof(uint64_t) * (size_t)c->n_ch_pad * b.l_ch_stride, c->stream));
@@ -260,6 +290,51 @@ int ua3reo_set_frequency(ua3reo_ctx* c, uint32_t channel, uint32_t freq_hz) {
     return ua3reo_set_fcw(c, channel, 1, &w);
 }
 
+// Control-plane calls and synchronous result reads touch the STM32 stage's buffers through `stream`: they first wait
+// for whatever that stage still has in flight on its own stream.  (What they enqueue on `stream` is ordered before
+// the next push's STM32 kernels by ev_frames.)
+static int rx_quiesce(ua3reo_ctx* c) {
+    if (c->rx_stream) UA3_CUDA(cudaStreamSynchronize(c->rx_stream));
+    return UA3_OK;
+}
+
+// Before a push writes ring slots: the STM32 stage of the push before the previous one may still be reading them.
+static int rx_ring_guard(ua3reo_ctx* c) {
+    const int slot = (int)(c->n_push & 1);
+    if (c->rx_done_valid[slot]) {
+        UA3_CUDA(cudaStreamWaitEvent(c->stream, c->ev_rx_done[slot], 0));
+        c->rx_done_valid[slot] = false;
+    }
+    return UA3_OK;
+}
+
+// processRxAudio()/FFT_doFFT() over the whole audio blocks / FFT frames that the ring holds, on the STM32 stream.
+static int rx_run_stage(ua3reo_ctx* c, cudaEvent_t* ev, int* launches) {
+    const uint32_t nb = (uint32_t)((c->w_pos - c->a_pos) / UA3_AUDIO_BLOCK);
+    const uint32_t nf = (uint32_t)((c->w_pos - c->f_pos) / UA3_FFT_SIZE);
+    const int set = (int)(c->n_push & 1);
+    c->rx.audio_out = c->rx_audio2[set]; c->rx.spectra = c->rx_spec2[set]; c->rx.waterfall = c->rx_wf2[set]; c->rx.cw_mag = c->rx_cw2[set];
+    c->rx_last_slot = set;
+    UA3_CUDA(cudaEventRecord(c->ev_frames, c->stream));
+    UA3_CUDA(cudaStreamWaitEvent(c->rx_stream, c->ev_frames, 0));
+    if (c->rxcopy_pending[set]) {                                // a pipelined read of push k-2 still owns this result set
+        UA3_CUDA(cudaStreamWaitEvent(c->rx_stream, c->ev_rxcopy[set], 0));
+        c->rxcopy_pending[set] = false;
+    }
+    UA3_CUDA(rx_launch_audio(c->rx, (uint32_t)(c->a_pos & c->b.ring_mask), nb, c->rx_stream, launches));
+    if (ev) cudaEventRecord(ev[kDdcKernels + 1], c->rx_stream);
+    UA3_CUDA(rx_launch_fft(c->rx, (uint32_t)(c->f_pos & c->b.ring_mask), nf, c->rx_stream, launches));
+    if (ev) cudaEventRecord(ev[kDdcKernels + 2], c->rx_stream);
+    const int slot = (int)(c->n_push & 1);
+    UA3_CUDA(cudaEventRecord(c->ev_rx_done[slot], c->rx_stream));
+    c->rx_done_valid[slot] = true;
+    c->a_pos += (uint64_t)nb * UA3_AUDIO_BLOCK;
+    c->f_pos += (uint64_t)nf * UA3_FFT_SIZE;
+    c->last_audio_blocks = nb;
+    c->last_fft_frames = nf;
+    return UA3_OK;
+}
+
 static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* frames_out, cudaMemcpyKind kind) {
     if (!c || (!src && n)) return fail(UA3_E_INVAL, "ua3reo_ddc_push: null argument");
     if ((size_t)c->carry + n > (size_t)c->max_block + UA3_ADC_PER_FRAME - 1 ||
@@ -291,27 +366,33 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
         UA3_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[c->n_push & 1], 0));
         c->copy_pending[c->n_push & 1] = false;
     }
+    { const int rc = rx_ring_guard(c); if (rc != UA3_OK) return rc; }
     int launches = 0;
     cudaEvent_t* ev = nullptr;
     if (n_proc && c->prof_used < c->prof_cap) ev = c->prof_ev.data() + (size_t)(c->prof_used++) * kProfEvents;
     if (n_proc && c->adc_stats_on)
         UA3_CUDA(adc_stats_launch(proc_src, n_proc, c->adc_stats, c->sm_count, c->stream, &launches));
-    if (n_proc)
-        UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, (uint32_t)(c->w_pos & c->b.ring_mask), c->sm_count, c->stream,
+    if (n_proc) {
+        // With the STM32 stage on, the persistent front kernel leaves as many SMs free as the previous push's
+        // rx_audio_kernel has CTAs (each fills one SM; at most 11), so that the two always run side by side: rx_audio is
+        // latency bound (0.8 ms per block of 2^20 ADC samples however few channels there are), and hiding it is worth
+        // the 7 % of front-kernel SMs up to about 8000 channels (measured: 1.75 -> 1.15 ms per block at 1024 channels,
+        // 4.52 -> 4.27 ms at 4096, but 15.7 -> 16.8 ms at 16384, where it already fills the machine on its own).
+        int front_sms = c->sm_count;
+        if (c->rx_on) {
+            const int rx_ctas = (int)((c->n_ch + 95u) / 96u);
+            const char* env = std::getenv("UA3REO_RX_RESERVE_SMS");
+            const int reserve = env ? std::atoi(env) : (c->n_ch > 8192u ? 0 : (rx_ctas < 11 ? rx_ctas : 11));
+            if (reserve > 0 && reserve < c->sm_count) front_sms = c->sm_count - reserve;
+        }
+        UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, (uint32_t)(c->w_pos & c->b.ring_mask), front_sms, c->stream,
                                   &launches, ev));
+    }
     c->w_pos += n_proc / UA3_ADC_PER_FRAME;
     c->last_audio_blocks = c->last_fft_frames = 0;
     if (c->rx_on) {
-        const uint32_t nb = (uint32_t)((c->w_pos - c->a_pos) / UA3_AUDIO_BLOCK);
-        const uint32_t nf = (uint32_t)((c->w_pos - c->f_pos) / UA3_FFT_SIZE);
-        UA3_CUDA(rx_launch_audio(c->rx, (uint32_t)(c->a_pos & c->b.ring_mask), nb, c->stream, &launches));
-        if (ev) cudaEventRecord(ev[kDdcKernels + 1], c->stream);
-        UA3_CUDA(rx_launch_fft(c->rx, (uint32_t)(c->f_pos & c->b.ring_mask), nf, c->stream, &launches));
-        if (ev) cudaEventRecord(ev[kDdcKernels + 2], c->stream);
-        c->a_pos += (uint64_t)nb * UA3_AUDIO_BLOCK;
-        c->f_pos += (uint64_t)nf * UA3_FFT_SIZE;
-        c->last_audio_blocks = nb;
-        c->last_fft_frames = nf;
+        const int rc = rx_run_stage(c, ev, &launches);
+        if (rc != UA3_OK) return rc;
     } else {
         c->a_pos = c->f_pos = c->w_pos;
         if (ev) { cudaEventRecord(ev[kDdcKernels + 1], c->stream); cudaEventRecord(ev[kDdcKernels + 2], c->stream); }
@@ -430,10 +511,13 @@ static int rx_allocate(ua3reo_ctx* c) {
     UA3_CUDA(dev_alloc(c, &r.params, (size_t)c->n_ch));
     UA3_CUDA(dev_alloc(c, &r.state, (size_t)c->n_ch));
     UA3_CUDA(dev_alloc(c, &r.order, (size_t)c->n_ch));
-    UA3_CUDA(dev_alloc(c, &r.audio_out, (size_t)c->n_ch * r.audio_ch_stride));
-    UA3_CUDA(dev_alloc(c, &r.spectra, (size_t)c->n_ch * r.spec_ch_stride));
-    UA3_CUDA(dev_alloc(c, &r.waterfall, (size_t)c->n_ch * r.spec_ch_stride));
-    UA3_CUDA(dev_alloc(c, &r.cw_mag, (size_t)c->n_ch * r.max_audio_blocks));
+    for (int i = 0; i < 2; ++i) {
+        UA3_CUDA(dev_alloc(c, &c->rx_audio2[i], (size_t)c->n_ch * r.audio_ch_stride));
+        UA3_CUDA(dev_alloc(c, &c->rx_spec2[i], (size_t)c->n_ch * r.spec_ch_stride));
+        UA3_CUDA(dev_alloc(c, &c->rx_wf2[i], (size_t)c->n_ch * r.spec_ch_stride));
+        UA3_CUDA(dev_alloc(c, &c->rx_cw2[i], (size_t)c->n_ch * r.max_audio_blocks));
+    }
+    r.audio_out = c->rx_audio2[0]; r.spectra = c->rx_spec2[0]; r.waterfall = c->rx_wf2[0]; r.cw_mag = c->rx_cw2[0];
     UA3_CUDA(dev_alloc(c, &r.wtf_hist, (size_t)c->n_ch * kWtfRows * kFftBins));
     UA3_CUDA(dev_alloc(c, &r.wtf_head, (size_t)c->n_ch));
     UA3_CUDA(dev_alloc(c, &r.wtf_pending_hz, (size_t)c->n_ch));
@@ -470,6 +554,7 @@ static int rx_allocate(ua3reo_ctx* c) {
 int ua3reo_rx_enable(ua3reo_ctx* c, int enable) {
     if (!c) return fail(UA3_E_INVAL, "null context");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     if (enable) {
         const int rc = rx_allocate(c);
         if (rc != UA3_OK) return rc;
@@ -486,6 +571,7 @@ static int rx_apply_settings(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua
                              const char* who) {
     if (!c || !settings || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_rx_set: range");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     const int rc = rx_allocate(c);
     if (rc != UA3_OK) return rc;
     std::vector<RxParams> np(c->h_par.begin() + first, c->h_par.begin() + first + n);
@@ -548,6 +634,7 @@ int ua3reo_rx_set_live(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua3reo_r
 int ua3reo_rx_set_notch(ua3reo_ctx* c, uint32_t first, uint32_t n, const uint16_t* notch_fc) {
     if (!c || !notch_fc || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_rx_set_notch: range");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     const int rc = rx_allocate(c);
     if (rc != UA3_OK) return rc;
     for (uint32_t i = 0; i < n; ++i) {
@@ -571,6 +658,7 @@ int ua3reo_rx_push_frames(ua3reo_ctx* c, const uint8_t* frames_host, size_t n) {
         UA3_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy[c->n_push & 1], 0));
         c->copy_pending[c->n_push & 1] = false;
     }
+    { const int rc = rx_ring_guard(c); if (rc != UA3_OK) return rc; }
     const uint32_t ring = c->b.frame_ch_stride;
     const uint32_t first = (uint32_t)(c->w_pos & c->b.ring_mask);
     const size_t n1 = (first + n <= ring) ? n : (size_t)(ring - first);
@@ -584,14 +672,7 @@ int ua3reo_rx_push_frames(ua3reo_ctx* c, const uint8_t* frames_host, size_t n) {
                                    (n - n1) * UA3_FRAME_BYTES, c->n_ch, cudaMemcpyHostToDevice, c->stream));
     c->w_pos += n;
     int launches = 0;
-    const uint32_t nb = (uint32_t)((c->w_pos - c->a_pos) / UA3_AUDIO_BLOCK);
-    const uint32_t nf = (uint32_t)((c->w_pos - c->f_pos) / UA3_FFT_SIZE);
-    UA3_CUDA(rx_launch_audio(c->rx, (uint32_t)(c->a_pos & c->b.ring_mask), nb, c->stream, &launches));
-    UA3_CUDA(rx_launch_fft(c->rx, (uint32_t)(c->f_pos & c->b.ring_mask), nf, c->stream, &launches));
-    c->a_pos += (uint64_t)nb * UA3_AUDIO_BLOCK;
-    c->f_pos += (uint64_t)nf * UA3_FFT_SIZE;
-    c->last_audio_blocks = nb;
-    c->last_fft_frames = nf;
+    { const int rc = rx_run_stage(c, nullptr, &launches); if (rc != UA3_OK) return rc; }
     c->last_frames = n;
     c->pushed = true;
     c->launches += (uint64_t)launches;
@@ -612,6 +693,7 @@ int ua3reo_rx_read_audio(ua3reo_ctx* c, int32_t* dst, size_t n_blocks) {
     if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_audio: STM32 stage not enabled");
     if (n_blocks != c->last_audio_blocks) return fail(UA3_E_INVAL, "ua3reo_rx_read_audio: n_blocks != blocks of last push");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     const size_t row = n_blocks * 2 * UA3_AUDIO_BLOCK * sizeof(int32_t);
     if (n_blocks)
         UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.audio_out, (size_t)c->rx.audio_ch_stride * sizeof(int32_t), row, c->n_ch,
@@ -625,6 +707,7 @@ int ua3reo_rx_read_spectra(ua3reo_ctx* c, float* dst, size_t n_frames) {
     if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_spectra: STM32 stage not enabled");
     if (n_frames != c->last_fft_frames) return fail(UA3_E_INVAL, "ua3reo_rx_read_spectra: n_frames != FFT frames of last push");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     const size_t row = n_frames * UA3_FFT_BINS * sizeof(float);
     if (n_frames)
         UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.spectra, (size_t)c->rx.spec_ch_stride * sizeof(float), row, c->n_ch,
@@ -633,11 +716,47 @@ int ua3reo_rx_read_spectra(ua3reo_ctx* c, float* dst, size_t n_frames) {
     return UA3_OK;
 }
 
+// Pipelined result reads: the copy is enqueued on the copy stream behind the STM32 stage of the last push and the
+// call returns at once; results are double buffered, so the next push's DDC *and* STM32 kernels overlap the copy (the
+// push after that waits for it before reusing the result set).  dst should be pinned host memory; ua3reo_sync() (or ua3reo_rx_sync) before it is read.
+int ua3reo_rx_read_audio_async(ua3reo_ctx* c, int32_t* dst, size_t n_blocks) {
+    if (!c || (!dst && n_blocks)) return fail(UA3_E_INVAL, "ua3reo_rx_read_audio_async: null argument");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_audio_async: STM32 stage not enabled");
+    if (n_blocks != c->last_audio_blocks) return fail(UA3_E_INVAL, "ua3reo_rx_read_audio_async: n_blocks != blocks of last push");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t row = n_blocks * 2 * UA3_AUDIO_BLOCK * sizeof(int32_t);
+    const int set = c->rx_last_slot;
+    UA3_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_rx_done[set], 0));
+    if (n_blocks)
+        UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.audio_out, (size_t)c->rx.audio_ch_stride * sizeof(int32_t), row, c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->copy_stream));
+    UA3_CUDA(cudaEventRecord(c->ev_rxcopy[set], c->copy_stream));
+    c->rxcopy_pending[set] = true;
+    return UA3_OK;
+}
+
+int ua3reo_rx_read_spectra_async(ua3reo_ctx* c, float* dst, size_t n_frames) {
+    if (!c || (!dst && n_frames)) return fail(UA3_E_INVAL, "ua3reo_rx_read_spectra_async: null argument");
+    if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_spectra_async: STM32 stage not enabled");
+    if (n_frames != c->last_fft_frames) return fail(UA3_E_INVAL, "ua3reo_rx_read_spectra_async: n_frames != FFT frames of last push");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t row = n_frames * UA3_FFT_BINS * sizeof(float);
+    const int set = c->rx_last_slot;
+    UA3_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_rx_done[set], 0));
+    if (n_frames)
+        UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.spectra, (size_t)c->rx.spec_ch_stride * sizeof(float), row, c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->copy_stream));
+    UA3_CUDA(cudaEventRecord(c->ev_rxcopy[set], c->copy_stream));
+    c->rxcopy_pending[set] = true;
+    return UA3_OK;
+}
+
 int ua3reo_rx_read_audio_usb(ua3reo_ctx* c, int16_t* dst, size_t n_blocks) {
     if (!c || (!dst && n_blocks)) return fail(UA3_E_INVAL, "ua3reo_rx_read_audio_usb: null argument");
     if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_audio_usb: STM32 stage not enabled");
     if (n_blocks != c->last_audio_blocks) return fail(UA3_E_INVAL, "ua3reo_rx_read_audio_usb: n_blocks != blocks of last push");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     if (!n_blocks) return UA3_OK;
     const size_t n_words = n_blocks * 2 * UA3_AUDIO_BLOCK;
     std::vector<float> undo(c->n_ch);
@@ -663,6 +782,7 @@ int ua3reo_rx_read_waterfall(ua3reo_ctx* c, uint16_t* dst, size_t n_frames) {
     if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_waterfall: STM32 stage not enabled");
     if (n_frames != c->last_fft_frames) return fail(UA3_E_INVAL, "ua3reo_rx_read_waterfall: n_frames != FFT frames of last push");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     const size_t row = n_frames * UA3_FFT_BINS * sizeof(uint16_t);
     if (n_frames)
         UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.waterfall, (size_t)c->rx.spec_ch_stride * sizeof(uint16_t), row, c->n_ch,
@@ -677,6 +797,7 @@ int ua3reo_rx_move_waterfall(ua3reo_ctx* c, uint32_t first, uint32_t n, const in
     if (!c || !freq_diff_hz || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_rx_move_waterfall: range");
     if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_move_waterfall: STM32 stage not enabled");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     // accumulate on the host copy so that two retunes between FFT frames add up like Freq - currentFFTFreq does
     std::vector<int32_t> pend(n);
     UA3_CUDA(cudaMemcpyAsync(pend.data(), c->rx.wtf_pending_hz + first, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -692,6 +813,7 @@ int ua3reo_rx_read_waterfall_history(ua3reo_ctx* c, uint16_t* dst) {
     if (!c || !dst) return fail(UA3_E_INVAL, "ua3reo_rx_read_waterfall_history: null argument");
     if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_waterfall_history: STM32 stage not enabled");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     const size_t per_ch = (size_t)kWtfRows * kFftBins;
     std::vector<uint16_t> ring((size_t)c->n_ch * per_ch);
     std::vector<uint32_t> head(c->n_ch);
@@ -710,6 +832,7 @@ int ua3reo_rx_read_cw(ua3reo_ctx* c, float* dst, size_t n_blocks) {
     if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_cw: STM32 stage not enabled");
     if (n_blocks != c->last_audio_blocks) return fail(UA3_E_INVAL, "ua3reo_rx_read_cw: n_blocks != blocks of last push");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     const size_t row = n_blocks * sizeof(float);
     if (n_blocks)
         UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.cw_mag, (size_t)c->rx.max_audio_blocks * sizeof(float), row, c->n_ch,
@@ -825,6 +948,7 @@ int ua3reo_rx_read_smeter(ua3reo_ctx* c, float* dst, int reset) {
     if (!c || !dst) return fail(UA3_E_INVAL, "ua3reo_rx_read_smeter: null argument");
     if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_smeter: STM32 stage not enabled");
     UA3_CUDA(cudaSetDevice(c->device));
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     const size_t off = offsetof(RxState, smeter_max);
     UA3_CUDA(cudaMemcpy2DAsync(dst, 2 * sizeof(float), reinterpret_cast<const uint8_t*>(c->rx.state) + off, sizeof(RxState),
                                2 * sizeof(float), c->n_ch, cudaMemcpyDeviceToHost, c->stream));
@@ -840,6 +964,7 @@ int ua3reo_sync(ua3reo_ctx* c) {
     UA3_CUDA(cudaSetDevice(c->device));
     UA3_CUDA(cudaStreamSynchronize(c->h2d_stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->rx_stream));
     UA3_CUDA(cudaStreamSynchronize(c->copy_stream));
     return UA3_OK;
 }

@@ -51,22 +51,40 @@ UA3_D int16_t frame_word(uint64_t f, int w) {
 
 // ------------------------------------------------------------------------------------------------
 // processRxAudio for n_blocks consecutive 192-sample blocks of every channel.
-// grid.x = ceil(n_ch / 16), block = one warp.
+// A warp serves 16 channels and never talks to another warp (no CTA barrier); a CTA is kRxAudioWarps such warps
+// whose shared-memory slices fill the SM (6 x 37 KB), so that the kernel occupies ceil(n_ch / 96) WHOLE SMs instead
+// of scattering one-warp CTAs over every SM: it is latency bound (a few warps per SM is all it can use), and packed
+// this way it runs beside the next block's persistent front kernel, which simply gets that many SMs fewer.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+constexpr int kRxAudioWarps = 6;
+constexpr int kRxBufFloats = kAudioBlock * 32;                         // s_buf[sample][lane]: lane's own rail, conflict free
+constexpr int kRxWinFloats = (kLmsTaps - 1 + kSubBlock) * 16;          // NLMS input window of the I lanes
+constexpr int kRxRefFloats = 2 * kSubBlock * 16;                       // lms2_reference of the I lanes
+constexpr size_t kRxAudioSmemPerWarp = (size_t)(kRxBufFloats + kRxWinFloats + kRxRefFloats) * sizeof(float);
+constexpr size_t kRxAudioSmemBytes = kRxAudioSmemPerWarp * kRxAudioWarps;
+
+__global__ void __launch_bounds__(32 * kRxAudioWarps, 1)
 rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t frame_ch_stride, uint32_t start,
                 uint32_t n_blocks, const RxParams* __restrict__ params, RxState* __restrict__ state, uint32_t n_ch,
                 int32_t* __restrict__ audio_out, uint32_t out_ch_stride, float* __restrict__ cw_mag, uint32_t cw_ch_stride,
                 const uint32_t* __restrict__ order) {
-    __shared__ float s_buf[kAudioBlock][32];            // [sample][lane]: lane's own rail, conflict free
-    __shared__ float s_win[kLmsTaps - 1 + kSubBlock][16];   // NLMS input window of the I lanes
-    __shared__ float s_ref[2 * kSubBlock][16];              // lms2_reference of the I lanes
+#if defined(UA3_HOST_EMU)
+    static float s_dyn[kRxAudioSmemBytes / sizeof(float)];
+#else
+    extern __shared__ __align__(16) float s_dyn[];
+#endif
+    const int warp = threadIdx.x >> 5;
+    float* s_base = s_dyn + (size_t)warp * (kRxAudioSmemPerWarp / sizeof(float));
+    float (*s_buf)[32] = reinterpret_cast<float (*)[32]>(s_base);
+    float (*s_win)[16] = reinterpret_cast<float (*)[16]>(s_base + kRxBufFloats);
+    float (*s_ref)[16] = reinterpret_cast<float (*)[16]>(s_base + kRxBufFloats + kRxWinFloats);
 
     const int lane = threadIdx.x & 31, pair = lane >> 1, rail = lane & 1;
     // Channels are visited in the host-built order that groups equal (mode, DNR, notch) settings, so that the
     // 16 channels of a warp take the same branches (mode is per-channel data; without the grouping a warp with
     // mixed modes executes every demodulator for every sample).
-    const uint32_t slot = blockIdx.x * 16u + (uint32_t)pair;
+    if ((blockIdx.x * (uint32_t)kRxAudioWarps + (uint32_t)warp) * 16u >= n_ch) return;    // whole warp beyond the bank (no barriers below)
+    const uint32_t slot = (blockIdx.x * (uint32_t)kRxAudioWarps + (uint32_t)warp) * 16u + (uint32_t)pair;
     const bool live = slot < n_ch;
     const uint32_t ch = order[live ? slot : (n_ch - 1u)];   // dead pairs shadow the last slot's channel and never store
     const RxParams& P = params[ch];
@@ -646,7 +664,12 @@ cudaError_t rx_launch_init_state(const RxBuffers& b, cudaStream_t st, int* launc
 
 cudaError_t rx_upload_constants(const float* window, const float* twiddle, const uint16_t* colors, const float* zoom_biquad,
                                 const float* zoom_fir) {
-    cudaError_t e = cudaMemcpyToSymbol(c_fft_window, window, sizeof(float) * kFftSize);
+    cudaError_t e = cudaSuccess;
+#if !defined(UA3_HOST_EMU)
+    e = cudaFuncSetAttribute(rx_audio_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRxAudioSmemBytes);
+    if (e != cudaSuccess) return e;
+#endif
+    e = cudaMemcpyToSymbol(c_fft_window, window, sizeof(float) * kFftSize);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbol(c_zoom_biquad, zoom_biquad, sizeof(float) * 80);
     if (e != cudaSuccess) return e;
@@ -712,7 +735,8 @@ cudaError_t rx_launch_usb_pack(const RxBuffers& b, uint32_t n_blocks, const floa
 
 cudaError_t rx_launch_audio(const RxBuffers& b, uint32_t start, uint32_t n_blocks, cudaStream_t st, int* launches) {
     if (!n_blocks) return cudaSuccess;
-    UA3_LAUNCH(rx_audio_kernel, (b.n_ch + 15u) / 16u, 32, 0, st, b.frames, b.ring_mask, b.frame_ch_stride, start, n_blocks,
+    const uint32_t per_cta = 16u * (uint32_t)kRxAudioWarps;
+    UA3_LAUNCH(rx_audio_kernel, (b.n_ch + per_cta - 1u) / per_cta, 32 * kRxAudioWarps, kRxAudioSmemBytes, st, b.frames, b.ring_mask, b.frame_ch_stride, start, n_blocks,
                b.params, b.state, b.n_ch, b.audio_out, b.audio_ch_stride, b.cw_mag, b.max_audio_blocks, b.order);
     if (launches) *launches += 1;
     return cudaGetLastError();
