@@ -148,6 +148,32 @@ def test_live_against_host_built_firmware(pkg, oracle):
     rx0.close()
 
 
+def test_every_filter_table_against_host_built_firmware(pkg, oracle):
+    """All 32 lattice LPF tables (audio_filters.c:59-122, selected by Filter_Width, :141-303) and the five SSB HPF corners
+    (:305-333), each on its own channel, against live runs of the reference firmware on that channel's frames."""
+    if not oracle.have_fw_rx():
+        pytest.skip("oracle/_ref/fw_rx did not travel with this snapshot")
+    widths = [300, 500, 1400, 1600, 1800, 2100, 2300, 2500, 2700, 2900, 3000, 3200, 3400, 3600, 3800, 4000,
+              4200, 4400, 4600, 4800, 5000, 5500, 6000, 6500, 7000, 7500, 8000, 8500, 9000, 9500, 10000, 15000]
+    cases = []
+    for i, w in enumerate(widths):
+        mode = 3 if w <= 500 else (i % 2 if w <= 3400 else (10 if i % 2 else 8))      # CW_L, LSB/USB, AM/NFM
+        cases.append(dict(mode=mode, filter_width=w))
+    for hp in (100, 200, 300, 400, 500):
+        cases.append(dict(mode=1, filter_width=3000, ssb_hpf_pass=hp))
+    n = 1024 * (192 * 6 + 1)
+    frames, audio, spec, sm = _run_frames_through_gpu(pkg, oracle, cases, n, [n], 4242)
+    rx0 = pkg.Receiver(1, 1024)
+    exact = 0
+    for i, c in enumerate(cases):
+        ref = oracle.run_fw_rx(frames[i], rx0.rx_defaults(**c).as_dict())
+        assert ref["audio"].shape[0] == audio.shape[1] == 6
+        check(audio[i], ref["audio"], "filter sweep %s audio" % c)
+        exact += int(np.array_equal(audio[i], ref["audio"]))
+    rx0.close()
+    assert exact >= len(cases) - 8, "only %d of %d filter cases bit-exact" % (exact, len(cases))     # FM (atan2f) may differ by an ulp
+
+
 def test_pipelined_stage_and_async_reads(pkg, oracle):
     """The STM32 stage runs on its own stream one push behind the DDC; results read with the *_async calls while the next
     push is already running must equal the synchronous reads of an identical receiver."""
