@@ -188,6 +188,23 @@ int ua3reo_rx_move_waterfall(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const 
 /* CW decoder front end (cw_decoder.c:43-66): the Goertzel magnitude at 350 Hz of every 192-sample block of the final
  * audio, for channels in CW_L / CW_U with cw_decoder set (0 elsewhere).  dst is [n_channels][n_blocks] float. */
 int ua3reo_rx_read_cw(ua3reo_ctx *ctx, float *dst_host, size_t n_blocks);
+/* The host half of the CW decoder: what CWDecoder_Process() (cw_decoder.c:69-170) does with the Goertzel magnitude of
+ * a 192-sample block - adaptive threshold, 6 ms noise blanker, dit/dah and gap classification against a rolling dit time,
+ * Morse table (:172-247).  One call per audio block and channel with that block's ua3reo_rx_read_cw() value and the
+ * HAL_GetTick() time in ms (4 ms per block at 48 kHz); decoded characters (a space for a word gap) are written to out
+ * (up to out_cap) and their number is returned; `wpm` is CW_Decoder_WPM.  Pure host function, fields named after the
+ * firmware's statics. */
+typedef struct ua3reo_cw_decoder {
+    float magnitudelimit, magnitudelimit_low;
+    uint8_t realstate, realstatebefore, filteredstate, filteredstatebefore, stop;
+    uint8_t reserved[1];
+    uint16_t wpm;
+    int64_t laststarttime, starttimehigh, highduration, startttimelow, lowduration, hightimesavg, lasthighduration;
+    char code[24];
+} ua3reo_cw_decoder;
+void ua3reo_cw_decoder_init(ua3reo_cw_decoder *st);
+int ua3reo_cw_decoder_step(ua3reo_cw_decoder *st, float magnitude, uint32_t tick_ms, char *out, int out_cap);
+
 /* ADC_MIN / ADC_MAX tracking of stm32_interface.v:384-397 over the ADC samples pushed since the last reset (the FPGA
  * resets to +2000 / -2000 when the MCU reads them with command 2, stm32_interface.v:172-205 <- fpga.c:222-284), and
  * the number of samples at either rail of the 12-bit range (what the AD9226 flags on its OTR pin). */

@@ -217,6 +217,41 @@ def test_pipelined_stage_and_async_reads(pkg, oracle):
             assert np.array_equal(got_s[b].numpy()[:, :ns], want_s[b]), "block %d spectra" % b
 
 
+def test_cw_decoder_end_to_end(pkg, oracle):
+    """Keyed carrier -> STM32 stage in CW_U with the decoder on (device Goertzel front end per 192-sample block)
+    -> host state machine (ua3reo_cw_decoder_step): the Morse text comes out, as the firmware shows it in its text bar."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_golden_cw as g
+    audio = g.keyed_audio("CQ CQ DE UA3REO UA3REO K", 20, amp=1.0, noise=0.0)
+    n = audio.size
+    # recover the on/off envelope (the generator's tone is sin(2 pi 350 t) * env) and key a +350 Hz complex exponential with it
+    t = np.arange(n) / 48000.0
+    key = np.zeros(n)
+    blk = 48                                                   # 1 ms resolution is plenty for 60 ms dits
+    a = np.abs(audio).reshape(-1, blk).max(1) > 0.1
+    key = np.repeat(a, blk).astype(np.float64)
+    rng = np.random.default_rng(5)
+    z = 6000.0 * key * np.exp(2j * np.pi * 350.0 * t) + rng.normal(0, 20, n) + 1j * rng.normal(0, 20, n)
+    words = np.stack([np.rint(z.imag), np.rint(z.real), np.rint(z.imag), np.rint(z.real)], 1).astype(np.int16)   # SPEC_Q, SPEC_I, VOICE_Q, VOICE_I
+    frames = words.astype(">i2").view(np.uint8).reshape(n, 8)
+    rx = pkg.Receiver(2, 1 << 22)
+    rx.rx_enable(True)
+    rx.rx_set([rx.rx_defaults(mode=4, filter_width=500, cw_decoder=1, agc=1), rx.rx_defaults(mode=1)])
+    dec = pkg.CwDecoder(pkg.load_library())
+    text = ""
+    step = 192 * 20
+    for off in range(0, n - step + 1, step):
+        rx.rx_push_frames(np.repeat(frames[None, off:off + step], 2, 0))
+        cw = rx.read_cw()
+        assert not cw[1].any()                                  # the decoder only runs in CW modes with TRX.CWDecoder set
+        for m in cw[0]:
+            text += dec.step(float(m))
+    rx.close()
+    assert "UA3REO UA3REO" in text, text          # (the first letters train the adaptive thresholds; AGC pumps the noise up in the tail)
+    assert 12 <= dec.wpm <= 26, dec.wpm
+
+
 def test_rejects_settings_without_firmware_table(pkg):
     rx = pkg.Receiver(2, 1024)
     rx.rx_enable(True)

@@ -105,6 +105,8 @@ def _bind(lib):
         "ua3reo_adc_stats": (c.c_int, [vp, c.POINTER(c.c_int16), c.POINTER(c.c_int16), c.POINTER(u32), c.c_int]),
         "ua3reo_smeter_dbm": (c.c_int16, [c.c_float, c.c_float, c.c_uint8]),
         "ua3reo_get_params": (c.c_int, [vp, vp, c.POINTER(c.c_int16), c.POINTER(c.c_int16), c.c_int]),
+        "ua3reo_cw_decoder_init": (None, [vp]),
+        "ua3reo_cw_decoder_step": (c.c_int, [vp, c.c_float, u32, vp, c.c_int]),
         "ua3reo_autogain_init": (None, [vp]),
         "ua3reo_autogain_step": (None, [vp, c.c_int16]),
         "ua3reo_duc_enable": (c.c_int, [vp, u32]),
@@ -157,6 +159,29 @@ def phrase_from_frequency(freq_hz, lib=None):
     swap = ctypes.c_int(0)
     w = lib.ua3reo_phrase_from_frequency(int(freq_hz), ctypes.byref(swap))
     return int(w), bool(swap.value)
+
+
+class CwDecoder(ctypes.Structure):
+    """Host half of the CW decoder (ua3reo_cw_decoder): feed one Goertzel magnitude per 192-sample block (Receiver.read_cw)."""
+    _fields_ = ([("magnitudelimit", ctypes.c_float), ("magnitudelimit_low", ctypes.c_float)] +
+                [(n, ctypes.c_uint8) for n in ("realstate", "realstatebefore", "filteredstate", "filteredstatebefore", "stop", "reserved")] +
+                [("wpm", ctypes.c_uint16)] +
+                [(n, ctypes.c_int64) for n in ("laststarttime", "starttimehigh", "highduration", "startttimelow", "lowduration",
+                                               "hightimesavg", "lasthighduration")] +
+                [("code", ctypes.c_char * 24)])
+
+    def __init__(self, lib=None):
+        super().__init__()
+        self._lib = lib or load_library()
+        self._lib.ua3reo_cw_decoder_init(ctypes.byref(self))
+        self._buf = ctypes.create_string_buffer(16)
+        self.tick_ms = 0
+
+    def step(self, magnitude, tick_ms=None):
+        """One audio block: returns the characters decoded by this block (a space marks a word gap)."""
+        self.tick_ms = self.tick_ms + 4 if tick_ms is None else int(tick_ms)
+        n = self._lib.ua3reo_cw_decoder_step(ctypes.byref(self), float(magnitude), self.tick_ms, self._buf, 16)
+        return self._buf.raw[:min(n, 16)].decode("ascii")
 
 
 class AutoGain(ctypes.Structure):

@@ -924,6 +924,8 @@ void ua3reo_autogain_step(ua3reo_autogain* st, int16_t adc_max_amplitude) {
     }
 }
 
+#include "cw_host.cpp.inc"
+
 int16_t ua3reo_smeter_dbm(float sample_max, float sample_min, uint8_t rf_gain) {
     // stm32f4xx_it.c:398-407, settings.h:11,19-21 (ADC_BITS 12, FPGA_BUS_BITS 16, ADC_VREF 1.0, ratio 4, calibration 0.2)
     float vpp = (sample_max / (float)rf_gain) - (sample_min / (float)rf_gain);
