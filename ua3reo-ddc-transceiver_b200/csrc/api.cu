@@ -245,6 +245,8 @@ int ua3reo_reset(ua3reo_ctx* c) {
     UA3_CUDA(cudaMemsetAsync(b.YI, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * b.yi_stride, c->stream));
     UA3_CUDA(cudaMemsetAsync(b.YQ, 0, sizeof(int16_t) * (size_t)c->n_ch_pad * b.yq_stride, c->stream));
     c->carry = 0; c->last_frames = 0; c->pushed = false;
+    UA3_CUDA(cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < 2; ++i) { c->rx_done_valid[i] = false; c->rxcopy_pending[i] = false; c->copy_pending[i] = false; }
     c->w_pos = c->a_pos = c->f_pos = 0;
     c->last_audio_blocks = c->last_fft_frames = 0;
     if (c->rx_alloc) {
@@ -1189,6 +1191,7 @@ int ua3reo_profile_end(ua3reo_ctx* c, double* kernel_ms, uint32_t n_kernels, uin
     if (!c || !kernel_ms) return fail(UA3_E_INVAL, "null argument");
     UA3_CUDA(cudaSetDevice(c->device));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->rx_stream));     // the STM32 stage records its events on its own stream
     for (uint32_t k = 0; k < n_kernels; ++k) kernel_ms[k] = 0.0;
     for (uint32_t b = 0; b < c->prof_used; ++b)
         for (uint32_t k = 0; k < (uint32_t)kProfEvents - 1 && k < n_kernels; ++k) {
