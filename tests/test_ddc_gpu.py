@@ -1,4 +1,6 @@
 """Parity of the CUDA DDC (through the C ABI) with the golden model: bit-exact frames."""
+import os
+
 import numpy as np
 import pytest
 
@@ -214,3 +216,14 @@ def test_get_params_packet(pkg, oracle):
     pkt, mn, mx = rx.get_params()
     assert pkt[0] == 1 and (mn, mx) == (0, 2047)          # ADC_OTR
     rx.close()
+
+
+def test_c_host_driver_runs(pkg):
+    """The C host program over the C ABI (host/ua3reo_rx_host.c, built by build.sh): full chain for a small bank."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(pkg.LIB_PATH), "ua3reo_rx_host")
+    if os.path.basename(pkg.LIB_PATH) != "libua3reo_b200.so" or not os.path.exists(exe):
+        pytest.skip("C host driver not built beside the library")
+    out = subprocess.run([exe, "40", "3", str(1 << 17), "1"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "channels" in out.stdout and "checksum" in out.stdout.lower()
