@@ -987,7 +987,16 @@ int ua3reo_duc_enable(ua3reo_ctx* c, uint32_t max_tx_samples) {
     if (c->duc_alloc) return (max_tx_samples <= c->duc.max_in) ? UA3_OK : fail(UA3_E_STATE, "ua3reo_duc_enable: already enabled with a smaller block");
     UA3_CUDA(cudaSetDevice(c->device));
     DucBuffers& d = c->duc;
-    d.n_ch = c->n_ch; d.max_in = max_tx_samples; d.nco_tab = c->b.nco_tab; d.fcw = c->b.fcw;
+    d.n_ch = c->n_ch; d.max_in = max_tx_samples; d.fcw = c->b.fcw;
+    {
+        int16_t* tab_dev = nullptr;
+        UA3_CUDA(dev_alloc(c, &tab_dev, (size_t)kNcoBigTabWords));
+        std::vector<int16_t> tab(kNcoBigTabWords);
+        build_duc_nco_table(tab.data());
+        UA3_CUDA(cudaMemcpyAsync(tab_dev, tab.data(), tab.size() * sizeof(int16_t), cudaMemcpyHostToDevice, c->stream));
+        UA3_CUDA(cudaStreamSynchronize(c->stream));
+        d.nco_tab = tab_dev;
+    }
     UA3_CUDA(dev_alloc(c, &d.state, (size_t)c->n_ch));
     UA3_CUDA(dev_alloc(c, &d.iq_in, (size_t)c->n_ch * max_tx_samples * 2));
     UA3_CUDA(dev_alloc(c, &d.dac, (size_t)c->n_ch * max_tx_samples * 1024));

@@ -18,14 +18,16 @@ namespace ua3 {
 __constant__ int16_t c_tx_c1[24];
 __constant__ int16_t c_tx_c2[24];
 
-// NCO sine, 14 bit: (sin_c*cos_f + sin_f*cos_c + 2^12) >> 13, P = phase << 10
-UA3_D int32_t nco_sin14(const uint32_t* __restrict__ tab, uint32_t P) {
-    const uint32_t w = tab[P >> 21];
-    const int32_t sc = (int32_t)w >> 16;
-    const int32_t cc = (int32_t)(int16_t)(w & 0xFFFFu);
-    const int32_t sf = (int32_t)nco_fine_level(P);
-    return (sc * kCosF + sf * cc + 4096) >> 13;
+// NCO sine, 14 bit: (sin_c*cos_f + sin_f*cos_c + 2^12) >> 13, P = phase << 10.  Like the receive front kernel, the DUC
+// reads it from a table indexed by (coarse address, fine-sine level) - 2048 x 26 int16 = 104 KB of shared memory per
+// CTA - instead of evaluating the angle sum every clock.
+UA3_HD int16_t duc_tab_entry(int32_t sc, int32_t cc, int32_t sf) { return (int16_t)((sc * kCosF + sf * cc + 4096) >> 13); }
+UA3_D int32_t nco_sin14(const int16_t* __restrict__ tab, uint32_t P) {
+    return tab[nco_bigtab_index(P >> 21, nco_fine_level(P))];
 }
+
+constexpr int kDucWarps = 4;                                     // 64 channels per CTA: one warp per SM sub-partition
+constexpr size_t kDucSmemBytes = (size_t)kBigTabWords * sizeof(int16_t);
 
 UA3_D int16_t tx_round14(int32_t acc) {      // tx_ciccomp.vhd:469 on the low 30 bits, wrap
     const uint32_t a30 = (uint32_t)acc & 0x3FFFFFFFu;
@@ -33,15 +35,24 @@ UA3_D int16_t tx_round14(int32_t acc) {      // tx_ciccomp.vhd:469 on the low 30
     return (int16_t)((int32_t)(r30 << 2) >> 16);
 }
 
-__global__ void __launch_bounds__(32)
-duc_kernel(const int16_t* __restrict__ iq_in, uint32_t n_in, uint32_t in_ch_stride, const uint32_t* __restrict__ nco_tab,
+__global__ void __launch_bounds__(32 * kDucWarps)
+duc_kernel(const int16_t* __restrict__ iq_in, uint32_t n_in, uint32_t in_ch_stride, const int16_t* __restrict__ nco_tab,
            const uint32_t* __restrict__ fcw, DucState* __restrict__ state, uint32_t n_ch, uint16_t* __restrict__ dac,
            size_t dac_ch_stride) {
-    __shared__ uint32_t s_tab[2048];
-    const int lane = threadIdx.x & 31, pair = lane >> 1, rail = lane & 1;
-    for (int i = lane; i < 2048; i += 32) s_tab[i] = nco_tab[i];
-    __syncwarp();
-    const uint32_t ch_raw = blockIdx.x * 16u + (uint32_t)pair;
+#if defined(UA3_HOST_EMU)
+    static int16_t s_tab[kBigTabWords];
+#else
+    extern __shared__ __align__(16) int16_t s_tab[];
+#endif
+    const int lane = threadIdx.x & 31, pair = lane >> 1, rail = lane & 1, warp = threadIdx.x >> 5;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(nco_tab);
+        uint4* dst = reinterpret_cast<uint4*>(s_tab);
+        for (int i = threadIdx.x; i < (int)(kDucSmemBytes / 16); i += 32 * kDucWarps) dst[i] = src[i];
+    }
+    __syncthreads();
+    const uint32_t ch_raw = (blockIdx.x * (uint32_t)kDucWarps + (uint32_t)warp) * 16u + (uint32_t)pair;
+    if ((blockIdx.x * (uint32_t)kDucWarps + (uint32_t)warp) * 16u >= n_ch) return;     // whole warp beyond the bank (no barriers below)
     const bool live = ch_raw < n_ch;
     const uint32_t ch = live ? ch_raw : (n_ch - 1u);
     DucState& S = state[ch];
@@ -57,6 +68,9 @@ duc_kernel(const int16_t* __restrict__ iq_in, uint32_t n_in, uint32_t in_ch_stri
     uint32_t P = (S.phase << 10) + (rail ? (1u << 30) : 0u);
     uint32_t otr = S.otr;
     const int64_t kLow = ~(int64_t)15;
+    // The interpolator feeds its first integrator only on the phase_0 clock (zero stuffing), so I6 is constant for the
+    // other 511 clocks of a 96 kHz period and the second integrator's increment is a constant that changes once.
+    int64_t c6 = (I6 >> 8) & kLow;
 
     const int16_t* in = iq_in + (size_t)ch * in_ch_stride;
     uint16_t* out = dac + (size_t)ch * dac_ch_stride;
@@ -94,8 +108,8 @@ duc_kernel(const int16_t* __restrict__ iq_in, uint32_t n_in, uint32_t in_ch_stri
                     const int64_t n10 = I10 + ((I9 >> 8) & kLow);
                     const int64_t n9 = I9 + ((I8 >> 8) & kLow);
                     const int64_t n8 = I8 + ((I7 >> 8) & kLow);
-                    const int64_t n7 = I7 + ((I6 >> 8) & kLow);
-                    if (t8 == 0 && u == 0) I6 = I6 + UP;                          // upsampling: only on the phase_0 clock
+                    const int64_t n7 = I7 + c6;
+                    if (t8 == 0 && u == 0) { I6 = I6 + UP; c6 = (I6 >> 8) & kLow; }   // upsampling: only on the phase_0 clock
                     I10 = n10; I9 = n9; I8 = n8; I7 = n7;
                     const int32_t m = o14 * nco_sin14(s_tab, P);                  // s14 x s14 -> s28
                     P += F;
@@ -123,15 +137,27 @@ duc_kernel(const int16_t* __restrict__ iq_in, uint32_t n_in, uint32_t in_ch_stri
     }
 }
 
+void build_duc_nco_table(int16_t* tab /* 2048 * 26 */) {
+    for (int k = 0; k < 2048; ++k)
+        for (int sf = 0; sf < kSfLevels; ++sf)
+            tab[nco_bigtab_index((uint32_t)k, (uint32_t)sf)] = duc_tab_entry(UA3_NCO_SIN_C[k], UA3_NCO_COS_C[k], sf);
+}
+
 cudaError_t duc_upload_constants() {
-    cudaError_t e = cudaMemcpyToSymbol(c_tx_c1, UA3_TXCOMP_C1, sizeof(int16_t) * 24);
+    cudaError_t e = cudaSuccess;
+#if !defined(UA3_HOST_EMU)
+    e = cudaFuncSetAttribute(duc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDucSmemBytes);
+    if (e != cudaSuccess) return e;
+#endif
+    e = cudaMemcpyToSymbol(c_tx_c1, UA3_TXCOMP_C1, sizeof(int16_t) * 24);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_tx_c2, UA3_TXCOMP_C2, sizeof(int16_t) * 24);
 }
 
 cudaError_t duc_launch(const DucBuffers& b, uint32_t n_in, cudaStream_t st, int* launches) {
     if (!n_in) return cudaSuccess;
-    UA3_LAUNCH(duc_kernel, (b.n_ch + 15u) / 16u, 32, 0, st, b.iq_in, n_in, b.max_in * 2u, b.nco_tab, b.fcw, b.state, b.n_ch,
+    const uint32_t per_cta = 16u * (uint32_t)kDucWarps;
+    UA3_LAUNCH(duc_kernel, (b.n_ch + per_cta - 1u) / per_cta, 32 * kDucWarps, kDucSmemBytes, st, b.iq_in, n_in, b.max_in * 2u, b.nco_tab, b.fcw, b.state, b.n_ch,
                b.dac, (size_t)b.max_in * 1024u);
     if (launches) *launches += 1;
     return cudaGetLastError();

@@ -19,7 +19,7 @@ struct DucState {
 
 struct DucBuffers {
     uint32_t n_ch = 0, max_in = 0;
-    const uint32_t* nco_tab = nullptr;
+    const int16_t* nco_tab = nullptr;   // [2048 * 26] 14-bit NCO sine by (coarse address, fine-sine level)
     const uint32_t* fcw = nullptr;      // shared with the DDC: one NCO tuning word per channel
     DucState* state = nullptr;          // [n_ch]
     int16_t* iq_in = nullptr;           // [n_ch][max_in][2]  TX_I, TX_Q (48 kHz, s16)
@@ -27,6 +27,7 @@ struct DucBuffers {
 };
 
 cudaError_t duc_upload_constants();
+void build_duc_nco_table(int16_t* tab);
 cudaError_t duc_launch(const DucBuffers& b, uint32_t n_in, cudaStream_t st, int* launches);
 
 }  // namespace ua3
