@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--channels-per-gpu", type=int, default=CH_PER_GPU)
     ap.add_argument("--block", type=int, default=BLOCK)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="ddc", choices=["ddc", "full_chain"],
+                    help="ddc (default, the contract's metric: BASELINE configs[2]/[3]) or full_chain (configs[4]: DDC + "
+                         "processRxAudio + FFT_doFFT per channel, modes LSB/USB/CW_U/AM/NFM round-robin, DNR + notch on half)")
     return ap.parse_args()
 
 
@@ -153,6 +156,17 @@ def run_ours(args):
     fcw_all = synth.random_fcw(n_ch * world, SEED)
     rx.set_fcw(fcw_all[rank * n_ch:(rank + 1) * n_ch])          # channels sharded by rank, contiguous slabs
     ext = torch.cuda.ExternalStream(rx.stream(), device=local)
+    full = args.workload == "full_chain"
+    audio_host = spec_host = None
+    if full:
+        # the STM32 stage for every channel; it runs on its own stream one push behind the DDC
+        rx.rx_enable(True)
+        mix = [(0, 2700), (1, 2700), (4, 500), (10, 6000), (8, 15000)]
+        rx.rx_set([rx.rx_defaults(mode=mix[c % 5][0], filter_width=mix[c % 5][1], dnr=(c // 5) % 2, notch=(c // 5) % 2)
+                   for c in range(n_ch)])
+        nb_max, nf_max = block // 1024 // 192 + 2, block // 1024 // 512 + 2
+        audio_host = [torch.empty((n_ch, nb_max, 384), dtype=torch.int32).pin_memory() for _ in range(2)]
+        spec_host = [torch.empty((n_ch, nf_max, 256), dtype=torch.float32).pin_memory() for _ in range(2)]
 
     # synthetic ADC: NB distinct blocks generated once on the host (pinned); rank 0 is the ingest rank
     NB = 4
@@ -216,6 +230,9 @@ def run_ours(args):
 
         def pull():
             rx.read_frames_async(frames_host[k[0] & 1])
+            if full:                                   # pipelined reads of the STM32 results of this push
+                rx.read_audio_async(audio_host[k[0] & 1])
+                rx.read_spectra_async(spec_host[k[0] & 1])
             k[0] += 1
         run_steps(n, host_blocks, after_push=pull)
         rx.sync()
@@ -235,6 +252,8 @@ def run_ours(args):
     with torch.cuda.stream(ext):
         e0.record()
     step_device_n(K)
+    if full:
+        rx.sync()                                      # the STM32 stage of the last push finishes on its own stream
     with torch.cuda.stream(ext):
         e1.record()
     barrier()
@@ -291,20 +310,28 @@ def run_ours(args):
         except Exception:
             pass
         step_bytes = 2.0 * block * (n_ch // 32) + 2 * 80.0 * n_ch * (block // 512) + 8.0 * n_ch * (block // 1024)
+        d2h = n_ch * (block // 1024) * 8
+        if full:
+            d2h += int(n_ch * (block / 1024.0 / 192.0) * 384 * 4 + n_ch * (block / 1024.0 / 512.0) * 256 * 4)
+        workload = ("BASELINE configs[2]/[3]: %d independent DDC channels per GPU (random tuning words, seed %d) "
+                    "over one shared synthetic 12-bit ADC stream, blocks of %d samples; full FPGA RX chain "
+                    "(NCO+mixer+CIC/512+compensator FIR+Hilbert FIR+Q delay+8-byte frames); "
+                    "N>1: channels sharded by rank, ADC block NCCL-broadcast from rank 0" % (n_ch, SEED, block))
+        if full:
+            workload = ("BASELINE configs[4]: full per-channel RX chain for %d channels per GPU - " % n_ch) + workload.split(": ", 1)[1] + \
+                       "; then processRxAudio + FFT_doFFT per channel (modes LSB/USB/CW_U/AM/NFM round-robin, DNR + notch on half)"
         line = {
-            "metric": "ddc_channel_adc_samples_per_s", "value": value, "unit": "channel*samples/s",
+            "metric": "rx_chain_channel_adc_samples_per_s" if full else "ddc_channel_adc_samples_per_s", "value": value,
+            "unit": "channel*samples/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]/[3]: %d independent DDC channels per GPU (random tuning words, seed %d) "
-                                   "over one shared synthetic 12-bit ADC stream, blocks of %d samples; full FPGA RX chain "
-                                   "(NCO+mixer+CIC/512+compensator FIR+Hilbert FIR+Q delay+8-byte frames); "
-                                   "N>1: channels sharded by rank, ADC block NCCL-broadcast from rank 0" % (n_ch, SEED, block),
+            "scaling": "weak", "vs_baseline": None, "dtype": "int64+f32" if full else "int64", "data": "synthetic",
+            "config": {"workload": workload,
                        "channels_total": n_ch * world, "channels_per_gpu": n_ch, "block_samples": block,
                        "real_time_channels": value / 49152000.0,
                        "l2": "per-step working set ~%.0f MB (chunk records + frames) exceeds the 126 MB L2; no flush needed"
                              % (step_bytes / 1e6)},
             "e2e": {"value": e2e, "unit": "channel*samples/s", "h2d_bytes_per_step": 2 * block,
-                    "d2h_bytes_per_step": n_ch * (block // 1024) * 8, "ms_per_step": ms_e2e / K},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
             "gpu_launches": int(launches),
             "roofline": {"bound": "int32_alu", "kernel": front_name, "achieved": achieved / 1e12, "peak": int32_peak / 1e12,
                          "unit": "TOP/s (INT32)", "frac": (achieved / int32_peak) if int32_peak else None,
