@@ -180,12 +180,14 @@ def test_pipelined_stage_and_async_reads(pkg, oracle):
     import torch
     cases = [dict(mode=1, dnr=1), dict(mode=0, notch=1, notch_fc=1300), dict(mode=10, filter_width=6000), dict(mode=8, filter_width=15000),
              dict(mode=4, filter_width=500, cw_decoder=1), dict(mode=1, fft_zoom=4)] * 20          # 120 channels: two rx_audio CTAs
-    n_blk, block = 6, 1024 * 192 * 2
-    adc = oracle.synth_adc(n_blk * block, seed=21)
+    block = 1024 * 192 * 2
+    sizes = [block, block, 1024 * 700 + 5, 1019, block - 1024 * 300, 1024 * 64, block, 1024 * 513 + 1000]      # ragged pushes too
+    adc = oracle.synth_adc(sum(sizes), seed=21)
     fcw = [605867 + 997 * i for i in range(len(cases))]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
 
     def make():
-        rx = pkg.Receiver(len(cases), block)
+        rx = pkg.Receiver(len(cases), 1 << 20)
         rx.set_fcw(fcw)
         rx.rx_enable(True)
         rx.rx_set([rx.rx_defaults(**c) for c in cases])
@@ -193,28 +195,30 @@ def test_pipelined_stage_and_async_reads(pkg, oracle):
 
     ref = make()
     want_a, want_s = [], []
-    for b in range(n_blk):
-        ref.push(adc[b * block:(b + 1) * block])
+    for b in range(len(sizes)):
+        ref.push(adc[offs[b]:offs[b + 1]])
         want_a.append(ref.read_audio()); want_s.append(ref.read_spectra())
     ref.close()
 
     rx = make()
-    dev = torch.from_numpy(adc.reshape(n_blk, block)).cuda()
-    got_a = [torch.empty((len(cases), 2, 384), dtype=torch.int32).pin_memory() for _ in range(n_blk)]
-    got_s = [torch.empty((len(cases), 1, 256), dtype=torch.float32).pin_memory() for _ in range(n_blk)]
+    dev = torch.from_numpy(adc).cuda()
+    got_a = [torch.empty((len(cases) * 6 * 384,), dtype=torch.int32).pin_memory() for _ in sizes]
+    got_s = [torch.empty((len(cases) * 3 * 256,), dtype=torch.float32).pin_memory() for _ in sizes]
     counts = []
-    for b in range(n_blk):                       # no host synchronisation inside the loop
-        rx.push(dev[b])
+    for b in range(len(sizes)):                  # no host synchronisation inside the loop
+        rx.push(dev[offs[b]:offs[b + 1]])
         na = rx.read_audio_async(got_a[b]); ns = rx.read_spectra_async(got_s[b])
         counts.append((na, ns))
     rx.sync()
     rx.close()
-    for b in range(n_blk):
+    assert sum(c[0] for c in counts) == sum(sizes) // 1024 // 192 and sum(c[1] for c in counts) == sum(sizes) // 1024 // 512
+    for b in range(len(sizes)):
         na, ns = counts[b]
-        assert (na, ns) == (want_a[b].shape[1], want_s[b].shape[1]) and na == 2
-        assert np.array_equal(got_a[b].numpy()[:, :na], want_a[b]), "block %d audio" % b
+        assert (na, ns) == (want_a[b].shape[1], want_s[b].shape[1])
+        if na:
+            assert np.array_equal(got_a[b].numpy()[:len(cases) * na * 384].reshape(len(cases), na, 384), want_a[b]), "push %d audio" % b
         if ns:
-            assert np.array_equal(got_s[b].numpy()[:, :ns], want_s[b]), "block %d spectra" % b
+            assert np.array_equal(got_s[b].numpy()[:len(cases) * ns * 256].reshape(len(cases), ns, 256), want_s[b]), "push %d spectra" % b
 
 
 def test_cw_decoder_end_to_end(pkg, oracle):
