@@ -1,11 +1,14 @@
 // ddc.cu - sm_100a kernels for the batched UA3REO receive DDC (one shared ADC stream, many channels).
 //
 // Launch sequence per ADC block of n = 512*M samples (M even), all on one stream:
-//   ddc_front_kernel   : ADC tile -> shared memory once per CTA, 32 channels x 8 chunks per tile,
-//                        one warp per chunk, lane = channel; writes chunk partial states L
-//   ddc_ciccomp_kernel : L (5-chunk comb window) -> 96 kHz CIC outputs (shared memory only) -> 65-tap compensator
-//                        -> 48 kHz outputs YI/YQ (int16)
-//   ddc_hilb_kernel    : YI (256-tap window), YQ (130 delay) -> 8-byte frames
+//   adc_expand_kernel  : int16 ADC block -> int32 pre-shifted << 9 (once per block); zeroes the front kernel's tile counter
+//   ddc_front_bt_kernel: persistent, one 1024-thread CTA per SM, 208 KB NCO table in shared memory; tiles of 256 channels x
+//                        4 chunks handed out from a global counter, pre-shifted ADC tiles double-buffered by TMA, no CTA
+//                        barrier in the loop; one warp per chunk, lane = channel; writes chunk partial states L
+//                        (ddc_front_kernel: 8 KB-table variant for banks below 256 channels)
+//   ddc_ciccomp_kernel : L records by one TMA bulk copy -> run-based comb recurrence -> 96 kHz CIC outputs (shared memory
+//                        only) -> 65-tap compensator, two frames per thread -> 48 kHz outputs YI/YQ (int16)
+//   ddc_hilb_kernel    : YI (256-tap antisymmetric window, 4 frames per thread), YQ (130 delay) -> 8-byte frames
 //   ddc_rotate_kernel  : move the tails of L/YI/YQ into their halos, advance the NCO phases
 #include "ddc_launch.h"
 #include "ddc_front.cuh"
