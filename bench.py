@@ -339,6 +339,9 @@ def run_ours(args):
                          "executed_ops_per_unit": static.get("sass_instructions_per_unit"),
                          "issue_frac": (static["sass_instructions_per_unit"] * float(n_ch) * block / front_s / int32_peak)
                                        if static.get("sass_instructions_per_unit") and front_s > 0 and int32_peak else None,
+                         "note": "achieved counts the 41 algorithmic INT32 ops per channel-sample of the HDL-literal formulation "
+                                 "(SURVEY.md 8d), which is why frac can exceed 1: the kernel executes executed_ops_per_unit "
+                                 "of them (table-driven NCO output stage, shifts fused into adds); issue_frac = executed ops / peak",
                          "ops_per_unit": A_INT_OPS, "units_per_launch": float(n_ch) * block,
                          "kernel_ms": front_s * 1e3,
                          "kernel_share_of_step": kms["front"] / max(sum(kms.values()), 1e-9),
