@@ -167,6 +167,25 @@ def run_ours(args):
         nb_max, nf_max = block // 1024 // 192 + 2, block // 1024 // 512 + 2
         audio_host = [torch.empty((n_ch, nb_max, 384), dtype=torch.int32).pin_memory() for _ in range(2)]
         spec_host = [torch.empty((n_ch, nf_max, 256), dtype=torch.float32).pin_memory() for _ in range(2)]
+    # N>1: the spectra are gathered back to rank 0 over NVLink (north_star): a device-to-device read of the last push's
+    # spectra on the library's copy stream, then an NCCL gather enqueued behind it on the same stream
+    gather_spectra = None
+    if full and world > 1:
+        nf_step = block // 1024 // 512
+        assert nf_step * 512 * 1024 == block, "--block must be a multiple of 512 frames for the spectra gather"
+        spec_dev = [torch.empty((n_ch, nf_step, 256), dtype=torch.float32, device="cuda") for _ in range(2)]
+        spec_all = [torch.empty((world, n_ch, nf_step, 256), dtype=torch.float32, device="cuda") for _ in range(2)] if rank == 0 else None
+        spec_all_host = [torch.empty((world, n_ch, nf_step, 256), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
+        cstream = torch.cuda.ExternalStream(rx.copy_stream(), device=local)
+
+        def gather_spectra(i, to_host):
+            b = i & 1
+            nf = rx.read_spectra_async(spec_dev[b])
+            assert nf == nf_step
+            with torch.cuda.stream(cstream):
+                dist.gather(spec_dev[b], list(spec_all[b].unbind(0)) if rank == 0 else None, dst=0)
+                if to_host and rank == 0:
+                    spec_all_host[b].copy_(spec_all[b], non_blocking=True)
 
     # synthetic ADC: NB distinct blocks generated once on the host (pinned); rank 0 is the ingest rank
     NB = 4
@@ -198,7 +217,7 @@ def run_ours(args):
             ev_ready[b].record(side)
         pending[i] = True
 
-    def run_steps(n, src_blocks, after_push=None):
+    def run_steps(n, src_blocks, after_push=None, to_host=False):
         if world > 1:
             pending.clear()
             prefetch(0, src_blocks)
@@ -210,6 +229,8 @@ def run_ours(args):
                     ext.wait_event(ev_ready[i & 1])
                     rx.push(bcast[i & 1])
                     ev_free[i & 1].record(ext)
+                if gather_spectra is not None:
+                    gather_spectra(i, to_host)
             else:
                 with torch.cuda.stream(ext):
                     rx.push(src_blocks[i % NB])
@@ -232,9 +253,10 @@ def run_ours(args):
             rx.read_frames_async(frames_host[k[0] & 1])
             if full:                                   # pipelined reads of the STM32 results of this push
                 rx.read_audio_async(audio_host[k[0] & 1])
-                rx.read_spectra_async(spec_host[k[0] & 1])
+                if gather_spectra is None:             # (N>1: the spectra go to rank 0 through the gather instead)
+                    rx.read_spectra_async(spec_host[k[0] & 1])
             k[0] += 1
-        run_steps(n, host_blocks, after_push=pull)
+        run_steps(n, host_blocks, after_push=pull, to_host=True)
         rx.sync()
 
     step_device_n(W)
@@ -319,7 +341,8 @@ def run_ours(args):
                     "N>1: channels sharded by rank, ADC block NCCL-broadcast from rank 0" % (n_ch, SEED, block))
         if full:
             workload = ("BASELINE configs[4]: full per-channel RX chain for %d channels per GPU - " % n_ch) + workload.split(": ", 1)[1] + \
-                       "; then processRxAudio + FFT_doFFT per channel (modes LSB/USB/CW_U/AM/NFM round-robin, DNR + notch on half)"
+                       "; then processRxAudio + FFT_doFFT per channel (modes LSB/USB/CW_U/AM/NFM round-robin, DNR + notch on half)" + \
+                       ("; spectra NCCL-gathered to rank 0 every step" if world > 1 else "")
         line = {
             "metric": "rx_chain_channel_adc_samples_per_s" if full else "ddc_channel_adc_samples_per_s", "value": value,
             "unit": "channel*samples/s",

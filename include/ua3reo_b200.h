@@ -99,6 +99,9 @@ int ua3reo_ddc_frames_device(ua3reo_ctx *ctx, const uint8_t **base, size_t *firs
 int ua3reo_sync(ua3reo_ctx *ctx);
 /* The context's CUDA stream (cudaStream_t), for callers that enqueue their own copies. */
 int ua3reo_stream(ua3reo_ctx *ctx, void **stream);
+/* The stream the pipelined result reads (ua3reo_ddc_read_frames_async, ua3reo_rx_read_*_async) run on, for callers that
+ * chain their own work behind them - e.g. an NCCL gather of the spectra a read has just placed in device memory. */
+int ua3reo_copy_stream(ua3reo_ctx *ctx, void **stream);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t ua3reo_launch_count(const ua3reo_ctx *ctx);
 
@@ -163,8 +166,8 @@ int ua3reo_rx_set_notch(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const uint1
 int ua3reo_rx_counts(ua3reo_ctx *ctx, size_t *audio_blocks, size_t *fft_frames);
 int ua3reo_rx_read_audio(ua3reo_ctx *ctx, int32_t *dst_host, size_t n_blocks);
 /* Pipelined variants: the copy is enqueued behind the STM32 stage of the last push (which runs on its own stream, one
- * push behind the DDC) and the call returns immediately; dst should be pinned host memory and is valid after
- * ua3reo_sync().  The next push's DDC kernels overlap both the stage and the copy. */
+ * push behind the DDC) and the call returns immediately; dst is pinned host memory or device memory (the copy
+ * kind is inferred) and is valid after ua3reo_sync() / for work enqueued on ua3reo_copy_stream().  The next push's DDC kernels overlap both the stage and the copy. */
 int ua3reo_rx_read_audio_async(ua3reo_ctx *ctx, int32_t *dst_host, size_t n_blocks);
 int ua3reo_rx_read_spectra_async(ua3reo_ctx *ctx, float *dst_host, size_t n_frames);
 /* The same audio as processRxAudio() hands to the USB audio class (audio_processor.c:415-432): volume undone,

@@ -43,7 +43,7 @@ typedef int cudaError_t;
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
 enum { cudaSuccess = 0 };
-enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
 enum { cudaStreamNonBlocking = 1 };
 struct cudaDeviceProp { int major = 10, minor = 0, multiProcessorCount = 2; };
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }

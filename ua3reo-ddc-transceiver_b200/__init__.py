@@ -97,6 +97,7 @@ def _bind(lib):
         "ua3reo_rx_read_audio_usb": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_smeter": (c.c_int, [vp, vp, c.c_int]),
         "ua3reo_rx_read_waterfall": (c.c_int, [vp, vp, sz]),
+        "ua3reo_copy_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_rx_read_audio_async": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_spectra_async": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_waterfall_history": (c.c_int, [vp, vp]),
@@ -471,6 +472,12 @@ class Receiver:
     def stream(self):
         s = ctypes.c_void_p()
         self._chk(self.lib.ua3reo_stream(self._h, ctypes.byref(s)))
+        return s.value or 0
+
+    def copy_stream(self):
+        """cudaStream_t of the pipelined result reads, as an integer (torch.cuda.ExternalStream)."""
+        s = ctypes.c_void_p()
+        self._chk(self.lib.ua3reo_copy_stream(self._h, ctypes.byref(s)))
         return s.value or 0
 
     def profile_begin(self, max_blocks):

@@ -731,7 +731,7 @@ int ua3reo_rx_read_audio_async(ua3reo_ctx* c, int32_t* dst, size_t n_blocks) {
     UA3_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_rx_done[set], 0));
     if (n_blocks)
         UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.audio_out, (size_t)c->rx.audio_ch_stride * sizeof(int32_t), row, c->n_ch,
-                                   cudaMemcpyDeviceToHost, c->copy_stream));
+                                   cudaMemcpyDefault, c->copy_stream));
     UA3_CUDA(cudaEventRecord(c->ev_rxcopy[set], c->copy_stream));
     c->rxcopy_pending[set] = true;
     return UA3_OK;
@@ -747,7 +747,7 @@ int ua3reo_rx_read_spectra_async(ua3reo_ctx* c, float* dst, size_t n_frames) {
     UA3_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_rx_done[set], 0));
     if (n_frames)
         UA3_CUDA(cudaMemcpy2DAsync(dst, row, c->rx.spectra, (size_t)c->rx.spec_ch_stride * sizeof(float), row, c->n_ch,
-                                   cudaMemcpyDeviceToHost, c->copy_stream));
+                                   cudaMemcpyDefault, c->copy_stream));
     UA3_CUDA(cudaEventRecord(c->ev_rxcopy[set], c->copy_stream));
     c->rxcopy_pending[set] = true;
     return UA3_OK;
@@ -970,6 +970,12 @@ int ua3reo_sync(ua3reo_ctx* c) {
     UA3_CUDA(cudaStreamSynchronize(c->stream));
     UA3_CUDA(cudaStreamSynchronize(c->rx_stream));
     UA3_CUDA(cudaStreamSynchronize(c->copy_stream));
+    return UA3_OK;
+}
+
+int ua3reo_copy_stream(ua3reo_ctx* c, void** stream) {
+    if (!c || !stream) return fail(UA3_E_INVAL, "null argument");
+    *stream = (void*)c->copy_stream;
     return UA3_OK;
 }
 
