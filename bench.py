@@ -173,19 +173,33 @@ def run_ours(args):
     if full and world > 1:
         nf_step = block // 1024 // 512
         assert nf_step * 512 * 1024 == block, "--block must be a multiple of 512 frames for the spectra gather"
-        spec_dev = [torch.empty((n_ch, nf_step, 256), dtype=torch.float32, device="cuda") for _ in range(2)]
-        spec_all = [torch.empty((world, n_ch, nf_step, 256), dtype=torch.float32, device="cuda") for _ in range(2)] if rank == 0 else None
-        spec_all_host = [torch.empty((world, n_ch, nf_step, 256), dtype=torch.float32).pin_memory() for _ in range(2)] if rank == 0 else None
+        GS = 4                                         # slots: the NCCL kernel only finds a free SM now and then (the front kernel and
+        #                                                rx_audio hold them all), so the gather may trail the compute by a step or two
+        spec_dev = [torch.empty((n_ch, nf_step, 256), dtype=torch.float32, device="cuda") for _ in range(GS)]
+        spec_all = [torch.empty((world, n_ch, nf_step, 256), dtype=torch.float32, device="cuda") for _ in range(GS)] if rank == 0 else None
+        spec_all_host = [torch.empty((world, n_ch, nf_step, 256), dtype=torch.float32).pin_memory() for _ in range(GS)] if rank == 0 else None
         cstream = torch.cuda.ExternalStream(rx.copy_stream(), device=local)
+        gstream = torch.cuda.Stream()                  # the gather runs here, so that the other pipelined reads are not held up
+        gather_pg = dist.new_group()                   # its own communicator: NCCL orders the collectives of one communicator, and a
+        #                                                gather that trails the compute must not sit in front of the next broadcast
+        ev_spec = [torch.cuda.Event() for _ in range(GS)]
+        ev_gdone = [torch.cuda.Event() for _ in range(GS)]
+        g_used = [False] * GS
 
         def gather_spectra(i, to_host):
-            b = i & 1
+            b = i % GS
+            if g_used[b]:
+                cstream.wait_event(ev_gdone[b])        # the gather of step i-2 has read spec_dev[b]
             nf = rx.read_spectra_async(spec_dev[b])
             assert nf == nf_step
-            with torch.cuda.stream(cstream):
-                dist.gather(spec_dev[b], list(spec_all[b].unbind(0)) if rank == 0 else None, dst=0)
+            ev_spec[b].record(cstream)
+            gstream.wait_event(ev_spec[b])
+            with torch.cuda.stream(gstream):
+                dist.gather(spec_dev[b], list(spec_all[b].unbind(0)) if rank == 0 else None, dst=0, group=gather_pg)
                 if to_host and rank == 0:
                     spec_all_host[b].copy_(spec_all[b], non_blocking=True)
+                ev_gdone[b].record(gstream)
+            g_used[b] = True
 
     # synthetic ADC: NB distinct blocks generated once on the host (pinned); rank 0 is the ingest rank
     NB = 4
@@ -241,6 +255,8 @@ def run_ours(args):
         """n ADC blocks, inputs resident in HBM (rank 0's device copy)."""
         run_steps(n, dev_blocks)
 
+    host_enqueue_ms = [0.0]
+
     def step_e2e_n(n):
         """Same steps through the host-facing C ABI: every step copies the ADC block from pinned host memory
         (H2D inside the timed region; at N>1 rank 0 ingests and the others receive the broadcast) and reads every
@@ -256,8 +272,12 @@ def run_ours(args):
                 if gather_spectra is None:             # (N>1: the spectra go to rank 0 through the gather instead)
                     rx.read_spectra_async(spec_host[k[0] & 1])
             k[0] += 1
+        t_host = time.perf_counter()
         run_steps(n, host_blocks, after_push=pull, to_host=True)
+        host_enqueue_ms[0] = 1e3 * (time.perf_counter() - t_host) / max(n, 1)     # host time to enqueue one step
         rx.sync()
+        if gather_spectra is not None:
+            gstream.synchronize()
 
     step_device_n(W)
     barrier()
@@ -276,6 +296,8 @@ def run_ours(args):
     step_device_n(K)
     if full:
         rx.sync()                                      # the STM32 stage of the last push finishes on its own stream
+        if gather_spectra is not None:
+            ext.wait_stream(gstream)                   # ... and the last gather
     with torch.cuda.stream(ext):
         e1.record()
     barrier()
@@ -354,7 +376,7 @@ def run_ours(args):
                        "l2": "per-step working set ~%.0f MB (chunk records + frames) exceeds the 126 MB L2; no flush needed"
                              % (step_bytes / 1e6)},
             "e2e": {"value": e2e, "unit": "channel*samples/s", "h2d_bytes_per_step": 2 * block,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "host_enqueue_ms_per_step": host_enqueue_ms[0]},
             "gpu_launches": int(launches),
             "roofline": {"bound": "int32_alu", "kernel": front_name, "achieved": achieved / 1e12, "peak": int32_peak / 1e12,
                          "unit": "TOP/s (INT32)", "frac": (achieved / int32_peak) if int32_peak else None,
@@ -377,6 +399,14 @@ def run_ours(args):
             "clocks": clocks,
         }
         print(json.dumps(line))
+    # tensors that were used on the library's copy stream must be released while that stream still exists (the caching
+    # allocator records an event on every stream a block was used on when the block is freed)
+    if gather_spectra is not None:
+        import gc
+        torch.cuda.synchronize()
+        del gather_spectra, spec_dev, spec_all, spec_all_host, cstream, gstream, ev_spec, ev_gdone, gather_pg
+        gc.collect()
+        torch.cuda.synchronize()
     rx.close()
     if world > 1:
         dist.destroy_process_group()
