@@ -287,7 +287,9 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    rx.profile_begin(K)
+    # inside the timed region only the dominant kernel is bracketed by CUDA events (two records per step); the per-kernel
+    # breakdown comes from a short second pass afterwards, outside the timed region
+    rx.profile_begin(K, kernel="front")
     launches0 = rx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -303,7 +305,14 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = rx.launch_count() - launches0
-    kms, nblocks = rx.profile_end()
+    kms_front, nblocks = rx.profile_end()
+    n_break = min(K, 16)
+    rx.profile_begin(n_break)
+    step_device_n(n_break)
+    if full:
+        rx.sync()
+    barrier()
+    kms_all, n_all = rx.profile_end()
     clocks = sampler.stop() if rank == 0 else None
 
     # end-to-end through the C ABI with host buffers
@@ -325,7 +334,7 @@ def run_ours(args):
     units = float(n_ch) * world * block * K
     value = units / (ms * 1e-3)
     e2e = units / (ms_e2e * 1e-3)
-    front_s = kms["front"] * 1e-3 / max(nblocks, 1)
+    front_s = kms_front["front"] * 1e-3 / max(nblocks, 1)
     achieved = A_INT_OPS * float(n_ch) * block / front_s if front_s > 0 else 0.0
 
     if rank == 0:
@@ -389,8 +398,10 @@ def run_ours(args):
                                  "of them (table-driven NCO output stage, shifts fused into adds); issue_frac = executed ops / peak",
                          "ops_per_unit": A_INT_OPS, "units_per_launch": float(n_ch) * block,
                          "kernel_ms": front_s * 1e3,
-                         "kernel_share_of_step": kms["front"] / max(sum(kms.values()), 1e-9),
-                         "all_kernels_ms_per_step": {k: v / max(nblocks, 1) for k, v in kms.items()},
+                         "kernel_share_of_step": front_s * 1e3 / (ms / K),
+                         "all_kernels_ms_per_step": {k: v / max(n_all, 1) for k, v in kms_all.items()},
+                         "all_kernels_note": "per-kernel times from a separate pass of %d steps right after the timed region "
+                                             "(events around every kernel); kernel_ms is from the timed region itself" % n_break,
                          "peak_source": "ua3reo_measure_int32_peak (IMAD+LOP3+IADD3 chains), measured live on this GPU; "
                                         "MEASURED_PEAKS.json has no integer peak",
                          "hbm": {"algorithmic_gbs": step_bytes / (ms / K * 1e-3) / 1e9,

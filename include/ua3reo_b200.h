@@ -290,6 +290,8 @@ int ua3reo_tx_feed_duc(ua3reo_ctx *ctx);
 #define UA3_DDC_KERNELS 5u
 #define UA3_PROFILED_KERNELS 7u
 int ua3reo_profile_begin(ua3reo_ctx *ctx, uint32_t max_blocks);
+/* As above with only the two events around kernel slot `kernel` (1 = front): the other slots read 0. */
+int ua3reo_profile_begin_kernel(ua3reo_ctx *ctx, uint32_t max_blocks, uint32_t kernel);
 int ua3reo_profile_end(ua3reo_ctx *ctx, double *kernel_ms, uint32_t n_kernels, uint32_t *blocks);
 
 /* Dependent-free INT32 issue-rate microbenchmark (IADD3 + IMAD interleaved) used as the roofline

@@ -126,6 +126,7 @@ def _bind(lib):
         "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_launch_count": (c.c_uint64, [vp]),
         "ua3reo_profile_begin": (c.c_int, [vp, u32]),
+        "ua3reo_profile_begin_kernel": (c.c_int, [vp, u32, u32]),
         "ua3reo_profile_end": (c.c_int, [vp, c.POINTER(c.c_double), u32, c.POINTER(u32)]),
         "ua3reo_measure_int32_peak": (c.c_int, [c.c_int, c.POINTER(c.c_double)]),
     }
@@ -480,8 +481,13 @@ class Receiver:
         self._chk(self.lib.ua3reo_copy_stream(self._h, ctypes.byref(s)))
         return s.value or 0
 
-    def profile_begin(self, max_blocks):
-        self._chk(self.lib.ua3reo_profile_begin(self._h, int(max_blocks)))
+    def profile_begin(self, max_blocks, kernel=None):
+        """kernel: None = events around every kernel; "front" etc. = only the two events around that kernel."""
+        if kernel is None:
+            self._chk(self.lib.ua3reo_profile_begin(self._h, int(max_blocks)))
+        else:
+            names = ["adc_expand", "front", "ciccomp", "hilb", "rotate", "rx_audio", "rx_fft"]
+            self._chk(self.lib.ua3reo_profile_begin_kernel(self._h, int(max_blocks), names.index(kernel)))
 
     def profile_end(self):
         ms = (ctypes.c_double * 7)()

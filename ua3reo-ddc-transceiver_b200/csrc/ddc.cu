@@ -530,10 +530,10 @@ cudaError_t ddc_upload_constants() {
 }
 
 cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, uint32_t ring_start,
-                             int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev) {
+                             int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev, uint32_t ev_mask) {
     const uint32_t n_chunks = n_samples / kCicR, n_frames = n_samples / kFrameAdc;
     if (n_chunks == 0) return cudaSuccess;
-    if (ev) cudaEventRecord(ev[0], st);
+    if (ev && ((ev_mask >> 0) & 1u)) cudaEventRecord(ev[0], st);
     // big-table kernel when a CTA tile (256 channels x 4 chunks) can be filled; the 8 KB-table kernel otherwise
     const bool big = b.front_variant != 1 && b.big_tab && (b.front_variant == 2 || ((b.n_ch_pad >> 5) >= (uint32_t)kBtCG && n_chunks >= (uint32_t)kBtTG));
     if (big) {
@@ -544,26 +544,26 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
         UA3_LAUNCH(adc_expand_kernel, (n8 + 255u) / 256u, 256, 0, st, adc_dev, n8, b.adc9, b.tile_counter);
         if (launches) *launches += 1;
 #endif
-        if (ev) cudaEventRecord(ev[1], st);
+        if (ev && ((ev_mask >> 1) & 1u)) cudaEventRecord(ev[1], st);
         UA3_LAUNCH(ddc_front_bt_kernel, grid, kBtThreads, kBtSmemBytes, st, adc_dev, b.adc9, n_chunks, b.big_tab, b.fcw, b.phase,
                    b.n_ch_pad, b.L, b.l_ch_stride, b.tile_counter);
     } else {
         const uint32_t n_tiles = ((n_chunks + kFrontWarps - 1) / kFrontWarps) * (b.n_ch_pad >> 5);
         const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count * 3);
-        if (ev) cudaEventRecord(ev[1], st);
+        if (ev && ((ev_mask >> 1) & 1u)) cudaEventRecord(ev[1], st);
         UA3_LAUNCH(ddc_front_kernel, grid, kFrontThreads, 0, st, adc_dev, n_chunks, b.nco_tab, b.fcw, b.phase, b.n_ch_pad,
                    b.L, b.l_ch_stride);
     }
-    if (ev) cudaEventRecord(ev[2], st);
+    if (ev && ((ev_mask >> 2) & 1u)) cudaEventRecord(ev[2], st);
     UA3_LAUNCH(ddc_ciccomp_kernel, dim3(b.n_ch, (n_frames + kCcFrames - 1) / kCcFrames), kCcThreads, 0, st, b.L, b.l_ch_stride, n_frames,
                b.YI, b.yi_stride, b.YQ, b.yq_stride);
-    if (ev) cudaEventRecord(ev[3], st);
+    if (ev && ((ev_mask >> 3) & 1u)) cudaEventRecord(ev[3], st);
     UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + kHbFrames - 1) / kHbFrames), kHbThreads, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
                n_frames, b.frames, b.frame_ch_stride, ring_start, b.ring_mask);
-    if (ev) cudaEventRecord(ev[4], st);
+    if (ev && ((ev_mask >> 4) & 1u)) cudaEventRecord(ev[4], st);
     UA3_LAUNCH(ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.YI, b.yi_stride,
                b.YQ, b.yq_stride, n_chunks, n_frames, b.phase, b.fcw, b.n_ch_pad);
-    if (ev) cudaEventRecord(ev[5], st);
+    if (ev && ((ev_mask >> 5) & 1u)) cudaEventRecord(ev[5], st);
     if (launches) *launches += kDdcKernels - 1;
     return cudaGetLastError();
 }

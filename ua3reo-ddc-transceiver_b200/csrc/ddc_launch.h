@@ -33,10 +33,10 @@ cudaError_t ddc_prepare_kernels();
 constexpr int kNcoBigTabWords = 2048 * 26;
 cudaError_t ddc_upload_constants();
 constexpr int kDdcKernels = 5;   // profile slots in launch order: adc_expand, front, cic+comp, hilb, rotate
-// ev: optional array of kDdcKernels + 1 events recorded before/after each kernel (profiling mode)
+// ev: optional array of kDdcKernels + 1 events recorded before/after each kernel (profiling mode); ev_mask selects which
 // ring_start: ring index that receives the block's first frame
 cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, uint32_t ring_start,
-                             int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev);
+                             int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev, uint32_t ev_mask = 0xFFFFFFFFu);
 cudaError_t measure_int32_peak(int sm_count, cudaStream_t st, double* ops_per_s);
 
 }  // namespace ua3
