@@ -221,6 +221,44 @@ def test_pipelined_stage_and_async_reads(pkg, oracle):
             assert np.array_equal(got_s[b].numpy()[:len(cases) * ns * 256].reshape(len(cases), ns, 256), want_s[b]), "push %d spectra" % b
 
 
+def test_many_small_pushes_wrap_the_ring(pkg, oracle):
+    """80 pushes of 2^16 samples into a receiver whose frame ring holds 2048 frames: the ring wraps more than twice while the
+    STM32 stage trails one push behind and every result leaves through the pipelined reads.  Frames must equal the golden
+    DDC and the audio must equal a receiver that got the same stream in three big pushes."""
+    import torch
+    n_push, block = 80, 1 << 16
+    cases = [dict(mode=1, dnr=1), dict(mode=0, notch=1), dict(mode=10, filter_width=6000), dict(mode=8, filter_width=15000)] * 10
+    adc = oracle.synth_adc(n_push * block, seed=77)
+    fcw = [605867 + 1009 * i for i in range(len(cases))]
+
+    small = pkg.Receiver(len(cases), block)
+    small.set_fcw(fcw); small.rx_enable(True); small.rx_set([small.rx_defaults(**c) for c in cases])
+    dev = torch.from_numpy(adc.reshape(n_push, block)).cuda()
+    fr = [torch.empty((len(cases), block // 1024, 8), dtype=torch.uint8).pin_memory() for _ in range(n_push)]
+    au = [torch.empty((len(cases) * 2 * 384,), dtype=torch.int32).pin_memory() for _ in range(n_push)]
+    na = []
+    for b in range(n_push):
+        small.push(dev[b])
+        small.read_frames_async(fr[b])
+        na.append(small.read_audio_async(au[b]))
+    small.sync()
+    small.close()
+    frames = np.concatenate([f.numpy() for f in fr], 1)
+    audio = np.concatenate([a.numpy()[:len(cases) * n * 384].reshape(len(cases), n, 384) for a, n in zip(au, na) if n], 1)
+
+    for ch in (0, 17, 39):
+        assert np.array_equal(frames[ch], oracle.golden_frames(adc, [fcw[ch]])[0]), "frames of channel %d" % ch
+    big = pkg.Receiver(len(cases), 1 << 21)
+    big.set_fcw(fcw); big.rx_enable(True); big.rx_set([big.rx_defaults(**c) for c in cases])
+    ref = []
+    cuts = [0, 2097152, 4194304, adc.size]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        big.push(adc[a:b]); ref.append(big.read_audio())
+    big.close()
+    ref = np.concatenate(ref, 1)
+    assert audio.shape == ref.shape and np.array_equal(audio, ref)
+
+
 def test_cw_decoder_end_to_end(pkg, oracle):
     """Keyed carrier -> STM32 stage in CW_U with the decoder on (device Goertzel front end per 192-sample block)
     -> host state machine (ua3reo_cw_decoder_step): the Morse text comes out, as the firmware shows it in its text bar."""
