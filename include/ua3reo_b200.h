@@ -5,15 +5,18 @@
  *
  * The reference has no FFI: its path sits behind void functions over global buffers
  * (SURVEY.md 8b).  Each entry point below names the reference interface it stands in for
- * (file:line under the reference tree).  Single-channel shims that keep the firmware's own
- * names live in ua3reo_fw_shim.h.
+ * (file:line under the reference tree).  The firmware's own entry points (processRxAudio,
+ * processTxAudio, FFT_doFFT, ReinitAudioFilters ...) implemented over this ABI for one receiver are in
+ * ua3reo-ddc-transceiver_b200/host/ua3reo_fw_shim.c, which is compiled with the firmware's headers.
  *
  * Conventions
  *   - every function returns 0 on success or a negative UA3_E_* code; ua3reo_last_error() gives
  *     the message of the calling thread's last failure.  (The firmware's functions return void
  *     and report through flags - FPGA_Buffer_underrun, fpga.c:16 - which has no batched analogue.)
  *   - the library owns all device state; the caller owns every host buffer it passes in.
- *   - one host thread per context; all work of a context is ordered on one CUDA stream.
+ *   - one host thread per context.  The DDC kernels of a context are ordered on one CUDA stream; the STM32 stage
+ *     runs one push behind on a second stream and result copies on a third - every call below states what it
+ *     waits for, and ua3reo_sync() waits for everything.
  *   - there is NO CPU fallback: without a usable CUDA device ua3reo_create() fails.
  */
 #ifndef UA3REO_B200_H
