@@ -39,7 +39,7 @@ def test_cw_decoder_live_against_host_built_firmware(pkg):
         pytest.skip("oracle/_ref/fw_cw not built here")
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import gen_golden_cw as g
-    rng = np.random.default_rng()
+    rng = np.random.default_rng(20261018)     # fixed seed: the round-end run must be reproducible
     for _ in range(3):
         words = " ".join("".join(rng.choice(list("ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789"), rng.integers(2, 6))) for _ in range(4))
         audio = g.keyed_audio(words, int(rng.integers(10, 36)), amp=float(rng.uniform(500, 6000)), noise=float(rng.uniform(5, 200)),
