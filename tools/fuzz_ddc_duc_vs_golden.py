@@ -32,7 +32,10 @@ for trial in range(4):
     got = np.concatenate(got, 1)
     pick = rng.choice(n_ch, min(n_ch, 12), replace=False)
     ref = pyoracle.golden_frames(adc, [int(fcw[c]) for c in pick])
-    ok = np.array_equal(got[pick], ref)
+    # the register-transfer model emits frame k part-way through its last 1024 samples, the block-based kernels when all
+    # of them have arrived: with a ragged total the model may be one frame ahead
+    assert 0 <= ref.shape[1] - got.shape[1] <= 1 and got.shape[1] == n // 1024
+    ok = np.array_equal(got[pick], ref[:, :got.shape[1]])
     # DUC on the same context
     rx.duc_enable(8)
     iq = rng.integers(-32768, 32768, (n_ch, 8, 2)).astype(np.int16)
