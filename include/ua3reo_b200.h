@@ -156,12 +156,20 @@ int ua3reo_rx_push_frames(ua3reo_ctx *ctx, const uint8_t *frames_host, size_t n)
 int ua3reo_rx_set(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const ua3reo_rx_settings *settings);
 /* The fields processRxAudio()/FFT_doFFT() read from TRX on EVERY call (mode, AGC/DNR/notch switches, volume, mute,
  * RF gain, squelch threshold, FFT averaging/enable, IQ swap, CW decoder; `Filter_Width > 0`, audio_processor.c:448),
- * applied without what ReinitAudioFilters()/InitNotchFilter()/FFT_Init() do: filter tables, notch coefficients and
- * the ZoomFFT decimator stay as the last ua3reo_rx_set() left them and no filter state is cleared. */
+ * applied without what ReinitAudioFilters()/InitNotchFilter()/InitAGC()/FFT_Init() do: filter tables, notch
+ * coefficients, AGC step sizes and the ZoomFFT decimator stay as the last full setter left them and no filter state
+ * is cleared. */
 int ua3reo_rx_set_live(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const ua3reo_rx_settings *settings);
 /* InitNotchFilter() (audio_filters.c:341-346) alone: recomputes the notch biquad for notch_fc[i] Hz (one per channel
  * of the range); like the firmware it leaves the biquad states as they are. */
 int ua3reo_rx_set_notch(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const uint16_t *notch_fc);
+/* InitAGC() (agc.c:14-19) alone: the AGC step sizes for agc_speed[i] (one per channel of the range, > 0).  Like the
+ * notch corner, TRX.Agc_speed is not read per call: ua3reo_rx_set_live() leaves the step sizes alone. */
+int ua3reo_rx_set_agc_speed(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const uint8_t *agc_speed);
+/* FFT_Init() (fft.c:185-210) alone: ZoomFFT factor fft_zoom[i] (1, 2, 4, 8, 16; one per channel of the range).  As in
+ * the firmware, a zoom above 1 clears the biquad and FIR-decimator states every time it is called, the accumulated
+ * zoom buffer and the averaged spectrum are kept. */
+int ua3reo_rx_fft_init(ua3reo_ctx *ctx, uint32_t first, uint32_t n, const uint8_t *fft_zoom);
 
 /* Results of the last push.  Audio: what processRxAudio() leaves in Processor_AudioBuffer_A/B
  * (audio_processor.c:377-394): per channel and block 384 int32, L/R interleaved.  dst is

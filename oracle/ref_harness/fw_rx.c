@@ -16,8 +16,8 @@
  *   - VFO frequency is held at 0 so that FFT_moveWaterfall() (fft.c:347-351) never shifts the averages
  * params.txt: `key value` lines applied before the init calls, and `at N key value` lines applied when N frames have
  *   been consumed (before that frame's processing) WITHOUT any re-initialisation - what a menu handler writing TRX
- *   does; the pseudo keys `reinit`, `notch_init` and `fft_init` call ReinitAudioFilters(), InitNotchFilter() and
- *   FFT_Init() at that point, as TRX_setMode() / the 1 s tick / the zoom menu do (trx_manager.c:217, stm32f4xx_it.c:395).
+ *   does; the pseudo keys `reinit`, `notch_init`, `agc_init` and `fft_init` call ReinitAudioFilters(), InitNotchFilter(), InitAGC()
+ *   and FFT_Init() at that point, as TRX_setMode() / the 1 s tick / the zoom menu do (trx_manager.c:217, stm32f4xx_it.c:395).
  * audio_out: per block 384 int32 (L,R interleaved; audio_processor.c:377-394) + 3 float (S-meter max, min,
  *            CW decoder Goertzel magnitude of the block or 0) + 384 int16 (USB_AUDIO_rx_buffer_a)
  * fft_out  : per FFT frame 256 float (FFTOutput_mean) + 256 uint16 (waterfall row 0) + float maxValueFFT
@@ -84,6 +84,7 @@ static void fire(const struct event *e)
     if (!strcmp(e->key, "reinit")) ReinitAudioFilters();
     else if (!strcmp(e->key, "notch_init")) InitNotchFilter();
     else if (!strcmp(e->key, "fft_init")) FFT_Init();
+    else if (!strcmp(e->key, "agc_init")) InitAGC();
     else if (!set_param(e->key, e->val)) { fprintf(stderr, "unknown parameter %s\n", e->key); exit(2); }
 }
 

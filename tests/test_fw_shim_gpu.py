@@ -73,6 +73,10 @@ RX_CASES = [
     ("reinit", dict(mode=0, notch=1), ((1000, "mode", 10), (1000, "filter_width", 6000), (1000, "reinit", 0),
                                        (1600, "notch_fc", 2200), (2000, "notch_init", 0),
                                        (2400, "fft_zoom", 2), (2400, "fft_init", 0))),
+    # TRX.Agc_speed only counts from the next InitAGC() (agc.c:14-19); FFT_Init() clears the ZoomFFT filter states even when the
+    # zoom is unchanged (fft.c:189-207)
+    ("agc_init_and_fft_init", dict(mode=0, fft_zoom=2), ((600, "agc_speed", 9), (1200, "agc_init", 0), (1500, "fft_init", 0),
+                                                         (2200, "agc_speed", 1), (2600, "fft_zoom", 4), (2600, "fft_init", 0))),
     # retunes as FFT_printFFT() sees them: rows and averages move sideways (FFT_moveWaterfall, fft.c:458-504)
     ("retune_up_down", dict(mode=0), ((1100, "freq", 3000), (2300, "freq", 1000), (3300, "freq", 1100))),
     ("retune_zoom2_far", dict(mode=0, fft_zoom=2), ((1500, "freq", 20000), (2800, "freq", 2000))),

@@ -90,6 +90,8 @@ def _bind(lib):
         "ua3reo_rx_set": (c.c_int, [vp, u32, u32, vp]),
         "ua3reo_rx_set_live": (c.c_int, [vp, u32, u32, vp]),
         "ua3reo_rx_set_notch": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_rx_set_agc_speed": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_rx_fft_init": (c.c_int, [vp, u32, u32, vp]),
         "ua3reo_rx_push_frames": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_counts": (c.c_int, [vp, c.POINTER(sz), c.POINTER(sz)]),
         "ua3reo_rx_read_audio": (c.c_int, [vp, vp, sz]),
@@ -313,6 +315,22 @@ class Receiver:
             a = np.repeat(a, self.n_channels - first)
         a = np.ascontiguousarray(a)
         self._chk(self.lib.ua3reo_rx_set_notch(self._h, int(first), a.size, a.ctypes.data))
+
+    def rx_set_agc_speed(self, speed, first=0):
+        """InitAGC() alone: one speed (1..) or one per channel from `first`."""
+        a = np.atleast_1d(np.asarray(speed, dtype=np.uint8))
+        if a.size == 1:
+            a = np.repeat(a, self.n_channels - first)
+        a = np.ascontiguousarray(a)
+        self._chk(self.lib.ua3reo_rx_set_agc_speed(self._h, int(first), a.size, a.ctypes.data))
+
+    def rx_fft_init(self, zoom, first=0):
+        """FFT_Init() alone: one zoom factor or one per channel from `first`."""
+        a = np.atleast_1d(np.asarray(zoom, dtype=np.uint8))
+        if a.size == 1:
+            a = np.repeat(a, self.n_channels - first)
+        a = np.ascontiguousarray(a)
+        self._chk(self.lib.ua3reo_rx_fft_init(self._h, int(first), a.size, a.ctypes.data))
 
     def rx_push_frames(self, frames):
         """frames: uint8 [n_channels, n, 8] I/Q frames (stm32_interface byte order) fed straight to the STM32 stage."""

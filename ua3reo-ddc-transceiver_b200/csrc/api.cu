@@ -594,6 +594,7 @@ static int rx_apply_settings(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua
             std::memcpy(np[i].hpf_k, old.hpf_k, sizeof old.hpf_k); std::memcpy(np[i].hpf_v, old.hpf_v, sizeof old.hpf_v);
             std::memcpy(np[i].notch, old.notch, sizeof old.notch);
             np[i].hpf_set = old.hpf_set; np[i].fft_zoom = old.fft_zoom;
+            np[i].agc_step_up = old.agc_step_up; np[i].agc_step_down = old.agc_step_down;   // InitAGC() is not per call (agc.c:14-19)
             np[i].lpf_on = settings[i].filter_width > 0;          // `if (CurrentVFO()->Filter_Width > 0)` is read per block (audio_processor.c:448)
         } else {
             const bool zoom_changed = np[i].fft_zoom != old.fft_zoom;
@@ -604,8 +605,9 @@ static int rx_apply_settings(ua3reo_ctx* c, uint32_t first, uint32_t n, const ua
         c->h_par[first + i] = np[i];
         if (live) {
             const uint16_t fw = c->h_set[first + i].filter_width, hp = c->h_set[first + i].ssb_hpf_pass, nf = c->h_set[first + i].notch_fc;
-            const uint8_t zoom = c->h_set[first + i].fft_zoom;
+            const uint8_t zoom = c->h_set[first + i].fft_zoom, agcs = c->h_set[first + i].agc_speed;
             c->h_set[first + i] = settings[i];
+            c->h_set[first + i].agc_speed = agcs;
             c->h_set[first + i].filter_width = fw; c->h_set[first + i].ssb_hpf_pass = hp; c->h_set[first + i].notch_fc = nf;
             c->h_set[first + i].fft_zoom = zoom;
         } else {
@@ -643,6 +645,57 @@ int ua3reo_rx_set_notch(ua3reo_ctx* c, uint32_t first, uint32_t n, const uint16_
     for (uint32_t i = 0; i < n; ++i) {
         rx_notch_coeffs(notch_fc[i], c->h_par[first + i].notch);
         c->h_set[first + i].notch_fc = notch_fc[i];
+    }
+    UA3_CUDA(cudaMemcpyAsync(c->rx.params + first, c->h_par.data() + first, sizeof(RxParams) * n, cudaMemcpyHostToDevice,
+                             c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+// FFT_Init() (fft.c:185-210) alone: selects the ZoomFFT decimator for TRX.FFT_Zoom and - whenever the zoom is above 1,
+// changed or not - clears the biquad and FIR-decimator states; the accumulation buffer FFTInput_ZOOMFFT and the averages
+// are left as they are.
+int ua3reo_rx_fft_init(ua3reo_ctx* c, uint32_t first, uint32_t n, const uint8_t* fft_zoom) {
+    if (!c || !fft_zoom || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_rx_fft_init: range");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const int rc = rx_allocate(c);
+    if (rc != UA3_OK) return rc;
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
+    std::vector<uint8_t> flags(n, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t z = fft_zoom[i] ? fft_zoom[i] : 1;
+        if (z != 1 && z != 2 && z != 4 && z != 8 && z != 16) return fail(UA3_E_INVAL, "ua3reo_rx_fft_init: zoom must be 1, 2, 4, 8 or 16");
+        flags[i] = z > 1 ? 4 : 0;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t z = fft_zoom[i] ? fft_zoom[i] : 1;
+        c->h_par[first + i].fft_zoom = z;
+        c->h_set[first + i].fft_zoom = z;
+    }
+    UA3_CUDA(cudaMemcpyAsync(c->rx.params + first, c->h_par.data() + first, sizeof(RxParams) * n, cudaMemcpyHostToDevice,
+                             c->stream));
+    UA3_CUDA(cudaMemcpyAsync(c->rx_flags, flags.data(), n, cudaMemcpyHostToDevice, c->stream));
+    int launches = 0;
+    UA3_CUDA(rx_launch_clear(c->rx, c->rx_flags, first, n, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+// InitAGC() (agc.c:14-19) alone: the AGC step sizes for TRX.Agc_speed; the gain state is untouched.  The firmware calls it
+// from the menu / encoder handlers right after changing the speed (encoder.c:140-143, lcd.c:885), not per audio block.
+int ua3reo_rx_set_agc_speed(ua3reo_ctx* c, uint32_t first, uint32_t n, const uint8_t* agc_speed) {
+    if (!c || !agc_speed || first > c->n_ch || n > c->n_ch - first) return fail(UA3_E_INVAL, "ua3reo_rx_set_agc_speed: range");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const int rc = rx_allocate(c);
+    if (rc != UA3_OK) return rc;
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
+    for (uint32_t i = 0; i < n; ++i)
+        if (agc_speed[i] == 0) return fail(UA3_E_INVAL, "ua3reo_rx_set_agc_speed: speed 0 (the firmware would divide by zero)");
+    for (uint32_t i = 0; i < n; ++i) {
+        c->h_par[first + i].agc_step_up = 500.0f / (float)agc_speed[i];
+        c->h_par[first + i].agc_step_down = c->h_par[first + i].agc_step_up / 10.0f;
+        c->h_set[first + i].agc_speed = agc_speed[i];
     }
     UA3_CUDA(cudaMemcpyAsync(c->rx.params + first, c->h_par.data() + first, sizeof(RxParams) * n, cudaMemcpyHostToDevice,
                              c->stream));

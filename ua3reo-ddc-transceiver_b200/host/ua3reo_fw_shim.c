@@ -78,6 +78,7 @@ float ua3reo_shim_cw_magnitude = 0.0f;            /* Goertzel magnitude of the l
 static ua3reo_ctx *rx_ctx;      /* audio: processRxAudio / processTxAudio */
 static ua3reo_ctx *fft_ctx;     /* panorama: FFT_doFFT */
 static uint16_t latched_notch_fc = 1000;
+static uint8_t latched_agc_speed = 3;    /* TRX.Agc_speed as of the last InitAGC() (agc.c:14-19) */
 static uint32_t shim_fft_freq = 0;       /* currentFFTFreq (fft.c:31) */
 static float smeter_seen_max, smeter_seen_min;
 static ua3reo_rx_settings rx_last, fft_last;
@@ -109,7 +110,7 @@ static void gather_rx(ua3reo_rx_settings *s, bool for_fft)
     s->filter_width = (uint16_t)CurrentVFO()->Filter_Width;
     s->ssb_hpf_pass = TRX.SSB_HPF_pass;
     s->agc = TRX.AGC; s->dnr = TRX.DNR;
-    s->agc_speed = TRX.Agc_speed ? TRX.Agc_speed : 1;    /* the menu keeps it in 1..; 0 would divide by zero in InitAGC (agc.c:17) and the library rejects it */
+    s->agc_speed = latched_agc_speed;
     s->notch = TRX.NotchFilter; s->notch_fc = latched_notch_fc;
     s->volume = TRX.Volume; s->mute = TRX.Mute; s->rf_gain = TRX.RF_Gain;
     s->fm_sql_threshold = TRX.FM_SQL_threshold;
@@ -180,7 +181,13 @@ void ReinitAudioFilters(void)
     apply_tx(true);
 }
 
-void InitAGC(void) {}                    /* agc.c:14-19: the step sizes follow TRX.Agc_speed through the settings block */
+void InitAGC(void)                       /* agc.c:14-19: step sizes from TRX.Agc_speed, latched here like the firmware's statics */
+{
+    latched_agc_speed = TRX.Agc_speed ? TRX.Agc_speed : 1;   /* the menus keep it in 1..4; 0 would divide by zero and the library rejects it */
+    if (!rx_ctx) return;
+    CHECK(ua3reo_rx_set_agc_speed(rx_ctx, 0, 1, &latched_agc_speed));
+    rx_last.agc_speed = latched_agc_speed;
+}
 void InitNoiseReduction(void) {}         /* noise_reduction.c:18-23: state is created zeroed with the context */
 
 void InitAudioFilters(void)              /* audio_filters.c:124-139: lattice/biquad instances, then InitNotchFilter() */
@@ -297,10 +304,13 @@ void processTxAudio(void)
 }
 
 /* ---- panorama: FFT_Init / FFT_doFFT numeric half (fft.c:185-328) ---- */
-void FFT_Init(void)
+void FFT_Init(void)                      /* fft.c:185-210 */
 {
     ensure_contexts();
-    apply_fft(true);                      /* selects the ZoomFFT decimator and clears its state (fft.c:187-209) */
+    if (!fft_last_valid) apply_fft(true);                        /* first call: the whole settings block */
+    const uint8_t zoom = TRX.FFT_Zoom ? TRX.FFT_Zoom : 1;
+    CHECK(ua3reo_rx_fft_init(fft_ctx, 0, 1, &zoom));              /* decimator selected, biquad/FIR states cleared when zoom > 1 */
+    fft_last.fft_zoom = zoom;
 }
 
 void FFT_doFFT(void)
