@@ -16,7 +16,7 @@
  *   - VFO frequency is held at 0 so that FFT_moveWaterfall() (fft.c:347-351) never shifts the averages
  * params.txt: `key value` lines applied before the init calls, and `at N key value` lines applied when N frames have
  *   been consumed (before that frame's processing) WITHOUT any re-initialisation - what a menu handler writing TRX
- *   does; the pseudo keys `reinit`, `notch_init`, `agc_init` and `fft_init` call ReinitAudioFilters(), InitNotchFilter(), InitAGC()
+ *   does; the pseudo keys `reinit`, `notch_init`, `agc_init`, `fft_init` (and `smeter_reset`, which zeroes the S-meter extremes) call ReinitAudioFilters(), InitNotchFilter(), InitAGC()
  *   and FFT_Init() at that point, as TRX_setMode() / the 1 s tick / the zoom menu do (trx_manager.c:217, stm32f4xx_it.c:395).
  * audio_out: per block 384 int32 (L,R interleaved; audio_processor.c:377-394) + 3 float (S-meter max, min,
  *            CW decoder Goertzel magnitude of the block or 0) + 384 int16 (USB_AUDIO_rx_buffer_a)
@@ -85,6 +85,10 @@ static void fire(const struct event *e)
     else if (!strcmp(e->key, "notch_init")) InitNotchFilter();
     else if (!strcmp(e->key, "fft_init")) FFT_Init();
     else if (!strcmp(e->key, "agc_init")) InitAGC();
+    else if (!strcmp(e->key, "smeter_reset")) {       /* the housekeeping tick after it has shown the S-meter (stm32f4xx_it.c:398-409) */
+        Processor_RX_Audio_Samples_MAX_value = 0;
+        Processor_RX_Audio_Samples_MIN_value = 0;
+    }
     else if (!set_param(e->key, e->val)) { fprintf(stderr, "unknown parameter %s\n", e->key); exit(2); }
 }
 

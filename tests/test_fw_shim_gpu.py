@@ -77,6 +77,8 @@ RX_CASES = [
     # zoom is unchanged (fft.c:189-207)
     ("agc_init_and_fft_init", dict(mode=0, fft_zoom=2), ((600, "agc_speed", 9), (1200, "agc_init", 0), (1500, "fft_init", 0),
                                                          (2200, "agc_speed", 1), (2600, "fft_zoom", 4), (2600, "fft_init", 0))),
+    # the housekeeping tick zeroes the S-meter extremes after showing them (stm32f4xx_it.c:398-409)
+    ("smeter_reset", dict(mode=1), ((800, "smeter_reset", 0), (2000, "smeter_reset", 0), (2001, "rf_gain", 20))),
     # retunes as FFT_printFFT() sees them: rows and averages move sideways (FFT_moveWaterfall, fft.c:458-504)
     ("retune_up_down", dict(mode=0), ((1100, "freq", 3000), (2300, "freq", 1000), (3300, "freq", 1100))),
     ("retune_zoom2_far", dict(mode=0, fft_zoom=2), ((1500, "freq", 20000), (2800, "freq", 2000))),

@@ -35,7 +35,7 @@ for run in range(n_runs):
     events = []
     for at in sorted(rng.integers(200, 3600, 10).tolist()):
         k = rng.choice(["volume", "agc", "mode", "notch", "rf_gain", "dnr", "mute", "fft_averaging", "filter_width", "notch_fc",
-                        "reinit", "notch_init", "fft_zoom+init", "freq", "agc_speed", "agc_speed+init", "fm_sql_threshold"])
+                        "reinit", "notch_init", "fft_zoom+init", "freq", "agc_speed", "agc_speed+init", "fm_sql_threshold", "smeter_reset"])
         if k == "volume": events.append((at, k, int(rng.integers(1, 101))))
         elif k in ("agc", "notch", "dnr", "mute"): events.append((at, k, int(rng.integers(2))))
         elif k == "mode": events.append((at, k, int(rng.choice([0, 1, 3, 4, 8, 10]))))
@@ -47,6 +47,7 @@ for run in range(n_runs):
         elif k == "filter_width": events.append((at, k, int(rng.choice(widths))))
         elif k == "notch_fc": events.append((at, k, int(rng.integers(200, 3500))))
         elif k == "reinit": events.append((at, "reinit", 0))
+        elif k == "smeter_reset": events.append((at, "smeter_reset", 0))
         elif k == "notch_init": events.append((at, "notch_init", 0))
         elif k == "fft_zoom+init": events += [(at, "fft_zoom", int(rng.choice([1, 2, 4, 8]))), (at, "fft_init", 0)]
         # retunes stay below 256 waterfall pixels ((diff / 187) * zoom): beyond that FFT_moveWaterfall reads past FFTOutput_mean
