@@ -58,6 +58,17 @@ int ua3reo_destroy(ua3reo_ctx *ctx);
 /* reset_n of the RX chain (UA3REO.bdf RX_N net): clears NCO phases and every filter state. */
 int ua3reo_reset(ua3reo_ctx *ctx);
 
+/* Clocking class of the I/Q frame.  On the board the four filter modules share reset = RX_N / clk_enable = RX
+ * (UA3REO.bdf) and run on three PLL clocks (MAIN_PLL.v:105-116), so the instant the MCU raises RX decides (a) which
+ * of the compensator's two delay lines the first CIC output enters (rx_ciccomp.vhd:339-361), (b) how many 48 kHz
+ * samples VOICE_I trails the Hilbert sum (serial MAC + output register, rx_hilb.vhd:907-947) and (c) whether the bus
+ * read sees data_delay.v's output before or after its clock edge.  Running the reference's VHDL over all 1024 release
+ * instants (tools/hdl_clocking_survey.py) gives six classes; the default is the most frequent one:
+ *   align_b = 1 (30 of 32 instants; 0 for the other two), d_i = 3 (2 for 1 of 32), d_q = 129 (130 for a late bus read).
+ * Applies to all channels; call before the first push or after ua3reo_reset(). */
+int ua3reo_ddc_set_clocking(ua3reo_ctx *ctx, int align_b, int d_i, int d_q);
+int ua3reo_ddc_get_clocking(const ua3reo_ctx *ctx, int *align_b, int *d_i, int *d_q);
+
 uint32_t ua3reo_n_channels(const ua3reo_ctx *ctx);
 uint32_t ua3reo_max_block_samples(const ua3reo_ctx *ctx);
 
@@ -80,7 +91,16 @@ int ua3reo_set_frequency(ua3reo_ctx *ctx, uint32_t channel, uint32_t freq_hz);
  *   ua3reo_ddc_push_device : adc already in device memory of the context's device
  * Both are asynchronous with respect to the host; ua3reo_sync() or a read waits.  A host buffer in pinned
  * memory must stay unchanged until then (whole-block host pushes are copied on a separate stream so that
- * the copy of block k+1 overlaps the kernels of block k). */
+ * the copy of block k+1 overlaps the kernels of block k).
+ * DEVICE PUSH CONTRACT: a device push of whole 1024-sample frames from a 16-byte aligned pointer is consumed IN PLACE
+ * (zero copy) by kernels on the context's stream (ua3reo_stream, created cudaStreamNonBlocking: it does NOT order
+ * itself after the legacy default stream or any other stream).  The caller must therefore
+ *   (1) make the context's stream wait for whatever produces adc_dev (cudaStreamWaitEvent on ua3reo_stream) before
+ *       the call, and
+ *   (2) leave the buffer unmodified and allocated until the push has completed (an event recorded on
+ *       ua3reo_stream after the call, or ua3reo_sync).
+ * The Python binding's Receiver.push() does both for torch tensors (wait_stream + record_stream + a kept reference),
+ * and sharding.AdcBroadcaster does both around its NCCL broadcast. */
 int ua3reo_ddc_push(ua3reo_ctx *ctx, const int16_t *adc_host, size_t n, size_t *frames_out);
 int ua3reo_ddc_push_device(ua3reo_ctx *ctx, const int16_t *adc_dev, size_t n, size_t *frames_out);
 

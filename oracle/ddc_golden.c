@@ -86,10 +86,12 @@ int ua3g_rx_cic_clock(ua3g_rx_cic *c, int32_t x)
  * and the 56-bit accumulator (:589-612) are all exact, so the sum is computed directly in int64.
  * Phase-0 delay line shifts on count 0, phase-1 on count 16 (:339-361): the sample taken into
  * phase-1 is the older one of each pair.
- * [convention] the module free-runs on its own PLL clock (UA3REO.bdf, MAIN_PLL c0), so which CIC
- * output falls into which branch is set by reset timing the source does not define.  We define:
- * even-indexed CIC outputs u[2k] -> phase-1 pipeline, odd-indexed u[2k+1] -> phase-0 pipeline,
- * one output per pair, computed when the odd sample arrives:  y[k] = sum_j h[j] * u[2k+1-j].
+ * Which CIC output falls into which branch depends on when RX is raised relative to the compensator clock
+ * (see "Clocking" at ua3g_ddc_init_clocking).  This function implements alignment A when n_in starts at 0:
+ * even-indexed CIC outputs u[2k] -> phase-1 pipeline, odd-indexed u[2k+1] -> phase-0 pipeline, one output per
+ * pair, computed when the odd sample arrives:  y[k] = sum_j h[j] * u[2k+1-j];  with n_in starting at 1 it is
+ * alignment B, y[k] = sum_j h[j] * u[2k-j].  Either way it reproduces rx_ciccomp.vhd sample for sample
+ * (tests/test_hdl_pin.py).
  * Output rounding (:616): convergent, on the low 31 bits, wrap not saturate.
  * ------------------------------------------------------------------------------------------ */
 void ua3g_rx_ciccomp_reset(ua3g_rx_ciccomp *c) { memset(c, 0, sizeof *c); }
@@ -119,7 +121,8 @@ int ua3g_rx_ciccomp_push(ua3g_rx_ciccomp *c, int16_t u, int16_t *y)
  *    mul_temp = x*c (s32, En30); product = (mul_temp + mul_temp[1]) >> 1  (convergent, En29)
  * accumulated in a 40-bit wrapping register (:907-931); output (:935) convergent >>14 on the
  * low 30 bits, wrap.  delay_pipeline(0) is the newest sample and pairs with coeff1 (:375-640).
- * [convention] the 2-sample latency of the serial MAC/output register is modelled as zero.
+ * The 2-sample latency of the serial MAC + output register (measured on the VHDL, tests/test_hdl_pin.py) is not
+ * in this function; the frame assembly in ua3g_ddc_push applies it (d_i).
  * ------------------------------------------------------------------------------------------ */
 void ua3g_rx_hilb_reset(ua3g_rx_hilb *h) { memset(h, 0, sizeof *h); }
 
@@ -181,16 +184,42 @@ uint32_t ua3g_phrase_from_frequency(uint32_t freq, int *iq_swap)
 }
 
 /* ------------------------------------------------------------------------------------------
- * Whole RX DDC, one channel.  Netlist from UA3REO.bdf: MIXER_I.datab <- NCO sin, MIXER_Q.datab
- * <- NCO cos; RX_CICCOMP_I/Q.filter_out -> SPEC_I/Q; RX_VOICE_HILBERT_I(comp I) -> VOICE_I;
- * RX_VOICE_DELAY_Q(comp Q) -> VOICE_Q.
- * [convention] each module downstream of rx_cic consumes every new upstream output exactly once,
- * in order (their free-running clocks are integer multiples of the upstream sample rate).
+ * Whole RX DDC, one channel.  Netlist from UA3REO.bdf (extracted by tools/bdf_netlist.py, checked in
+ * tests/test_hdl_pin.py): MIXER_I.datab <- NCO sin, MIXER_Q.datab <- NCO cos; RX_CICCOMP_I/Q.filter_out ->
+ * SPEC_I/Q; RX_VOICE_HILBERT_I(comp I) -> VOICE_I; RX_VOICE_DELAY_Q(comp Q) -> VOICE_Q.
+ *
+ * Clocking.  All four RX filter modules share reset = RX_N and clk_enable = RX, their clocks are MAIN_PLL
+ * outputs of clk_sys with zero phase shift (c0 = /32 compensator, c1 = /4 Hilbert, c2 = /1024 Q delay and MCU
+ * interrupt), so ONE free parameter decides how the four words of a frame line up: T_rx, the instant the MCU
+ * raises RX relative to the PLL clocks (plus tau, how long after the 48 kHz edge the MCU reads the words).
+ * tools/hdl_clocking_survey.py sweeps all 1024 values of T_rx through the reference's own VHDL; the frame is
+ * always  SPEC = Y[k], VOICE_I = H[k - d_i], VOICE_Q = Y_Q[k - d_q]  with Y the compensator output for one of
+ * the two polyphase alignments, H the Hilbert sum of Y_I with zero latency, and
+ *     alignment B for 30 of 32 values of T_rx mod 32 (A for the other two),
+ *     d_i = 3 for 31 of 32 (2 otherwise: the serial MAC + output register cost two samples, sampling a third),
+ *     d_q = 129 when the MCU reads within about 2 us of the edge (tau <= 100 clk_sys ticks: 85 %), else 130.
+ * The class is a parameter of the model; the default is the board's most frequent one, (B, 3, 129).  The
+ * round-1 model used (A, 0, 130), which no T_rx produces: it skewed VOICE_I against VOICE_Q by 2.5 samples
+ * where the board has 1.5 (or 0.5).
+ * [convention] ideal PLL: derived clock edges coincide with clk_sys edges and a register clocked at the same
+ * instant as its producer sees the producer's previous value.
  * ------------------------------------------------------------------------------------------ */
-void ua3g_ddc_init(ua3g_ddc *d, uint32_t fcw22)
+int ua3g_ddc_init_clocking(ua3g_ddc *d, uint32_t fcw22, int align_b, int d_i, int d_q)
 {
     memset(d, 0, sizeof *d);
     d->fcw = fcw22 & 0x3FFFFF;
+    if ((align_b != 0 && align_b != 1) || d_i < 0 || d_i > UA3G_MAX_DI || d_q < 1 || d_q > UA3G_QDELAY) return -1;
+    d->clk.align_b = align_b;
+    d->clk.d_i = d_i;
+    d->clk.d_q = d_q;
+    /* alignment B: the first CIC output enters input_pipeline_phase0, as if one (zero) output had gone before */
+    d->comp_i.n_in = d->comp_q.n_in = (uint32_t)align_b;
+    return 0;
+}
+
+void ua3g_ddc_init(ua3g_ddc *d, uint32_t fcw22)
+{
+    ua3g_ddc_init_clocking(d, fcw22, UA3G_CLOCKING_DEFAULT_ALIGN_B, UA3G_CLOCKING_DEFAULT_DI, UA3G_CLOCKING_DEFAULT_DQ);
 }
 
 size_t ua3g_ddc_push(ua3g_ddc *d, const int16_t *adc, size_t n, uint8_t *frames, size_t max_frames,
@@ -215,8 +244,12 @@ size_t ua3g_ddc_push(ua3g_ddc *d, const int16_t *adc, size_t n, uint8_t *frames,
             const int oi = ua3g_rx_ciccomp_push(&d->comp_i, d->cic_i.outreg, &yi);
             const int oq = ua3g_rx_ciccomp_push(&d->comp_q, d->cic_q.outreg, &yq);
             if (oi && oq) {
-                const int16_t vi = ua3g_rx_hilb_push(&d->hilb, yi);
-                const int16_t vq = ua3g_delay_push(&d->qdelay, yq);
+                /* VOICE_I trails the zero-latency Hilbert sum by d_i samples, VOICE_Q is SPEC_Q d_q samples ago */
+                memmove(&d->vi_fifo[1], &d->vi_fifo[0], UA3G_MAX_DI * sizeof(int16_t));
+                d->vi_fifo[0] = ua3g_rx_hilb_push(&d->hilb, yi);
+                const int16_t vi = d->vi_fifo[d->clk.d_i];
+                const int16_t vq = d->qdelay.dl[d->clk.d_q - 1];
+                ua3g_delay_push(&d->qdelay, yq);
                 if (frames && nf < max_frames) ua3g_frame_pack(frames + 8 * nf, yq, yi, vq, vi);
                 nf++;
                 d->n_frames++;

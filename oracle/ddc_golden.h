@@ -13,13 +13,19 @@
  *   FPGA/tx_ciccomp.vhd:199-483, FPGA/tx_cic.vhd:153-420, FPGA/tx_mixer.v:64-71,
  *   FPGA/tx_summator.v:74-80, FPGA/DAC_corrector.v:15-21
  *
- * PARITY PINNING: the reference ships no testbench, golden vector or known-answer test for this
- * path and no HDL simulator exists in the build image, so the model is pinned only by (a) every
- * coefficient/ROM constant, read mechanically from the HDL by tools/gen_tables.py and checksummed,
- * and (b) analytic identities (DC gain, impulse responses, rate identities) in tests/.  Items the
- * HDL leaves undetermined are CONVENTIONS of this model, marked [convention] in ddc_golden.c:
- * NCO start phase/latency and 28->14 bit rounding (encrypted Altera IP), which CIC output lands
- * in which compensator polyphase branch (free-running clocks), serial-MAC latencies (modelled as 0).
+ * PARITY PINNING: the reference ships no testbench, golden vector or known-answer test for this path, and no HDL
+ * simulator exists in the build image.  The model is pinned by EXECUTING THE REFERENCE'S VHDL: tools/vhdl_eval.py
+ * parses rx_cic / rx_ciccomp / rx_hilb / tx_cic / tx_ciccomp.vhd where they lie and evaluates them cycle by cycle
+ * (a Python interpreter and a C translation built into oracle/_ref/libua3_hdl.so, run against each other);
+ * tests/test_hdl_pin.py requires every filter function here to reproduce the HDL's output register edge for edge
+ * (rx_cic, tx_cic) or sample for sample (the serial-MAC filters), requires the whole receive chain - four clock
+ * domains composed as UA3REO.bdf wires them (tools/bdf_netlist.py) - to reproduce the HDL's frame for every clocking
+ * class, and compares both with the committed HDL vectors tests/golden/hdl_cases.npz.  Beyond that: every
+ * coefficient/ROM constant is read mechanically from the HDL by tools/gen_tables.py and checksummed, and tests/ hold
+ * the analytic identities (DC gain, impulse responses, rate identities).
+ * What stays a CONVENTION, marked [convention] in ddc_golden.c: the NCO start phase/latency and its 28 -> 14 bit
+ * rounding (encrypted Altera IP, no source to execute), the ideal-PLL edge alignment, and the Verilog one-liners
+ * (mixer = signed lpm_mult, nco_shift, rx_mixer_shift, data_delay, tx_summator, DAC_corrector), which are restated.
  */
 #ifndef UA3_DDC_GOLDEN_H
 #define UA3_DDC_GOLDEN_H
@@ -52,6 +58,18 @@ typedef struct {
 typedef struct { int16_t dl[UA3G_HILB_TAPS]; } ua3g_rx_hilb;     /* delay_pipeline rx_hilb.vhd:375-385 */
 typedef struct { int16_t dl[UA3G_QDELAY]; } ua3g_delay;          /* data_delay.v:9-30 */
 
+/* Frame clocking class (see "clocking" in ddc_golden.c): which compensator polyphase branch the first CIC output
+ * enters, how many 48 kHz samples VOICE_I trails the Hilbert sum, how many samples VOICE_Q trails SPEC_Q. */
+typedef struct {
+    int align_b;         /* 0: CIC outputs 0,2,4.. -> input_pipeline_phase1 ("A"); 1: -> input_pipeline_phase0 ("B") */
+    int d_i;             /* 0..3: VOICE_I[n] = hilbert(SPEC_I)[n - d_i] */
+    int d_q;             /* 1..130: VOICE_Q[n] = SPEC_Q[n - d_q] */
+} ua3g_clocking;
+#define UA3G_CLOCKING_DEFAULT_ALIGN_B 1
+#define UA3G_CLOCKING_DEFAULT_DI 3
+#define UA3G_CLOCKING_DEFAULT_DQ 129
+#define UA3G_MAX_DI 3
+
 typedef struct {
     uint32_t fcw;        /* 22-bit tuning word (stm32_interface.v:159-169) */
     uint32_t phase;      /* 22-bit accumulator */
@@ -61,6 +79,8 @@ typedef struct {
     ua3g_delay qdelay;
     uint64_t n_adc;      /* ADC samples consumed */
     uint64_t n_frames;   /* 48 kHz frames produced */
+    ua3g_clocking clk;
+    int16_t vi_fifo[UA3G_MAX_DI + 1];   /* Hilbert outputs waiting d_i samples */
 } ua3g_ddc;
 
 /* NCO: sin14/cos14 for a 22-bit phase (A.1). */
@@ -82,8 +102,10 @@ int16_t ua3g_rx_hilb_push(ua3g_rx_hilb *h, int16_t y);
 void ua3g_delay_reset(ua3g_delay *d);
 int16_t ua3g_delay_push(ua3g_delay *d, int16_t q);
 
-/* whole RX DDC for one channel */
+/* whole RX DDC for one channel; clocking class = the board's most frequent one (B, 3, 129) */
 void ua3g_ddc_init(ua3g_ddc *d, uint32_t fcw22);
+/* same with an explicit clocking class; returns -1 when a field is out of range */
+int ua3g_ddc_init_clocking(ua3g_ddc *d, uint32_t fcw22, int align_b, int d_i, int d_q);
 /* Feeds n ADC samples (12-bit two's complement, sign-extended int16). Writes produced 8-byte
  * frames (stm32_interface order: SPEC_Q hi,lo, SPEC_I hi,lo, VOICE_Q hi,lo, VOICE_I hi,lo) to
  * frames (capacity max_frames) and returns how many were produced.  If cic_i/cic_q are non-NULL

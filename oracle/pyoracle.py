@@ -31,6 +31,8 @@ def lib():
         L.ua3g_ddc_push.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]
         L.ua3g_ddc_init.argtypes = [ctypes.c_void_p, ctypes.c_uint32]
+        L.ua3g_ddc_init_clocking.restype = ctypes.c_int
+        L.ua3g_ddc_init_clocking.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.ua3g_phrase_from_frequency.restype = ctypes.c_uint32
         L.ua3g_phrase_from_frequency.argtypes = [ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
         L.ua3g_nco.argtypes = [ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
@@ -52,9 +54,13 @@ def lib():
 class GoldenDDC:
     """One channel of the register-transfer golden DDC (ddc_golden.c); state persists across push()."""
 
-    def __init__(self, fcw):
+    def __init__(self, fcw, clocking=None):
+        """clocking: None = the model's default class (B, 3, 129), else (align_b, d_i, d_q)"""
         self._st = ctypes.create_string_buffer(DDC_STATE_BYTES)
-        lib().ua3g_ddc_init(self._st, int(fcw) & 0x3FFFFF)
+        if clocking is None:
+            lib().ua3g_ddc_init(self._st, int(fcw) & 0x3FFFFF)
+        elif lib().ua3g_ddc_init_clocking(self._st, int(fcw) & 0x3FFFFF, *[int(v) for v in clocking]) != 0:
+            raise ValueError("bad clocking class %r" % (clocking,))
 
     def push(self, adc, want_cic=False):
         adc = np.ascontiguousarray(adc, dtype=np.int16)
@@ -71,12 +77,34 @@ class GoldenDDC:
         return frames[:nf].copy()
 
 
-def golden_frames(adc, fcws):
+def golden_frames(adc, fcws, clocking=None):
     """uint8 [n_ch, n_frames, 8] for a list of tuning words over one ADC stream."""
     out = []
     for w in fcws:
-        out.append(GoldenDDC(w).push(adc))
+        out.append(GoldenDDC(w, clocking).push(adc))
     return np.stack(out)
+
+
+def golden_mixer(adc, fcw):
+    """(x_i, x_q): the s23 words RX_CIC_I/Q.filter_in see for every ADC sample (golden NCO + mixer conventions)"""
+    L = lib()
+    adc = np.asarray(adc, np.int64)
+    n = adc.size
+    phase = (np.arange(n, dtype=np.int64) * int(fcw)) & 0x3FFFFF
+    uniq, inv = np.unique(phase, return_inverse=True)
+    s14 = np.zeros(uniq.size, np.int64)
+    c14 = np.zeros(uniq.size, np.int64)
+    s = ctypes.c_int32(0)
+    c = ctypes.c_int32(0)
+    for i, ph in enumerate(uniq):
+        L.ua3g_nco(int(ph), ctypes.byref(s), ctypes.byref(c))
+        s14[i], c14[i] = s.value, c.value
+
+    def mix(nco14):
+        p = adc * (nco14[inv] >> 2)
+        p &= 0x7FFFFF
+        return np.where(p >> 22, p - (1 << 23), p)
+    return mix(s14), mix(c14)
 
 
 def synth_adc(n, seed=20261018, tones=8, noise_lsb=8.0, level_dbfs=-6.0):

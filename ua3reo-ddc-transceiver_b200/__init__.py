@@ -74,6 +74,8 @@ def _bind(lib):
         "ua3reo_create": (c.c_int, [c.c_int, u32, u32, c.POINTER(vp)]),
         "ua3reo_destroy": (c.c_int, [vp]),
         "ua3reo_reset": (c.c_int, [vp]),
+        "ua3reo_ddc_set_clocking": (c.c_int, [vp, c.c_int, c.c_int, c.c_int]),
+        "ua3reo_ddc_get_clocking": (c.c_int, [vp, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
         "ua3reo_n_channels": (u32, [vp]),
         "ua3reo_max_block_samples": (u32, [vp]),
         "ua3reo_set_fcw": (c.c_int, [vp, u32, u32, vp]),
@@ -234,6 +236,15 @@ class Receiver:
     def reset(self):
         self._chk(self.lib.ua3reo_reset(self._h))
 
+    def set_clocking(self, align_b=1, d_i=3, d_q=129):
+        """Clocking class of the I/Q frame (include/ua3reo_b200.h: ua3reo_ddc_set_clocking); before the first push."""
+        self._chk(self.lib.ua3reo_ddc_set_clocking(self._h, int(align_b), int(d_i), int(d_q)))
+
+    def get_clocking(self):
+        a, i, q = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._chk(self.lib.ua3reo_ddc_get_clocking(self._h, ctypes.byref(a), ctypes.byref(i), ctypes.byref(q)))
+        return a.value, i.value, q.value
+
     def set_fcw(self, fcw, first=0):
         a = np.ascontiguousarray(fcw, dtype=np.uint32)
         self._chk(self.lib.ua3reo_set_fcw(self._h, int(first), a.size, a.ctypes.data))
@@ -256,6 +267,14 @@ class Receiver:
         else:  # torch tensor
             if adc.is_cuda:
                 assert adc.dtype.itemsize == 2 and adc.is_contiguous()
+                # The library consumes whole-block device pushes IN PLACE on its own non-blocking stream: order that
+                # stream after the tensor's producer (torch's current stream), tell the caching allocator that the
+                # library stream uses the memory, and keep the tensor alive until the next push has been issued.
+                import torch
+                lib_stream = torch.cuda.ExternalStream(self.stream(), device=adc.device)
+                lib_stream.wait_stream(torch.cuda.current_stream(adc.device))
+                adc.record_stream(lib_stream)
+                self._keep_dev = (getattr(self, "_keep_dev", (None, None))[1], adc)   # this push and the one before
                 self._chk(self.lib.ua3reo_ddc_push_device(self._h, adc.data_ptr(), adc.numel(), ctypes.byref(n)))
             else:
                 assert adc.dtype.itemsize == 2 and adc.is_contiguous()

@@ -265,6 +265,23 @@ int ua3reo_reset(ua3reo_ctx* c) {
     return UA3_OK;
 }
 
+int ua3reo_ddc_set_clocking(ua3reo_ctx* c, int align_b, int d_i, int d_q) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    if ((align_b != 0 && align_b != 1) || d_i < 0 || d_i > kMaxDI || d_q < 1 || d_q > kYQHalo)
+        return fail(UA3_E_INVAL, "ua3reo_ddc_set_clocking: align_b in {0,1}, d_i in 0..3, d_q in 1..130");
+    if (c->pushed) return fail(UA3_E_STATE, "ua3reo_ddc_set_clocking: only before the first push or after ua3reo_reset()");
+    c->b.align_b = align_b; c->b.d_i = d_i; c->b.d_q = d_q;
+    return UA3_OK;
+}
+
+int ua3reo_ddc_get_clocking(const ua3reo_ctx* c, int* align_b, int* d_i, int* d_q) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    if (align_b) *align_b = c->b.align_b;
+    if (d_i) *d_i = c->b.d_i;
+    if (d_q) *d_q = c->b.d_q;
+    return UA3_OK;
+}
+
 uint32_t ua3reo_n_channels(const ua3reo_ctx* c) { return c ? c->n_ch : 0; }
 uint32_t ua3reo_max_block_samples(const ua3reo_ctx* c) { return c ? c->max_block : 0; }
 uint64_t ua3reo_launch_count(const ua3reo_ctx* c) { return c ? c->launches : 0; }

@@ -244,7 +244,7 @@ ddc_front_bt_kernel(const int16_t* __restrict__ adc, const int32_t* __restrict__
 
 // ------------------------------------------------------------------------------------------------
 // cic combs + compensator FIR, fused: CTA = (channel, tile of 128 frames).
-//   stage  : the tile's chunk records (256 chunks + 68 halo, both rails, 80 B each = 25.9 KB) arrive in shared memory
+//   stage  : the tile's chunk records (256 chunks + 69 halo, both rails, 80 B each = 26 KB) arrive in shared memory
 //            with ONE TMA bulk copy, in the order the front kernel wrote them (no transposition, no staging code).
 //   combs  : run-based.  With S_m = A512 S_{m-1} + L_m and z_m = (S_m)[stage 5] the five combs are the 5th backward
 //            difference of z, which annihilates the (degree <= 4 polynomial) response to whatever state preceded a run.
@@ -270,7 +270,7 @@ static_assert((kCcRecs * kLRec * 8) % 16 == 0, "TMA bulk size");
 
 __global__ void __launch_bounds__(kCcThreads)
 ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_t n_frames, int16_t* __restrict__ YI,
-                   uint32_t yi_stride, int16_t* __restrict__ YQ, uint32_t yq_stride) {
+                   uint32_t yi_stride, int16_t* __restrict__ YQ, uint32_t yq_stride, uint32_t align_b) {
     __shared__ __align__(128) uint64_t s_rec[kCcRecs * kLRec];       // 324 x 10 x 8 B, record-major as in global memory
     __shared__ __align__(16) int32_t s_u[2][kCcUPitch];
     __shared__ __align__(8) uint64_t s_bar;
@@ -279,7 +279,7 @@ ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_
     const uint32_t k0 = blockIdx.y * kCcFrames;                      // first frame of the tile
     const uint32_t nk = min((uint32_t)kCcFrames, n_frames - k0);
     const uint32_t n_rec = 2 * nk + kLHalo;
-    // record index (array, halo included) of the tile's first staged record: chunk 2*k0 - 68 -> array index 2*k0
+    // record index (array, halo included) of the tile's first staged record: chunk 2*k0 - 69 -> array index 2*k0
     const uint64_t* src = L + (size_t)ch * l_ch_stride + (size_t)(2 * k0) * kLRec;
 #if !defined(UA3_HOST_EMU)
     if (tid == 0) {
@@ -296,7 +296,10 @@ ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_
 #if !defined(UA3_HOST_EMU)
     mbar_wait(&s_bar, 0);
 #endif
-    // ---- combs: CIC outputs u'[c] for chunks c = 2*k0 - 64 .. 2*k0 + 2*nk - 1  ->  s_u[rail][0 .. 64 + 2*nk) ----
+    // ---- combs: CIC outputs u'[c] for chunks c = 2*k0 - 65 .. 2*k0 + 2*nk - 1.  The 65-tap window of frame k ends at
+    // u'[2k] in alignment A and at u'[2k - 1] in alignment B (rx_ciccomp.vhd:339-361: which of the two delay lines a
+    // CIC output enters); the outputs are stored so that the window is s_u[rail][2k .. 2k + 64] either way: output m
+    // goes to s_u[m - 1 + align_b], and alignment A never needs m = 0. ----
     const uint32_t n_out = 2 * nk + kUHalo;
     const uint32_t n_runs = (n_out + kCcRun - 1) / kCcRun;
     if (tid < 2 * n_runs) {
@@ -319,8 +322,10 @@ ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_
             t = y - d2; d2 = y; y = t;
             t = y - d3; d3 = y; y = t;
             t = y - d4; d4 = y; y = t;
-            if (j >= (uint32_t)kCcWarm)                              // output_typeconvert <= section_out10(59 DOWNTO 44)
-                s_u[rail][m0 + j - kCcWarm] = (int32_t)(int16_t)(uint16_t)(y >> 44);
+            if (j >= (uint32_t)kCcWarm) {                            // output_typeconvert <= section_out10(59 DOWNTO 44)
+                const uint32_t pos = m0 + j - kCcWarm + align_b;     // = m + align_b; stored at pos - 1
+                if (pos) s_u[rail][pos - 1] = (int32_t)(int16_t)(uint16_t)(y >> 44);
+            }
         }
     }
     __syncthreads();
@@ -378,16 +383,17 @@ constexpr int kHbWin = 528;                           // widened window: 511 sam
 __global__ void __launch_bounds__(kHbThreads)
 ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_t* __restrict__ YQ, uint32_t yq_stride,
                 uint32_t n_frames, uint64_t* __restrict__ frames, uint32_t frame_ch_stride, uint32_t ring_start,
-                uint32_t ring_mask) {
-    __shared__ __align__(16) int32_t s_y[kHbWin];  // window: s_y[i] = yI[k0 - 255 + i], zero padded
+                uint32_t ring_mask, uint32_t d_i, uint32_t d_q) {
+    __shared__ __align__(16) int32_t s_y[kHbWin];  // window: s_y[i] = yI[k0 - d_i - 255 + i], zero padded
     __shared__ uint32_t s_b0[18], s_b1[18];        // bit planes of the window, 32 samples per word
     const uint32_t ch = blockIdx.x;
     const uint32_t k0 = blockIdx.y * kHbFrames;
     const uint32_t nk = min((uint32_t)kHbFrames, n_frames - k0);
     const uint32_t tid = threadIdx.x;
-    const int16_t* src = YI + (size_t)ch * yi_stride + k0;
+    // VOICE_I of frame k is the Hilbert sum d_i samples back (serial MAC + output register, rx_hilb.vhd:907-947)
+    const int16_t* src = YI + (size_t)ch * yi_stride + k0 + (kMaxDI - d_i);
     for (uint32_t i = tid; i < 512; i += kHbThreads) {     // every warp: 32 consecutive samples -> one word per plane
-        const int32_t v = (i < nk + kYIHalo) ? (int32_t)src[i] : 0;
+        const int32_t v = (i < nk + 255u) ? (int32_t)src[i] : 0;
         s_y[i] = v;
         const uint32_t w0 = __ballot_sync(0xffffffffu, v & 1), w1 = __ballot_sync(0xffffffffu, v & 2);
         if ((tid & 31) == 0) { s_b0[i >> 5] = w0; s_b1[i >> 5] = w1; }
@@ -414,7 +420,8 @@ ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_
                 acc[o] += (uint32_t)c_hilb_c32[4 * v + e] * (uint32_t)(rw[3 + o - e] - lw[o + e]);
         l0 = l1; r1 = r0;
     }
-    const int16_t* qsrc = YQ + (size_t)ch * yq_stride + k0 + kt;     // qsrc[kYQHalo + o] = yQ[k], qsrc[o] = yQ[k - 130]
+    const int16_t* qsrc = YQ + (size_t)ch * yq_stride + k0 + kt;     // qsrc[kYQHalo + o] = yQ[k], qsrc[kYQHalo - d_q + o] = yQ[k - d_q]
+    const int16_t* isrc = YI + (size_t)ch * yi_stride + kYIHalo + k0 + kt;   // isrc[o] = yI[k]
     uint64_t* dst = frames + (size_t)ch * frame_ch_stride;
 #pragma unroll
     for (int o = 0; o < kHbPer; ++o) {
@@ -437,8 +444,7 @@ ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_
         const uint32_t a30 = a & 0x3FFFFFFFu;
         const uint32_t r30 = (a30 + 0x1FFFu + ((a >> 14) & 1u)) & 0x3FFFFFFFu;
         const int16_t vi = (int16_t)((int32_t)(r30 << 2) >> 16);
-        const int16_t yi = (int16_t)s_y[kYIHalo + kt + o];
-        dst[(ring_start + k0 + kt + o) & ring_mask] = frame_pack(qsrc[kYQHalo + o], yi, qsrc[o], vi);
+        dst[(ring_start + k0 + kt + o) & ring_mask] = frame_pack(qsrc[kYQHalo + o], isrc[o], qsrc[kYQHalo - d_q + o], vi);
     }
 }
 
@@ -455,15 +461,18 @@ ddc_rotate_kernel(uint64_t* __restrict__ L, uint32_t l_ch_stride,
     int16_t* yi = YI + (size_t)ch * yi_stride;
     int16_t* yq = YQ + (size_t)ch * yq_stride;
     constexpr int kLPer = (kLHalo * kLRec + 255) / 256;               // halo words per thread
-    uint64_t vl[kLPer]; int16_t vyi = 0, vyq = 0;
+    static_assert(kYIHalo <= 512 && kYQHalo <= 256, "halo rotation: two YI words and one YQ word per thread");
+    uint64_t vl[kLPer]; int16_t vyi = 0, vyi2 = 0, vyq = 0;
 #pragma unroll
     for (int q = 0; q < kLPer; ++q) { const uint32_t w = t + 256u * q; vl[q] = (w < kLHalo * kLRec) ? l[(size_t)n_chunks * kLRec + w] : 0; }
     if (t < kYIHalo) vyi = yi[n_frames + t];
+    if (t + 256 < kYIHalo) vyi2 = yi[n_frames + t + 256];
     if (t < kYQHalo) vyq = yq[n_frames + t];
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < kLPer; ++q) { const uint32_t w = t + 256u * q; if (w < kLHalo * kLRec) l[w] = vl[q]; }
     if (t < kYIHalo) yi[t] = vyi;
+    if (t + 256 < kYIHalo) yi[t + 256] = vyi2;
     if (t < kYQHalo) yq[t] = vyq;
     if (t == 0 && ch < n_ch) phase[ch] = (phase[ch] + fcw[ch] * (n_chunks * (uint32_t)kCicR)) & 0x3FFFFFu;
 }
@@ -556,10 +565,10 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
     }
     if (ev && ((ev_mask >> 2) & 1u)) cudaEventRecord(ev[2], st);
     UA3_LAUNCH(ddc_ciccomp_kernel, dim3(b.n_ch, (n_frames + kCcFrames - 1) / kCcFrames), kCcThreads, 0, st, b.L, b.l_ch_stride, n_frames,
-               b.YI, b.yi_stride, b.YQ, b.yq_stride);
+               b.YI, b.yi_stride, b.YQ, b.yq_stride, (uint32_t)b.align_b);
     if (ev && ((ev_mask >> 3) & 1u)) cudaEventRecord(ev[3], st);
     UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + kHbFrames - 1) / kHbFrames), kHbThreads, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
-               n_frames, b.frames, b.frame_ch_stride, ring_start, b.ring_mask);
+               n_frames, b.frames, b.frame_ch_stride, ring_start, b.ring_mask, (uint32_t)b.d_i, (uint32_t)b.d_q);
     if (ev && ((ev_mask >> 4) & 1u)) cudaEventRecord(ev[4], st);
     UA3_LAUNCH(ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.YI, b.yi_stride,
                b.YQ, b.yq_stride, n_chunks, n_frames, b.phase, b.fcw, b.n_ch_pad);

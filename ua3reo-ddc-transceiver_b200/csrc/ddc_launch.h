@@ -24,6 +24,11 @@ struct DdcBuffers {
     uint64_t* frames = nullptr;    // [n_ch][ring] 8-byte frames, a ring per channel (ring is a power of two)
     uint32_t frame_ch_stride = 0;  // ring size in frames
     uint32_t ring_mask = 0;
+    // Clocking class of the frame (which of the board's reset-release instants is reproduced; the classes and their
+    // frequencies were measured by running the reference's VHDL, oracle/ddc_golden.c "Clocking"):
+    int align_b = 1;               // compensator polyphase alignment: 1 = "B" y[k] = sum h[j] u[2k-j], 0 = "A" y[k] = sum h[j] u[2k+1-j]
+    int d_i = 3;                   // VOICE_I[n] = hilbert(SPEC_I)[n - d_i], 0..kMaxDI (serial MAC + output register of rx_hilb.vhd)
+    int d_q = 129;                 // VOICE_Q[n] = SPEC_Q[n - d_q], 1..130 (data_delay.v, 130 registers, sampled before or after its clock edge)
 };
 
 void build_cic_weights(uint64_t G[25]);

@@ -32,11 +32,12 @@ constexpr int kFrameBytes = 8;      // stm32_interface.v:228-271
 
 // ---- layout of the per-chunk CIC partial-state records in HBM ----
 // One record per (channel, 512-sample chunk): 2 rails x 5 integrator partial states (u64).
-constexpr int kLHalo = 68;          // chunks of history: 64 CIC outputs for the 65-tap compensator + 4 for the 5-chunk comb window
+constexpr int kLHalo = 69;          // chunks of history: 65 CIC outputs for the 65-tap compensator in either polyphase alignment + 4 for the 5-chunk comb window
 constexpr int kLRec = 10;           // u64 per record: [rail][stage]
-constexpr int kUHalo = 64;          // 96 kHz samples of history for the 65-tap compensator
-constexpr int kYIHalo = 255;        // 48 kHz samples of history for the 256-tap Hilbert FIR
-constexpr int kYQHalo = 130;        // data_delay depth
+constexpr int kUHalo = 65;          // 96 kHz samples of history for the 65-tap compensator (64 in alignment A, 65 in alignment B)
+constexpr int kMaxDI = 3;           // largest VOICE_I latency of a clocking class (ddc_launch.h)
+constexpr int kYIHalo = 255 + kMaxDI;   // 48 kHz samples of history for the 256-tap Hilbert FIR evaluated up to kMaxDI samples back
+constexpr int kYQHalo = 130;        // data_delay depth (d_q of a clocking class is 129 or 130)
 
 // ---- front kernel tiling ----
 constexpr int kFrontWarps = 8;                     // warps per CTA, one 512-sample chunk each
