@@ -224,8 +224,9 @@ class Receiver:
 
     def close(self):
         if self._h is not None:
-            self.lib.ua3reo_destroy(self._h)
+            self.lib.ua3reo_destroy(self._h)      # synchronises the context's streams first
             self._h = None
+            self._inflight = []
 
     def __del__(self):
         try:
@@ -257,8 +258,10 @@ class Receiver:
     def set_frequency(self, channel, freq_hz):
         self._chk(self.lib.ua3reo_set_frequency(self._h, int(channel), int(freq_hz)))
 
-    def push(self, adc):
-        """adc: 1-D int16 numpy array (host) or a CUDA torch tensor of dtype int16 on this device."""
+    def push(self, adc, assume_ordered=False):
+        """adc: 1-D int16 numpy array (host) or a CUDA torch tensor of dtype int16 on this device.
+        assume_ordered: the caller has already ordered the library stream after the tensor's producer and keeps the
+        tensor alive and unchanged until the push completes (sharding.AdcBroadcaster does)."""
         n = ctypes.c_size_t(0)
         if isinstance(adc, np.ndarray):
             a = np.ascontiguousarray(adc, dtype=np.int16)
@@ -268,14 +271,19 @@ class Receiver:
             if adc.is_cuda:
                 assert adc.dtype.itemsize == 2 and adc.is_contiguous()
                 # The library consumes whole-block device pushes IN PLACE on its own non-blocking stream: order that
-                # stream after the tensor's producer (torch's current stream), tell the caching allocator that the
-                # library stream uses the memory, and keep the tensor alive until the next push has been issued.
-                import torch
-                lib_stream = torch.cuda.ExternalStream(self.stream(), device=adc.device)
-                lib_stream.wait_stream(torch.cuda.current_stream(adc.device))
-                adc.record_stream(lib_stream)
-                self._keep_dev = (getattr(self, "_keep_dev", (None, None))[1], adc)   # this push and the one before
+                # stream after the tensor's producer (torch's current stream) and keep the tensor alive until an event
+                # recorded behind the push has completed.  (Tensor.record_stream is not used: the caching allocator
+                # would touch the library's stream when the tensor dies, possibly after close() destroyed it.)
+                lib_stream = None
+                if not assume_ordered:
+                    import torch
+                    lib_stream = torch.cuda.ExternalStream(self.stream(), device=adc.device)
+                    lib_stream.wait_stream(torch.cuda.current_stream(adc.device))
                 self._chk(self.lib.ua3reo_ddc_push_device(self._h, adc.data_ptr(), adc.numel(), ctypes.byref(n)))
+                if lib_stream is not None:
+                    ev = torch.cuda.Event()
+                    ev.record(lib_stream)
+                    self._inflight = [(e, t) for e, t in getattr(self, "_inflight", []) if not e.query()] + [(ev, adc)]
             else:
                 assert adc.dtype.itemsize == 2 and adc.is_contiguous()
                 self._keep = adc
@@ -506,6 +514,7 @@ class Receiver:
 
     def sync(self):
         self._chk(self.lib.ua3reo_sync(self._h))
+        self._inflight = []
 
     def stream(self):
         s = ctypes.c_void_p()

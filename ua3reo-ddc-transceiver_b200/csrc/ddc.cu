@@ -263,7 +263,8 @@ constexpr int kCcOut = kCcChunks + kUHalo;             // CIC outputs per rail a
 constexpr int kCcRun = 11;                             // outputs per run; odd, so that the strided 64-bit record reads of a half warp fall into distinct banks
 constexpr int kCcWarm = kLHalo - kUHalo;               // 4 records of run-in
 constexpr int kCcThreads = 128;
-constexpr int kCcUPitch = kCcOut + 8;                  // int32 samples per rail, zero padded for the vector reads
+constexpr int kCcUPitch = (kCcOut + 8 + 3) & ~3;       // int32 samples per rail, zero padded for the vector reads; a multiple of 4 keeps rail 1 16-byte aligned
+static_assert(kCcUPitch % 4 == 0, "16-byte vector reads of s_u");
 static_assert(2 * ((kCcOut + kCcRun - 1) / kCcRun) <= kCcThreads, "one thread per (rail, run)");
 static_assert(2 * (kCcFrames / 2) <= kCcThreads, "one thread per (rail, frame pair)");
 static_assert((kCcRecs * kLRec * 8) % 16 == 0, "TMA bulk size");

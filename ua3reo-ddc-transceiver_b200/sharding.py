@@ -27,27 +27,88 @@ def torch_uint8():
 
 
 class AdcBroadcaster:
-    """Double-buffered broadcast of ADC blocks from the ingest rank (torch tensors on the compute device)."""
+    """Pipelined broadcast of ADC blocks from the ingest rank into a small ring of device buffers.
 
-    def __init__(self, block_samples, device, src=0, dist=None):
+    The library consumes a device push in place on its own stream (include/ua3reo_b200.h, DEVICE PUSH CONTRACT), so the
+    broadcaster owns both orderings: the consumer stream waits for the broadcast that filled a buffer (`acquire`), and
+    the broadcast that refills a buffer waits for the consumer work that read it (`release`).  Broadcasts run on a side
+    stream, so that the transfer of block i+1 overlaps the kernels of block i:
+
+        bc.prefetch(block0)
+        for i in range(n):
+            if i + 1 < n: bc.prefetch(block[i + 1])     # rank `src` passes its block, the others None
+            buf = bc.acquire()                          # consumer stream now waits for the broadcast of block i
+            rx.push(buf, assume_ordered=True)           # enqueued on the consumer stream
+            bc.release(buf)                             # buffer may be refilled once that push has finished
+
+    On CPU tensors (gloo, the unit tests) everything is synchronous and the events are skipped."""
+
+    def __init__(self, block_samples, device, src=0, dist=None, consumer_stream=None, n_buffers=2, group=None):
         import torch
+        self.torch = torch
         self.dist = dist
+        self.group = group
         self.src = src
-        self.bufs = [torch.empty(block_samples, dtype=torch.int16, device=device) for _ in range(2)]
-        self.i = 0
+        self.cuda = torch.device(device).type == "cuda"
+        self.bufs = [torch.empty(block_samples, dtype=torch.int16, device=device) for _ in range(n_buffers)]
+        self.n_filled = 0          # blocks broadcast so far
+        self.n_taken = 0           # blocks handed to the consumer so far
+        if self.cuda:
+            assert consumer_stream is not None, "AdcBroadcaster on a GPU needs the stream that consumes the blocks (rx.stream())"
+            self.consumer = consumer_stream if isinstance(consumer_stream, torch.cuda.Stream) else \
+                torch.cuda.ExternalStream(int(consumer_stream), device=device)
+            self.side = torch.cuda.Stream(device=device)
+            self.ev_ready = [torch.cuda.Event() for _ in range(n_buffers)]
+            self.ev_free = [torch.cuda.Event() for _ in range(n_buffers)]
+            self.released = [False] * n_buffers
+
+    def _world(self):
+        return 1 if self.dist is None else self.dist.get_world_size(self.group)
+
+    def prefetch(self, local_block=None):
+        """Enqueues the broadcast of the next block.  Rank `src` passes the block (same device, or pinned host memory)."""
+        assert self.n_filled - self.n_taken < len(self.bufs), "AdcBroadcaster: every buffer holds a block that was not acquired yet"
+        b = self.n_filled % len(self.bufs)
+        buf = self.bufs[b]
+        is_src = self._world() == 1 or self.dist.get_rank(self.group) == self.src
+        if not self.cuda:
+            if is_src:
+                buf.copy_(local_block)
+            if self._world() > 1:
+                self.dist.broadcast(buf.view(torch_uint8()), src=self.src, group=self.group)
+        else:
+            torch = self.torch
+            with torch.cuda.stream(self.side):
+                if self.released[b]:
+                    self.side.wait_event(self.ev_free[b])          # the push that read this buffer has finished
+                    self.released[b] = False
+                if is_src:
+                    buf.copy_(local_block, non_blocking=True)
+                if self._world() > 1:
+                    self.dist.broadcast(buf.view(torch_uint8()), src=self.src, group=self.group)   # no int16 in NCCL: move bytes
+                self.ev_ready[b].record(self.side)
+        self.n_filled += 1
+
+    def acquire(self):
+        """The oldest prefetched block; the consumer stream is made to wait for its broadcast."""
+        assert self.n_taken < self.n_filled, "AdcBroadcaster.acquire without a prefetch"
+        b = self.n_taken % len(self.bufs)
+        self.n_taken += 1
+        if self.cuda:
+            self.consumer.wait_event(self.ev_ready[b])
+        return self.bufs[b]
+
+    def release(self, buf):
+        """Call after the consumer's work on `buf` has been enqueued on the consumer stream."""
+        if self.cuda:
+            b = next(i for i, x in enumerate(self.bufs) if x is buf)
+            self.ev_free[b].record(self.consumer)
+            self.released[b] = True
 
     def next_block(self, local_block=None):
-        """Rank `src` passes its block (tensor, same device); every rank gets the broadcast block back."""
-        buf = self.bufs[self.i & 1]
-        self.i += 1
-        if self.dist is None or self.dist.get_world_size() == 1:
-            if local_block is not None:
-                buf.copy_(local_block, non_blocking=True)
-            return buf
-        if self.dist.get_rank() == self.src:
-            buf.copy_(local_block, non_blocking=True)
-        self.dist.broadcast(buf.view(torch_uint8()), src=self.src)   # NCCL/gloo have no int16: move the bytes
-        return buf
+        """prefetch + acquire in one call (no overlap).  On a GPU the caller still calls release(buf) after the push."""
+        self.prefetch(local_block)
+        return self.acquire()
 
 
 def gather_rows(local_rows, n_total, dist):
