@@ -275,6 +275,10 @@ int ua3reo_duc_enable(ua3reo_ctx *ctx, uint32_t max_tx_samples);
 /* The TX I/Q words the MCU sends on command 3 (stm32_interface.v:206-227 <- FPGA_fpgadata_sendiq, fpga.c:403-436):
  * iq_host is [n_channels][n][2] int16 (I, Q).  Produces n*1024 DAC words per channel. */
 int ua3reo_duc_push(ua3reo_ctx *ctx, const int16_t *iq_host, size_t n);
+/* The same samples in the byte order of the wire: wire_host is [n_channels][n][4] bytes, for every sample
+ * Q hi, Q lo, I hi, I lo - what FPGA_fpgadata_sendiq() writes after command 3 (fpga.c:403-436) and stm32_interface.v:206-227
+ * reassembles into Q_HOLD / I_HOLD -> TX_Q / TX_I.  The mirror of the 8-byte RX frame of ua3reo_ddc_read_frames. */
+int ua3reo_duc_push_wire(ua3reo_ctx *ctx, const uint8_t *wire_host, size_t n);
 /* The 14-bit offset-binary words DAC_corrector.v:15-21 drives onto the DAC pins: dst [n_channels][n*1024] uint16. */
 int ua3reo_duc_read_dac(ua3reo_ctx *ctx, uint16_t *dst_host, size_t n);
 int ua3reo_duc_dac_device(ua3reo_ctx *ctx, const uint16_t **base, size_t *n_words, size_t *channel_stride_words);

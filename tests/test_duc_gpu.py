@@ -52,3 +52,27 @@ def test_duc_then_ddc_loopback(pkg, oracle):
     k = int(np.argmax(sp))
     f = (k if k < z.size / 2 else k - z.size) * 48000.0 / z.size
     assert abs(abs(f) - 1500.0) < 1300.0 and np.abs(z).mean() > 300
+
+
+def test_duc_wire_order_entry(pkg, oracle):
+    """ua3reo_duc_push_wire takes the command-3 bytes (Q hi, Q lo, I hi, I lo: fpga.c:403-436, stm32_interface.v:206-227)."""
+    rng = np.random.default_rng(12)
+    n_ch, n = 5, 9
+    fcw = rng.integers(1, 1 << 21, n_ch).astype(np.uint32)
+    iq = rng.integers(-32768, 32768, (n_ch, n, 2)).astype(np.int16)
+    iq[0, 0] = [-32768, 32767]
+    wire = np.zeros((n_ch, n, 4), np.uint8)
+    u = iq.view(np.uint16)
+    wire[..., 0], wire[..., 1] = u[..., 1] >> 8, u[..., 1] & 0xFF          # Q first
+    wire[..., 2], wire[..., 3] = u[..., 0] >> 8, u[..., 0] & 0xFF
+    out = []
+    for use_wire in (False, True):
+        rx = pkg.Receiver(n_ch, 1 << 14)
+        rx.set_fcw(fcw)
+        rx.duc_enable(16)
+        rx.duc_push_wire(wire) if use_wire else rx.duc_push(iq)
+        out.append(rx.duc_read_dac())
+        rx.close()
+    assert np.array_equal(out[0], out[1])
+    ref, _ = oracle.GoldenDUC(fcw[0]).push(iq[0, :, 0], iq[0, :, 1])
+    assert np.array_equal(out[1][0], ref)

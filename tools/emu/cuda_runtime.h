@@ -31,6 +31,8 @@
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 struct uint4 { uint32_t x, y, z, w; };
 struct ulonglong2 { unsigned long long x, y; };
+struct int2 { int x, y; };
+static inline int2 make_int2(int a, int b) { return int2{a, b}; }
 static inline ulonglong2 make_ulonglong2(unsigned long long a, unsigned long long b) { return ulonglong2{a, b}; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 using std::min; using std::max;

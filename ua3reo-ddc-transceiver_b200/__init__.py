@@ -116,6 +116,7 @@ def _bind(lib):
         "ua3reo_autogain_step": (None, [vp, c.c_int16]),
         "ua3reo_duc_enable": (c.c_int, [vp, u32]),
         "ua3reo_duc_push": (c.c_int, [vp, vp, sz]),
+        "ua3reo_duc_push_wire": (c.c_int, [vp, vp, sz]),
         "ua3reo_duc_read_dac": (c.c_int, [vp, vp, sz]),
         "ua3reo_duc_dac_device": (c.c_int, [vp, c.POINTER(vp), c.POINTER(sz), c.POINTER(sz)]),
         "ua3reo_duc_read_otr": (c.c_int, [vp, vp]),
@@ -466,6 +467,14 @@ class Receiver:
         assert a.ndim == 3 and a.shape[0] == self.n_channels and a.shape[2] == 2
         self._keep_tx = a
         self._chk(self.lib.ua3reo_duc_push(self._h, a.ctypes.data, a.shape[1]))
+        self._last_tx = a.shape[1]
+        return a.shape[1]
+
+    def duc_push_wire(self, wire):
+        """wire: uint8 [n_channels, n, 4] = Q hi, Q lo, I hi, I lo per sample (command 3 of the bus); returns n."""
+        a = np.ascontiguousarray(wire, dtype=np.uint8)
+        assert a.ndim == 3 and a.shape[0] == self.n_channels and a.shape[2] == 4
+        self._chk(self.lib.ua3reo_duc_push_wire(self._h, a.ctypes.data, a.shape[1]))
         self._last_tx = a.shape[1]
         return a.shape[1]
 

@@ -17,6 +17,9 @@
 using namespace ua3;
 #include "rx_host.cpp.inc"
 
+// SMs the front kernel leaves to the STM32 stage (see push_common).  Measured (tools/gpu/sweep_rx_reserve.sh): 1024 channels
+// 1.022 / 1.037 / 1.071 ms per step at 6 / 8 / 12 SMs; 4096 channels 3.707 / 3.739 / 3.768 ms at 4 / 6 / 8.
+static constexpr int kRxReserveSmall = 6, kRxReserveLarge = 4;
 static constexpr int kProfEvents = kDdcKernels + 3;   // 5 DDC kernels, rx_audio, rx_fft: 8 event points per block
 static thread_local std::string g_err;
 
@@ -67,6 +70,8 @@ struct ua3reo_ctx {
     // bound and packed into a few whole SMs (rx.cu), so it overlaps the next push's persistent front kernel, which
     // takes its tiles from a counter and simply runs on the SMs that are left.
     cudaStream_t rx_stream = nullptr;
+    cudaStream_t rx_stream2 = nullptr;             // FFT_doFFT kernels: independent of the audio kernels, so they run beside them
+    cudaEvent_t ev_fft_done = nullptr;
     cudaEvent_t ev_frames = nullptr;               // the frames (and every earlier operation of `stream`) of the push are done
     cudaEvent_t ev_rx_done[2] = {nullptr, nullptr};   // STM32 stage of push k (k & 1) has finished
     bool rx_done_valid[2] = {false, false};
@@ -130,6 +135,8 @@ static int ctx_free(ua3reo_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->rx_stream) { cudaStreamSynchronize(c->rx_stream); cudaStreamDestroy(c->rx_stream); }
+    if (c->rx_stream2) { cudaStreamSynchronize(c->rx_stream2); cudaStreamDestroy(c->rx_stream2); }
+    if (c->ev_fft_done) cudaEventDestroy(c->ev_fft_done);
     if (c->ev_frames) cudaEventDestroy(c->ev_frames);
     for (int i = 0; i < 2; ++i) if (c->ev_rx_done[i]) cudaEventDestroy(c->ev_rx_done[i]);
     for (int i = 0; i < 2; ++i) if (c->ev_rxcopy[i]) cudaEventDestroy(c->ev_rxcopy[i]);
@@ -177,7 +184,10 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
         int prio_lo = 0, prio_hi = 0;
         e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->rx_stream, cudaStreamNonBlocking, prio_hi);
+        // the FFT kernels yield to the audio kernels (the longer chain), both go before the DDC
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->rx_stream2, cudaStreamNonBlocking, prio_hi < prio_lo - 1 ? prio_hi + 1 : prio_hi);
     }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_fft_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_frames, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_rx_done[i], cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&c->ev_rxcopy[i], cudaEventDisableTiming);
@@ -335,16 +345,25 @@ static int rx_run_stage(ua3reo_ctx* c, cudaEvent_t* ev, int* launches) {
     const int set = (int)(c->n_push & 1);
     c->rx.audio_out = c->rx_audio2[set]; c->rx.spectra = c->rx_spec2[set]; c->rx.waterfall = c->rx_wf2[set]; c->rx.cw_mag = c->rx_cw2[set];
     c->rx_last_slot = set;
+    // processRxAudio and FFT_doFFT touch disjoint state and outputs: their kernels run on two streams side by side
+    // (serialised on one stream only while per-kernel profiling events are being recorded)
+    cudaStream_t fft_st = ev ? c->rx_stream : c->rx_stream2;
     UA3_CUDA(cudaEventRecord(c->ev_frames, c->stream));
     UA3_CUDA(cudaStreamWaitEvent(c->rx_stream, c->ev_frames, 0));
+    if (fft_st != c->rx_stream) UA3_CUDA(cudaStreamWaitEvent(fft_st, c->ev_frames, 0));
     if (c->rxcopy_pending[set]) {                                // a pipelined read of push k-2 still owns this result set
         UA3_CUDA(cudaStreamWaitEvent(c->rx_stream, c->ev_rxcopy[set], 0));
+        if (fft_st != c->rx_stream) UA3_CUDA(cudaStreamWaitEvent(fft_st, c->ev_rxcopy[set], 0));
         c->rxcopy_pending[set] = false;
     }
     UA3_CUDA(rx_launch_audio(c->rx, (uint32_t)(c->a_pos & c->b.ring_mask), nb, c->rx_stream, launches));
     if (ev && ((c->prof_mask >> (kDdcKernels + 1)) & 1u)) cudaEventRecord(ev[kDdcKernels + 1], c->rx_stream);
-    UA3_CUDA(rx_launch_fft(c->rx, (uint32_t)(c->f_pos & c->b.ring_mask), nf, c->rx_stream, launches));
+    UA3_CUDA(rx_launch_fft(c->rx, (uint32_t)(c->f_pos & c->b.ring_mask), nf, fft_st, launches));
     if (ev && ((c->prof_mask >> (kDdcKernels + 2)) & 1u)) cudaEventRecord(ev[kDdcKernels + 2], c->rx_stream);
+    if (fft_st != c->rx_stream) {
+        UA3_CUDA(cudaEventRecord(c->ev_fft_done, fft_st));
+        UA3_CUDA(cudaStreamWaitEvent(c->rx_stream, c->ev_fft_done, 0));
+    }
     const int slot = (int)(c->n_push & 1);
     UA3_CUDA(cudaEventRecord(c->ev_rx_done[slot], c->rx_stream));
     c->rx_done_valid[slot] = true;
@@ -393,16 +412,16 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
     if (n_proc && c->adc_stats_on)
         UA3_CUDA(adc_stats_launch(proc_src, n_proc, c->adc_stats, c->sm_count, c->stream, &launches));
     if (n_proc) {
-        // With the STM32 stage on, the persistent front kernel leaves as many SMs free as the previous push's
-        // rx_audio_kernel has CTAs (each fills one SM; at most 11), so that the two always run side by side: rx_audio is
-        // latency bound (0.8 ms per block of 2^20 ADC samples however few channels there are), and hiding it is worth
-        // the 7 % of front-kernel SMs up to about 8000 channels (measured: 1.75 -> 1.15 ms per block at 1024 channels,
-        // 4.52 -> 4.27 ms at 4096, but 15.7 -> 16.8 ms at 16384, where it already fills the machine on its own).
+        // With the STM32 stage on, the persistent front kernel leaves a few SMs free for the previous push's STM32 kernels
+        // (rx_filter / rx_post / rx_fft on the high-priority rx_stream), so that the two stages always run side by side:
+        // a front CTA owns a whole SM (all shared memory and registers), nothing can share one with it.  The STM32 stage
+        // needs about 4 % of the machine; it gets the SMs its resident warps can fill, at most kRxReserveSmall / kRxReserveLarge.
         int front_sms = c->sm_count;
         if (c->rx_on) {
-            const int rx_ctas = (int)((c->n_ch + 95u) / 96u);
             const char* env = std::getenv("UA3REO_RX_RESERVE_SMS");
-            const int reserve = env ? std::atoi(env) : (c->n_ch > 8192u ? 0 : (rx_ctas < 11 ? rx_ctas : 11));
+            const int want = rx_audio_sms(c->n_ch);
+            const int cap = c->n_ch <= 2048u ? kRxReserveSmall : kRxReserveLarge;   // a longer step leaves the stage more time per SM
+            const int reserve = env ? std::atoi(env) : (want < cap ? want : cap);
             if (reserve > 0 && reserve < c->sm_count) front_sms = c->sm_count - reserve;
         }
         UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, (uint32_t)(c->w_pos & c->b.ring_mask), front_sms, c->stream,
@@ -505,7 +524,7 @@ void ua3reo_rx_defaults(ua3reo_rx_settings* s) {
     s->filter_width = 2700; s->ssb_hpf_pass = 300; s->notch_fc = 1000;
 }
 
-// slot -> channel permutation that groups channels taking the same branches of rx_audio_kernel (stable sort)
+// slot -> channel permutation that groups channels taking the same branches of rx_filter_kernel / rx_post_kernel (stable sort)
 static int rx_upload_order(ua3reo_ctx* c) {
     std::vector<uint32_t> order(c->n_ch);
     for (uint32_t i = 0; i < c->n_ch; ++i) order[i] = i;
@@ -537,6 +556,9 @@ static int rx_allocate(ua3reo_ctx* c) {
         UA3_CUDA(dev_alloc(c, &c->rx_wf2[i], (size_t)c->n_ch * r.spec_ch_stride));
         UA3_CUDA(dev_alloc(c, &c->rx_cw2[i], (size_t)c->n_ch * r.max_audio_blocks));
     }
+    UA3_CUDA(dev_alloc(c, &r.scratch, rx_scratch_floats(c->n_ch, r.max_audio_blocks)));
+    if (const char* v = std::getenv("UA3REO_RX_SPLIT")) r.split_audio = std::atoi(v) != 0;
+    UA3_CUDA(dev_alloc(c, &r.fft_in, rx_fft_in_floats(c->n_ch, r.max_fft_frames)));
     r.audio_out = c->rx_audio2[0]; r.spectra = c->rx_spec2[0]; r.waterfall = c->rx_wf2[0]; r.cw_mag = c->rx_cw2[0];
     UA3_CUDA(dev_alloc(c, &r.wtf_hist, (size_t)c->n_ch * kWtfRows * kFftBins));
     UA3_CUDA(dev_alloc(c, &r.wtf_head, (size_t)c->n_ch));
@@ -1095,6 +1117,23 @@ int ua3reo_duc_push(ua3reo_ctx* c, const int16_t* iq_host, size_t n) {
     UA3_CUDA(duc_launch(c->duc, (uint32_t)n, c->stream, &launches));
     c->launches += (uint64_t)launches;
     c->last_tx = n;
+    return UA3_OK;
+}
+
+int ua3reo_duc_push_wire(ua3reo_ctx* c, const uint8_t* wire_host, size_t n) {
+    if (!c || (!wire_host && n)) return fail(UA3_E_INVAL, "ua3reo_duc_push_wire: null argument");
+    if (!c->duc_alloc) return fail(UA3_E_STATE, "ua3reo_duc_push_wire: call ua3reo_duc_enable first");
+    if (n > c->duc.max_in) return fail(UA3_E_TOOBIG, "ua3reo_duc_push_wire: more samples than max_tx_samples");
+    // stm32_interface.v:206-227: k=300 Q_HOLD[15:8], 301 Q_HOLD[7:0], 302 I_HOLD[15:8], 303 I_HOLD[7:0] -> TX_I, TX_Q
+    std::vector<int16_t> iq((size_t)c->n_ch * n * 2);
+    for (size_t i = 0; i < (size_t)c->n_ch * n; ++i) {
+        const uint8_t* w = wire_host + 4 * i;
+        iq[2 * i] = (int16_t)(uint16_t)(((uint16_t)w[2] << 8) | w[3]);        // I
+        iq[2 * i + 1] = (int16_t)(uint16_t)(((uint16_t)w[0] << 8) | w[1]);    // Q
+    }
+    const int rc = ua3reo_duc_push(c, iq.data(), n);
+    if (rc != UA3_OK) return rc;
+    UA3_CUDA(cudaStreamSynchronize(c->stream));      // iq is a temporary: the host->device copy must have finished
     return UA3_OK;
 }
 
