@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--total-channels", type=int, default=8192, help="--scaling strong: channels over all GPUs (configs[3])")
     ap.add_argument("--workload", default="all", choices=["all", "ddc", "full_chain"])
+    ap.add_argument("--comm-sms", type=int, default=None,
+                    help="N>1: SMs the front kernel leaves to the NCCL broadcast kernel (default 1; NCCL is held to as many channels)")
     return ap.parse_args()
 
 
@@ -259,6 +261,8 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
     fcw_all = synth.random_fcw(n_ch * world, SEED)
     my_fcw = fcw_all[rank * n_ch:(rank + 1) * n_ch]                      # channels sharded by rank, contiguous slabs
     rx.set_fcw(my_fcw)
+    if world > 1:
+        rx.reserve_sms(args.comm_sms if args.comm_sms is not None else 1)      # the broadcast of block i+1 runs UNDER the kernels of block i
     ext = torch.cuda.ExternalStream(rx.stream(), device=local)
     audio_host = spec_host = None
     if full:
@@ -413,7 +417,12 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
     # sustained: >= args.sustained_seconds of back-to-back steps, clocks sampled
     sustained = None
     if not args.no_sustained:
-        n_sus = max(K, int(args.sustained_seconds * 1e3 / (ms / K)) + 1)
+        ms_all = ms
+        if world > 1:                                  # every rank must run the SAME number of steps (one broadcast each)
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_all = float(t[0])
+        n_sus = max(K, int(args.sustained_seconds * 1e3 / (ms_all / K)) + 1)
         sus_sampler = ClockSampler(local).start() if rank == 0 else None
         barrier()
         e0.record(ext)
@@ -438,7 +447,15 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
         rx.push(dev_blocks[1], assume_ordered=True)
     got = rx.read_frames()
     picks = sorted({0, n_ch - 1})
-    ddc_ok = all(np.array_equal(got[c], pyoracle.GoldenDDC(int(my_fcw[c])).push(host_np[1])) for c in picks)
+    ddc_ok = True
+    for c in picks:
+        ref = pyoracle.GoldenDDC(int(my_fcw[c])).push(host_np[1])
+        if not np.array_equal(got[c], ref):
+            ddc_ok = False
+            bad = np.argwhere(got[c] != ref)
+            sys.stderr.write("bench.py: rank %d channel %d (fcw %d): %d of %d frame bytes differ, first at frame %d byte %d; "
+                             "frames got %s expected %s\n" % (rank, c, int(my_fcw[c]), bad.shape[0], ref.size, bad[0][0], bad[0][1],
+                                                               got.shape, ref.shape))
     audio_ok, audio_note = None, None
     if full:
         if pyoracle.have_fw_rx():
@@ -549,6 +566,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                        "channels_total": n_ch * world, "channels_per_gpu": n_ch, "block_samples": block,
                        "real_time_channels": value / 49152000.0,
                        "clocking_class": "B/3/129 (the board's most frequent frame alignment, DESIGN.md 2)",
+                       "comm_sms": (args.comm_sms if args.comm_sms is not None else 1) if world > 1 else 0,
                        "l2": "per-step working set ~%.0f MB (chunk records + frames) exceeds the 126 MB L2; no flush needed"
                              % (step_bytes / 1e6)},
             "e2e": {"value": e2e, "unit": "channel*samples/s", "h2d_bytes_per_step": 2 * block,
@@ -622,6 +640,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device - this repo has no CPU fallback (use --impl reference for the CPU model)")
     torch.cuda.set_device(local)
     if world > 1:
+        # the broadcast moves 2 MB per step: one NCCL channel (= one CTA) is plenty, and that is how many SMs are kept for it
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", str(max(1, args.comm_sms if args.comm_sms is not None else 1)))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     want_cpu = world == 1 and not args.no_cpu_baseline
     if args.scaling == "strong":

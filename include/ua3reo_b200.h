@@ -69,6 +69,12 @@ int ua3reo_reset(ua3reo_ctx *ctx);
 int ua3reo_ddc_set_clocking(ua3reo_ctx *ctx, int align_b, int d_i, int d_q);
 int ua3reo_ddc_get_clocking(const ua3reo_ctx *ctx, int *align_b, int *d_i, int *d_q);
 
+/* Leaves n_sms streaming multiprocessors out of the persistent front kernel's grid for work the CALLER runs beside the
+ * pushes - typically the NCCL kernel that broadcasts the next ADC block (a front CTA owns a whole SM, so a collective
+ * kernel can only run on an SM the front kernel does not occupy; without this it waits for the gap between two pushes).
+ * 0 (default) gives the front kernel every SM.  Independent of the SMs kept for the STM32 stage. */
+int ua3reo_reserve_sms(ua3reo_ctx *ctx, int n_sms);
+
 uint32_t ua3reo_n_channels(const ua3reo_ctx *ctx);
 uint32_t ua3reo_max_block_samples(const ua3reo_ctx *ctx);
 

@@ -76,6 +76,7 @@ def _bind(lib):
         "ua3reo_reset": (c.c_int, [vp]),
         "ua3reo_ddc_set_clocking": (c.c_int, [vp, c.c_int, c.c_int, c.c_int]),
         "ua3reo_ddc_get_clocking": (c.c_int, [vp, c.POINTER(c.c_int), c.POINTER(c.c_int), c.POINTER(c.c_int)]),
+        "ua3reo_reserve_sms": (c.c_int, [vp, c.c_int]),
         "ua3reo_n_channels": (u32, [vp]),
         "ua3reo_max_block_samples": (u32, [vp]),
         "ua3reo_set_fcw": (c.c_int, [vp, u32, u32, vp]),
@@ -246,6 +247,10 @@ class Receiver:
         a, i, q = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         self._chk(self.lib.ua3reo_ddc_get_clocking(self._h, ctypes.byref(a), ctypes.byref(i), ctypes.byref(q)))
         return a.value, i.value, q.value
+
+    def reserve_sms(self, n_sms):
+        """Keep n_sms SMs out of the front kernel's grid for the caller's concurrent kernels (an NCCL broadcast)."""
+        self._chk(self.lib.ua3reo_reserve_sms(self._h, int(n_sms)))
 
     def set_fcw(self, fcw, first=0):
         a = np.ascontiguousarray(fcw, dtype=np.uint32)

@@ -19,7 +19,7 @@ using namespace ua3;
 
 // SMs the front kernel leaves to the STM32 stage (see push_common).  Measured (tools/gpu/sweep_rx_reserve.sh): 1024 channels
 // 1.022 / 1.037 / 1.071 ms per step at 6 / 8 / 12 SMs; 4096 channels 3.707 / 3.739 / 3.768 ms at 4 / 6 / 8.
-static constexpr int kRxReserveSmall = 6, kRxReserveLarge = 4;
+static constexpr int kRxReserveSmall = 5, kRxReserveLarge = 4;   // at least; the front kernel hands back every SM its round count does not need
 static constexpr int kProfEvents = kDdcKernels + 3;   // 5 DDC kernels, rx_audio, rx_fft: 8 event points per block
 static thread_local std::string g_err;
 
@@ -51,6 +51,7 @@ struct ua3reo_ctx {
     bool stage_busy[2] = {false, false};
     uint64_t n_host_push = 0;
     uint32_t n_ch = 0, n_ch_pad = 0, max_block = 0;
+    int comm_sms = 0;               // SMs left to the caller's concurrent kernels (ua3reo_reserve_sms)
     DdcBuffers b;
     int16_t* adc_stage = nullptr;   // device [max_block + 1024]: carry + new samples
     uint32_t carry = 0;
@@ -292,6 +293,13 @@ int ua3reo_ddc_get_clocking(const ua3reo_ctx* c, int* align_b, int* d_i, int* d_
     return UA3_OK;
 }
 
+int ua3reo_reserve_sms(ua3reo_ctx* c, int n_sms) {
+    if (!c) return fail(UA3_E_INVAL, "null context");
+    if (n_sms < 0 || n_sms >= c->sm_count / 2) return fail(UA3_E_INVAL, "ua3reo_reserve_sms: 0 <= n_sms < half the device");
+    c->comm_sms = n_sms;
+    return UA3_OK;
+}
+
 uint32_t ua3reo_n_channels(const ua3reo_ctx* c) { return c ? c->n_ch : 0; }
 uint32_t ua3reo_max_block_samples(const ua3reo_ctx* c) { return c ? c->max_block : 0; }
 uint64_t ua3reo_launch_count(const ua3reo_ctx* c) { return c ? c->launches : 0; }
@@ -416,13 +424,13 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
         // (rx_filter / rx_post / rx_fft on the high-priority rx_stream), so that the two stages always run side by side:
         // a front CTA owns a whole SM (all shared memory and registers), nothing can share one with it.  The STM32 stage
         // needs about 4 % of the machine; it gets the SMs its resident warps can fill, at most kRxReserveSmall / kRxReserveLarge.
-        int front_sms = c->sm_count;
+        int front_sms = c->sm_count - c->comm_sms;
         if (c->rx_on) {
             const char* env = std::getenv("UA3REO_RX_RESERVE_SMS");
             const int want = rx_audio_sms(c->n_ch);
             const int cap = c->n_ch <= 2048u ? kRxReserveSmall : kRxReserveLarge;   // a longer step leaves the stage more time per SM
             const int reserve = env ? std::atoi(env) : (want < cap ? want : cap);
-            if (reserve > 0 && reserve < c->sm_count) front_sms = c->sm_count - reserve;
+            if (reserve > 0 && reserve < front_sms) front_sms -= reserve;
         }
         UA3_CUDA(ddc_launch_block(c->b, proc_src, n_proc, (uint32_t)(c->w_pos & c->b.ring_mask), front_sms, c->stream,
                                   &launches, ev, c->prof_mask));

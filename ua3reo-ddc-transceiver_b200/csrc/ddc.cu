@@ -548,7 +548,12 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
     const bool big = b.front_variant != 1 && b.big_tab && (b.front_variant == 2 || ((b.n_ch_pad >> 5) >= (uint32_t)kBtCG && n_chunks >= (uint32_t)kBtTG));
     if (big) {
         const uint32_t n_tiles = (((b.n_ch_pad >> 5) + kBtCG - 1) / kBtCG) * ((n_chunks + kBtTG - 1) / kBtTG);
-        const uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count);
+        // Tiles all take the same time, so the kernel lasts ceil(n_tiles / grid) tile times: of the SMs it may use it takes
+        // only as many as that number of rounds needs (2048 tiles: 137 CTAs do 15 rounds exactly like 146 would) and
+        // leaves the others to whatever runs beside it - the STM32 stage, an NCCL broadcast.
+        uint32_t grid = (uint32_t)min((uint64_t)n_tiles, (uint64_t)sm_count);
+        const uint32_t rounds = (n_tiles + grid - 1) / grid;
+        grid = (n_tiles + rounds - 1) / rounds;
 #if !defined(UA3_HOST_EMU)
         const uint32_t n8 = n_chunks * (uint32_t)kCicR / 8u;
         UA3_LAUNCH(adc_expand_kernel, (n8 + 255u) / 256u, 256, 0, st, adc_dev, n8, b.adc9, b.tile_counter);
