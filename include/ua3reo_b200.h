@@ -265,6 +265,18 @@ typedef struct ua3reo_autogain {
 } ua3reo_autogain;
 void ua3reo_autogain_init(ua3reo_autogain *st);
 void ua3reo_autogain_step(ua3reo_autogain *st, int16_t adc_max_amplitude);
+/* The stages of processRxAudio() that the firmware also exports as functions of their own, run on a caller buffer with
+ * (and updating) the channel's state - for callers that use them individually; processRxAudio itself is ua3reo_ddc_push /
+ * ua3reo_rx_push_frames.  buf_host is read and, except for UA3_STAGE_DNR, overwritten in place.
+ *   UA3_STAGE_DC_FILTER  void dc_filter(float32_t *buf, int16_t n, uint8_t stateNum)      audio_filters.h:51, audio_filters.c:358-373; arg = stateNum 0..5
+ *   UA3_STAGE_AGC        void DoAGC(float32_t *buf, int16_t n)                             agc.h:9, agc.c:21-67
+ *   UA3_STAGE_DNR        void processNoiseReduction(float32_t *in, float32_t *out)         noise_reduction.h:16, noise_reduction.c:25-37; n = 64,
+ *                        the prediction goes to out_host (which may equal buf_host); nothing happens when the channel's DNR is off */
+#define UA3_STAGE_DC_FILTER 0
+#define UA3_STAGE_AGC 1
+#define UA3_STAGE_DNR 2
+int ua3reo_rx_stage(ua3reo_ctx *ctx, uint32_t channel, int stage, float *buf_host, float *out_host, size_t n, int arg);
+
 /* TRX_RX_dBm of the 100 ms housekeeping tick (stm32f4xx_it.c:398-409) from the S-meter extremes: pure host function. */
 int16_t ua3reo_smeter_dbm(float sample_max, float sample_min, uint8_t rf_gain);
 /* S-meter accumulators Processor_RX_Audio_Samples_MAX/MIN_value (audio_processor.c:491-501): dst [n_channels][2];
@@ -297,12 +309,13 @@ int ua3reo_duc_read_otr(ua3reo_ctx *ctx, uint32_t *dst_host);
  * what FPGA_fpgadata_sendiq() (fpga.c:403-436) puts on the bus and the DUC above consumes.
  * ------------------------------------------------------------------------------------------- */
 typedef struct ua3reo_tx_settings {
-    uint8_t mode;            /* TRX_MODE_*: LSB USB IQ CW_L CW_U DIGI_L DIGI_U NFM WFM AM */
+    uint8_t mode;            /* TRX_MODE_*: LSB USB IQ CW_L CW_U DIGI_L DIGI_U NO_TX NFM WFM AM LOOPBACK (trx_manager.h:11-24) */
     uint8_t mute;            /* TRX.Mute */
     uint8_t tune;            /* TRX_tune (carrier at the selected power) */
     uint8_t key_down;        /* TRX_key_serial || TRX_ptt_hard || TRX_key_hard (CW keying, audio_processor.c:146) */
     uint8_t rf_power;        /* TRX.RF_Power, percent of MAX_TX_AMPLITUDE (settings.h:13) */
-    uint8_t reserved[3];
+    uint8_t volume;          /* TRX.Volume: output level of TRX_MODE_LOOPBACK (audio_processor.c:231) */
+    uint8_t reserved[2];
     uint16_t filter_width;   /* CurrentVFO()->Filter_Width (also selects the FM modulation index, :597-605) */
     uint16_t ssb_hpf_pass;   /* TRX.SSB_HPF_pass */
 } ua3reo_tx_settings;
@@ -319,6 +332,10 @@ int ua3reo_tx_process(ua3reo_ctx *ctx, const int16_t *mic_host, size_t n_blocks)
 /* I/Q of the last call: iq_words [n_channels][n_blocks*192][2] int16 (I, Q as sent on the wire) and/or iq_float
  * (same shape, FPGA_Audio_SendBuffer_I/Q contents); either may be NULL. */
 int ua3reo_tx_read_iq(ua3reo_ctx *ctx, int16_t *iq_words, float *iq_float, size_t n_blocks);
+/* TRX_MODE_LOOPBACK (audio_processor.c:228-249): the block does not go to the FPGA but, scaled by Volume / 50, to the codec.
+ * dst [n_channels][n_blocks*192][2] int32 (left, right = left) - what the firmware copies into CODEC_Audio_Buffer_RX; zeros for
+ * channels in any other mode. */
+int ua3reo_tx_read_loopback(ua3reo_ctx *ctx, int32_t *dst_host, size_t n_blocks);
 /* Runs the DUC over the I/Q words of the last ua3reo_tx_process() without leaving the device. */
 int ua3reo_tx_feed_duc(ua3reo_ctx *ctx);
 

@@ -214,16 +214,17 @@ class GoldenDUC:
 
 FW_TX = os.path.join(_HERE, "_ref", "fw_tx")
 TX_PARAM_KEYS = {"mode": "mode", "filter_width": "filter_width", "ssb_hpf_pass": "hpf_pass", "rf_power": "rf_power",
-                 "mute": "mute", "tune": "tune", "key_down": "key"}
+                 "mute": "mute", "tune": "tune", "key_down": "key", "volume": "volume"}
 
 
 def have_fw_tx():
     return os.path.exists(FW_TX)
 
 
-def run_fw_tx(mic, settings, workdir=None, binary=None, env=None):
+def run_fw_tx(mic, settings, workdir=None, binary=None, env=None, want_codec=False):
     """Runs the host-built reference firmware's processTxAudio() over int16 [n, 2] codec samples (n multiple of 192).
-    Returns (iq_words int16 [n, 2], iq_float float32 [n, 2])."""
+    Returns (iq_words int16 [n, 2], iq_float float32 [n, 2]) and, with want_codec, the int32 [n, 2] the loopback branch
+    hands to the codec."""
     import tempfile
     mic = np.ascontiguousarray(mic, dtype=np.int16).reshape(-1, 2)
     with tempfile.TemporaryDirectory(dir=workdir) as d:
@@ -234,7 +235,9 @@ def run_fw_tx(mic, settings, workdir=None, binary=None, env=None):
                     f.write("%s %d\n" % (TX_PARAM_KEYS[k], int(v)))
         mic.tofile(mp_)
         subprocess.check_call([binary or FW_TX, pp, mp_, op], env=env)
-        raw = np.fromfile(op, dtype=np.uint8).reshape(-1, 192 * 2 * 4 + 192 * 2 * 2)
+        raw = np.fromfile(op, dtype=np.uint8).reshape(-1, 192 * 2 * 4 + 192 * 2 * 2 + 192 * 2 * 4)
         f = np.ascontiguousarray(raw[:, :1536]).view(np.float32).reshape(-1, 2)
-        w = np.ascontiguousarray(raw[:, 1536:]).view(np.int16).reshape(-1, 2)
+        w = np.ascontiguousarray(raw[:, 1536:2304]).view(np.int16).reshape(-1, 2)
+        if want_codec:
+            return w, f, np.ascontiguousarray(raw[:, 2304:]).view(np.int32).reshape(-1, 2)
         return w, f

@@ -10,7 +10,9 @@
  * where readHalfFromCircleBuffer32() will read them for a DMA counter of 0 (the stub's value), raises
  * Processor_NeedTXBuffer and calls processTxAudio(); FPGA_Audio_Buffer_State alternates as the bus driver
  * does (fpga.c:440-465).  iq_out: per block 192 x (float I, float Q) as left in FPGA_Audio_SendBuffer_I/Q,
- * followed by 192 x (int16 I, int16 Q) as FPGA_fpgadata_sendiq() converts them for the wire (fpga.c:409,424).
+ * followed by 192 x (int16 I, int16 Q) as FPGA_fpgadata_sendiq() converts them for the wire (fpga.c:409,424), followed by
+ * 384 int32: the half of CODEC_Audio_Buffer_RX that TRX_MODE_LOOPBACK fills instead (audio_processor.c:228-249; zeros in the
+ * other modes).  In loopback mode nothing is sent to the FPGA, the float I/Q are then FPGA_Audio_Buffer_I/Q_tmp.
  */
 #include "stm32f4xx_hal.h"
 #include "arm_math.h"
@@ -66,14 +68,21 @@ int main(int argc, char **argv)
         const int half = FPGA_Audio_Buffer_State ? FPGA_AUDIO_BUFFER_HALF_SIZE : 0;
         float f[192 * 2];
         int16_t w[192 * 2];
+        const int loopback = (TRX_getMode() == TRX_MODE_LOOPBACK) && !TRX_tune;
+        int32_t codec[192 * 2];
+        memset(codec, 0, sizeof codec);
         for (int i = 0; i < 192; i++) {
-            f[2 * i] = FPGA_Audio_SendBuffer_I[half + i];
-            f[2 * i + 1] = FPGA_Audio_SendBuffer_Q[half + i];
-            w[2 * i] = (int16_t)(float32_t)FPGA_Audio_SendBuffer_I[half + i];      /* fpga.c:424 */
-            w[2 * i + 1] = (int16_t)(float32_t)FPGA_Audio_SendBuffer_Q[half + i];  /* fpga.c:409 */
+            const float fi_ = loopback ? FPGA_Audio_Buffer_I_tmp[i] : FPGA_Audio_SendBuffer_I[half + i];
+            const float fq_ = loopback ? FPGA_Audio_Buffer_Q_tmp[i] : FPGA_Audio_SendBuffer_Q[half + i];
+            f[2 * i] = fi_;
+            f[2 * i + 1] = fq_;
+            w[2 * i] = (int16_t)(float32_t)fi_;      /* fpga.c:424 */
+            w[2 * i + 1] = (int16_t)(float32_t)fq_;  /* fpga.c:409 */
         }
+        if (loopback) memcpy(codec, &CODEC_Audio_Buffer_RX[WM8731_DMA_state ? FPGA_AUDIO_BUFFER_SIZE : 0], sizeof codec);
         fwrite(f, sizeof(float), 192 * 2, fo);
         fwrite(w, sizeof(int16_t), 192 * 2, fo);
+        fwrite(codec, sizeof(int32_t), 192 * 2, fo);
         FPGA_Audio_Buffer_State = !FPGA_Audio_Buffer_State;
     }
     fclose(fi); fclose(fo);

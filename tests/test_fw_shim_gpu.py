@@ -148,3 +148,30 @@ def test_fpga_bus_driver_cpu_vs_gpu_shim(pkg, oracle, tmp_path, tmp_path_factory
     assert np.array_equal(tail[0], tail[1]), "rings / FFTInput_I/Q / FPGA_samples / underrun flag"
     rings = tail[1][:4 * 384 * 4].view(np.float32)
     assert np.abs(rings).max() > 100                                                   # real signal went through
+
+
+@pytest.mark.parametrize("agc,speed,dnr,mode", [(1, 3, 1, 1), (1, 1, 0, 0), (0, 3, 1, 3), (1, 5, 1, 5)])
+def test_stage_functions_cpu_vs_gpu_shim(pkg, tmp_path, tmp_path_factory, agc, speed, dnr, mode):
+    """dc_filter() / DoAGC() / processNoiseReduction() (audio_filters.h:51, agc.h:9, noise_reduction.h:16) called on their own:
+    the reference's translation units against host/ua3reo_fw_shim.c over ua3reo_rx_stage, same driver (fw_stage.c), 40 blocks
+    with the gain ramp, the clip branch and the NLMS weights in motion.  IEEE +,-,*,/ only: bit-exact."""
+    import subprocess
+    ref_bin, shim_bin = os.path.join(ROOT, "oracle", "_ref", "fw_stage"), os.path.join(ROOT, "oracle", "_ref", "fw_stage_b200")
+    for b in (ref_bin, shim_bin):
+        if not os.path.exists(b):
+            pytest.skip("host-built firmware harness %s did not travel with the snapshot" % os.path.basename(b))
+    rng = np.random.default_rng(agc * 8 + dnr * 4 + mode)
+    n = 192 * 40
+    t = np.arange(n)
+    x = (2000 * np.sin(2 * np.pi * 0.02 * t) * (1 + 0.9 * np.sin(2 * np.pi * t / 2000.0)) + rng.normal(0, 150, n) + 300).astype(np.float32)
+    x[192 * 20:192 * 21] *= 40.0                                   # a burst: the clip branch of DoAGC (agc.c:41-45)
+    fin = tmp_path / "in.f32"
+    x.tofile(fin)
+    outs = []
+    for binary, env in ((ref_bin, None), (shim_bin, _shim_env(pkg, tmp_path_factory))):
+        out = tmp_path / (os.path.basename(binary) + ".out")
+        subprocess.check_call([binary, str(agc), str(speed), str(dnr), str(mode), str(fin), str(out)], env=env)
+        outs.append(np.fromfile(out, dtype=np.float32).reshape(-1, 2, 192))
+    assert outs[0].shape == outs[1].shape == (40, 2, 192)
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32)), "stage outputs differ (max |d| %g)" % np.abs(outs[0] - outs[1]).max()
+    assert np.abs(outs[0][:, 0]).max() > 1 and not np.array_equal(outs[0][:, 0], outs[0][:, 1])

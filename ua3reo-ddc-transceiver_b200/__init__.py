@@ -40,9 +40,9 @@ MODE_LSB, MODE_USB, MODE_IQ, MODE_CW_L, MODE_CW_U, MODE_DIGI_L, MODE_DIGI_U, MOD
 class TxSettings(ctypes.Structure):
     """struct ua3reo_tx_settings (include/ua3reo_b200.h)."""
     _fields_ = [("mode", ctypes.c_uint8), ("mute", ctypes.c_uint8), ("tune", ctypes.c_uint8), ("key_down", ctypes.c_uint8),
-                ("rf_power", ctypes.c_uint8), ("reserved", ctypes.c_uint8 * 3), ("filter_width", ctypes.c_uint16),
-                ("ssb_hpf_pass", ctypes.c_uint16)]
-    FIELDS = ("mode", "mute", "tune", "key_down", "rf_power", "filter_width", "ssb_hpf_pass")
+                ("rf_power", ctypes.c_uint8), ("volume", ctypes.c_uint8), ("reserved", ctypes.c_uint8 * 2),
+                ("filter_width", ctypes.c_uint16), ("ssb_hpf_pass", ctypes.c_uint16)]
+    FIELDS = ("mode", "mute", "tune", "key_down", "rf_power", "volume", "filter_width", "ssb_hpf_pass")
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k in self.FIELDS}
@@ -101,6 +101,7 @@ def _bind(lib):
         "ua3reo_rx_read_spectra": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_audio_usb": (c.c_int, [vp, vp, sz]),
         "ua3reo_rx_read_smeter": (c.c_int, [vp, vp, c.c_int]),
+        "ua3reo_rx_stage": (c.c_int, [vp, u32, c.c_int, vp, vp, sz, c.c_int]),
         "ua3reo_rx_read_waterfall": (c.c_int, [vp, vp, sz]),
         "ua3reo_copy_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_rx_read_audio_async": (c.c_int, [vp, vp, sz]),
@@ -127,6 +128,7 @@ def _bind(lib):
         "ua3reo_tx_set_live": (c.c_int, [vp, u32, u32, vp]),
         "ua3reo_tx_process": (c.c_int, [vp, vp, sz]),
         "ua3reo_tx_read_iq": (c.c_int, [vp, vp, vp, sz]),
+        "ua3reo_tx_read_loopback": (c.c_int, [vp, vp, sz]),
         "ua3reo_tx_feed_duc": (c.c_int, [vp]),
         "ua3reo_sync": (c.c_int, [vp]),
         "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
@@ -457,6 +459,14 @@ class Receiver:
         self._chk(self.lib.ua3reo_get_params(self._h, pkt.ctypes.data, ctypes.byref(mn), ctypes.byref(mx), 1 if dac_otr else 0))
         return pkt, int(mn.value), int(mx.value)
 
+    def rx_stage(self, channel, stage, buf, arg=0):
+        """dc_filter (stage 0, arg = stateNum), DoAGC (1) or processNoiseReduction (2, 64 samples) on a float32 buffer with the
+        channel's state; returns the result (include/ua3reo_b200.h: ua3reo_rx_stage)."""
+        a = np.array(buf, dtype=np.float32, copy=True)
+        out = a.copy()
+        self._chk(self.lib.ua3reo_rx_stage(self._h, int(channel), int(stage), a.ctypes.data, out.ctypes.data, a.size, int(arg)))
+        return out if stage == 2 else a
+
     def read_smeter(self, reset=False):
         out = np.empty((self.n_channels, 2), np.float32)
         self._chk(self.lib.ua3reo_rx_read_smeter(self._h, out.ctypes.data, 1 if reset else 0))
@@ -521,6 +531,12 @@ class Receiver:
         f = np.empty(a.shape, np.float32)
         self._chk(self.lib.ua3reo_tx_read_iq(self._h, w.ctypes.data, f.ctypes.data, nb))
         return w, f
+
+    def tx_read_loopback(self, n_blocks):
+        """int32 [n_channels, n_blocks*192, 2]: what TRX_MODE_LOOPBACK hands to the codec (zeros for other modes)."""
+        out = np.empty((self.n_channels, int(n_blocks) * AUDIO_BLOCK, 2), np.int32)
+        self._chk(self.lib.ua3reo_tx_read_loopback(self._h, out.ctypes.data, int(n_blocks)))
+        return out
 
     def tx_feed_duc(self):
         self._chk(self.lib.ua3reo_tx_feed_duc(self._h))

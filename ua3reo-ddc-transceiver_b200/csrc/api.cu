@@ -90,6 +90,7 @@ struct ua3reo_ctx {
     std::vector<ua3reo_rx_settings> h_set;
     std::vector<RxParams> h_par;
     uint8_t* rx_flags = nullptr;        // device scratch for rx_set's state-clear flags
+    float* stage_buf = nullptr;         // device scratch of ua3reo_rx_stage: 2 x 4096 floats
     int32_t* adc_stats = nullptr;       // device: min, max, samples at the rails (since the last reset)
     bool adc_stats_on = false;
     size_t last_audio_blocks = 0, last_fft_frames = 0;
@@ -1049,6 +1050,30 @@ int16_t ua3reo_smeter_dbm(float sample_max, float sample_min, uint8_t rf_gain) {
     return (int16_t)(10 * (Y * 0.3010299956639812f));
 }
 
+int ua3reo_rx_stage(ua3reo_ctx* c, uint32_t channel, int stage, float* buf_host, float* out_host, size_t n, int arg) {
+    if (!c || !buf_host || channel >= c->n_ch) return fail(UA3_E_INVAL, "ua3reo_rx_stage: bad arguments");
+    if (stage < UA3_STAGE_DC_FILTER || stage > UA3_STAGE_DNR) return fail(UA3_E_INVAL, "ua3reo_rx_stage: unknown stage");
+    if (n == 0 || n > 4096) return fail(UA3_E_INVAL, "ua3reo_rx_stage: 1..4096 samples");
+    if (stage == UA3_STAGE_DC_FILTER && (arg < 0 || arg > 5)) return fail(UA3_E_INVAL, "ua3reo_rx_stage: dc_filter stateNum is 0..5");
+    if (stage == UA3_STAGE_DNR && (n != 64 || !out_host)) return fail(UA3_E_INVAL, "ua3reo_rx_stage: the DNR takes 64 samples and an output buffer");
+    UA3_CUDA(cudaSetDevice(c->device));
+    { const int rc = rx_allocate(c); if (rc != UA3_OK) return rc; }
+    { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
+    if (!c->stage_buf) UA3_CUDA(dev_alloc(c, &c->stage_buf, (size_t)2 * 4096));
+    UA3_CUDA(cudaMemcpyAsync(c->stage_buf, buf_host, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (stage == UA3_STAGE_DNR)                     // DNR off: the firmware returns without touching bufferOut
+        UA3_CUDA(cudaMemcpyAsync(c->stage_buf + 4096, out_host, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    int launches = 0;
+    UA3_CUDA(rx_launch_stage(c->rx, stage, c->stage_buf, c->stage_buf + 4096, (uint32_t)n, channel, arg, c->stream, &launches));
+    c->launches += (uint64_t)launches;
+    if (stage == UA3_STAGE_DNR)
+        UA3_CUDA(cudaMemcpyAsync(out_host, c->stage_buf + 4096, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    else
+        UA3_CUDA(cudaMemcpyAsync(buf_host, c->stage_buf, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
 int ua3reo_rx_read_smeter(ua3reo_ctx* c, float* dst, int reset) {
     if (!c || !dst) return fail(UA3_E_INVAL, "ua3reo_rx_read_smeter: null argument");
     if (!c->rx_alloc) return fail(UA3_E_STATE, "ua3reo_rx_read_smeter: STM32 stage not enabled");
@@ -1183,7 +1208,7 @@ int ua3reo_duc_read_otr(ua3reo_ctx* c, uint32_t* dst) {
 void ua3reo_tx_defaults(ua3reo_tx_settings* s) {
     if (!s) return;
     std::memset(s, 0, sizeof *s);
-    s->mode = kModeUSB; s->rf_power = 20; s->filter_width = 2700; s->ssb_hpf_pass = 300;   // settings.c:33-94
+    s->mode = kModeUSB; s->rf_power = 20; s->volume = 20; s->filter_width = 2700; s->ssb_hpf_pass = 300;   // settings.c:33-94
 }
 
 int ua3reo_tx_enable(ua3reo_ctx* c, uint32_t max_blocks) {
@@ -1198,6 +1223,7 @@ int ua3reo_tx_enable(ua3reo_ctx* c, uint32_t max_blocks) {
     UA3_CUDA(dev_alloc(c, &t.mic, (size_t)c->n_ch * per_ch));
     UA3_CUDA(dev_alloc(c, &t.iq_f, (size_t)c->n_ch * per_ch));
     UA3_CUDA(dev_alloc(c, &t.iq_w, (size_t)c->n_ch * per_ch));
+    UA3_CUDA(dev_alloc(c, &t.loop_out, (size_t)c->n_ch * per_ch));
     UA3_CUDA(dev_alloc(c, &c->tx_flags, (size_t)c->n_ch));
     float T[513];
     cmsis_sin_table(T);
@@ -1285,6 +1311,19 @@ int ua3reo_tx_read_iq(ua3reo_ctx* c, int16_t* iq_words, float* iq_float, size_t 
                                    cudaMemcpyDeviceToHost, c->stream));
     if (n && iq_float)
         UA3_CUDA(cudaMemcpy2DAsync(iq_float, n * sizeof(float), c->tx.iq_f, stride * sizeof(float), n * sizeof(float), c->n_ch,
+                                   cudaMemcpyDeviceToHost, c->stream));
+    UA3_CUDA(cudaStreamSynchronize(c->stream));
+    return UA3_OK;
+}
+
+int ua3reo_tx_read_loopback(ua3reo_ctx* c, int32_t* dst, size_t n_blocks) {
+    if (!c || (!dst && n_blocks)) return fail(UA3_E_INVAL, "ua3reo_tx_read_loopback: null argument");
+    if (!c->tx_alloc) return fail(UA3_E_STATE, "ua3reo_tx_read_loopback: transmit audio not enabled");
+    if (n_blocks != c->last_tx_blocks) return fail(UA3_E_INVAL, "ua3reo_tx_read_loopback: n_blocks != blocks of last call");
+    UA3_CUDA(cudaSetDevice(c->device));
+    const size_t n = n_blocks * UA3_AUDIO_BLOCK * 2, stride = (size_t)c->tx.max_blocks * UA3_AUDIO_BLOCK * 2;
+    if (n)
+        UA3_CUDA(cudaMemcpy2DAsync(dst, n * sizeof(int32_t), c->tx.loop_out, stride * sizeof(int32_t), n * sizeof(int32_t), c->n_ch,
                                    cudaMemcpyDeviceToHost, c->stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
     return UA3_OK;

@@ -940,6 +940,87 @@ rx_fft_kernel(uint32_t n_frames, const RxParams* __restrict__ params, RxState* _
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stand-alone stages on a caller buffer, with the channel's state: the firmware's dc_filter(), DoAGC() and
+// processNoiseReduction() as entry points of their own (audio_filters.h:51, agc.h:9, noise_reduction.h:16).  One thread:
+// these are single-channel calls on 64..512 samples, kept for callers that use the functions individually.
+// ------------------------------------------------------------------------------------------------
+__global__ void rx_stage_kernel(int stage, float* __restrict__ buf, float* __restrict__ out, uint32_t n, const RxParams* __restrict__ params,
+                                RxState* __restrict__ state, uint32_t ch, int arg) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const RxParams& P = params[ch];
+    RxState& S = state[ch];
+    if (stage == 0) {                                                // dc_filter(buf, n, stateNum = arg) (audio_filters.c:358-373)
+        const float A1 = (float)(1.0 - 0.00048828125);
+        float dx = S.dc_x[arg], dy = S.dc_y[arg];
+        for (uint32_t i = 0; i < n; ++i) {
+            const float x = buf[i];
+            const float delta_x = x - dx;
+            const float a1y = A1 * dy;
+            const float y = delta_x + a1y;
+            dx = x; dy = y; buf[i] = y;
+        }
+        S.dc_x[arg] = dx; S.dc_y[arg] = dy;
+    } else if (stage == 1) {                                         // DoAGC(buf, n) (agc.c:21-67)
+        float agc_gain = S.agc_gain, agc_old = S.agc_gain_old;
+        float amax = buf[0];
+        for (uint32_t i = 1; i < n; ++i) if (amax < buf[i]) amax = buf[i];
+        if (amax == 0.0f) amax = 0.001f;
+        const float target = 7000.0f / amax;
+        if (target > agc_gain) {
+            float st = (target - agc_gain) / P.agc_step_up;
+            if (st > 1.0f) st = 1.0f;
+            agc_gain += st;
+        } else {
+            agc_gain -= (agc_gain - target) / P.agc_step_down;
+        }
+        if (agc_gain < 0.0f) agc_gain = 0.0f;
+        if ((agc_gain * amax) > 10000.0f) agc_gain = target;
+        if (!P.agc_on || P.mode == kModeDIGIL || P.mode == kModeDIGIU) agc_gain = 1.0f;
+        if (agc_old != agc_gain) {
+            float gstep = 0.0f;
+            if (agc_old > agc_gain) gstep = -(agc_old - agc_gain) / (float)(int)n;
+            if (agc_old < agc_gain) gstep = (agc_gain - agc_old) / (float)(int)n;
+            for (uint32_t i = 0; i < n; ++i) { agc_old += gstep; buf[i] = buf[i] * agc_old; }
+        } else {
+            for (uint32_t i = 0; i < n; ++i) buf[i] = buf[i] * agc_gain;
+        }
+        S.agc_gain = agc_gain; S.agc_gain_old = agc_old;
+    } else if (stage == 2) {                                         // processNoiseReduction(buf, out): 64 samples (noise_reduction.c:25-37)
+        if (!P.dnr_on) return;
+        uint32_t idx_old = S.lms_idx_old, idx_new = S.lms_idx_new;
+        float energy = S.lms_energy, x0 = S.lms_x0;
+        float win[kLmsTaps - 1 + kSubBlock];
+        for (int i = 0; i < kLmsTaps - 1; ++i) win[i] = S.lms_hist[i];
+        for (int i = 0; i < kSubBlock; ++i) { win[kLmsTaps - 1 + i] = buf[i]; S.lms_ref[idx_new + i] = buf[i]; }
+        for (int i = 0; i < kSubBlock; ++i) {
+            const float in = win[i + kLmsTaps - 1];
+            energy -= x0 * x0;
+            energy += in * in;
+            float acc = 0.0f;
+            for (int t = 0; t < kLmsTaps; ++t) acc += win[i + t] * S.lms_w[t];
+            out[i] = acc;
+            const float e = S.lms_ref[idx_old + i] - acc;
+            const float wg = (e * 0.000001f) / (energy + 0.000000119209289f);
+            for (int t = 0; t < kLmsTaps; ++t) S.lms_w[t] += wg * win[i + t];
+            x0 = win[i];
+        }
+        for (int i = 0; i < kLmsTaps - 1; ++i) S.lms_hist[i] = win[kSubBlock + i];
+        idx_old += kSubBlock;
+        if (idx_old >= 2 * kSubBlock) idx_old = 0;
+        idx_new = idx_old + kSubBlock;
+        if (idx_new >= 2 * kSubBlock) idx_new = 0;
+        S.lms_energy = energy; S.lms_x0 = x0; S.lms_idx_old = idx_old; S.lms_idx_new = idx_new;
+    }
+}
+
+cudaError_t rx_launch_stage(const RxBuffers& b, int stage, float* buf_dev, float* out_dev, uint32_t n, uint32_t ch, int arg, cudaStream_t st,
+                            int* launches) {
+    UA3_LAUNCH(rx_stage_kernel, 1, 32, 0, st, stage, buf_dev, out_dev, n, b.params, b.state, ch, arg);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void rx_clear_filters_kernel(RxState* __restrict__ state, const uint8_t* __restrict__ flags, uint32_t first,
                                         uint32_t n) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

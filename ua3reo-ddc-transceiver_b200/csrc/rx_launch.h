@@ -40,6 +40,8 @@ size_t rx_scratch_floats(uint32_t n_ch, uint32_t max_audio_blocks);
 size_t rx_fft_in_floats(uint32_t n_ch, uint32_t max_fft_frames);
 int rx_audio_sms(uint32_t n_ch);        // SMs the STM32 audio kernels can keep busy (16 warps per SM)
 cudaError_t rx_launch_fft(const RxBuffers& b, uint32_t start, uint32_t n_frames, cudaStream_t st, int* launches);
+cudaError_t rx_launch_stage(const RxBuffers& b, int stage, float* buf_dev, float* out_dev, uint32_t n, uint32_t ch, int arg, cudaStream_t st,
+                            int* launches);
 cudaError_t rx_launch_clear(const RxBuffers& b, const uint8_t* flags_dev, uint32_t first, uint32_t n, cudaStream_t st,
                             int* launches);
 cudaError_t rx_launch_init_state(const RxBuffers& b, cudaStream_t st, int* launches);

@@ -46,7 +46,7 @@ UA3_D float table_sin(float x, float quarter) {
 __global__ void __launch_bounds__(32)
 tx_audio_kernel(const int16_t* __restrict__ mic, uint32_t n_blocks, uint32_t mic_ch_stride, const TxParams* __restrict__ params,
                 TxState* __restrict__ state, uint32_t n_ch, float* __restrict__ iq_f, int16_t* __restrict__ iq_w,
-                uint32_t out_ch_stride) {
+                int32_t* __restrict__ loop_out, uint32_t out_ch_stride) {
     __shared__ float s_i[kTxHilbTaps - 1 + kAudioBlock];     // [200 history | 192 new] input of the I-buffer FIR
     __shared__ float s_q[kTxHilbTaps - 1 + kAudioBlock];
     __shared__ float s_oi[kAudioBlock], s_oq[kAudioBlock];
@@ -171,11 +171,16 @@ tx_audio_kernel(const int16_t* __restrict__ mic, uint32_t n_blocks, uint32_t mic
         // ---- mute, output (float as left in FPGA_Audio_SendBuffer_I/Q, int16 as sendiq puts it on the wire) ----
         float* of = iq_f + (size_t)ch * out_ch_stride * 2 + (size_t)blk * kAudioBlock * 2;
         int16_t* ow = iq_w + (size_t)ch * out_ch_stride * 2 + (size_t)blk * kAudioBlock * 2;
+        int32_t* ol = loop_out + (size_t)ch * out_ch_stride * 2 + (size_t)blk * kAudioBlock * 2;
+        const bool loopback = (mode == kModeLoopback) && !P.tune;    // :228: the block goes to the codec, not to the FPGA
         for (int i = lane; i < kAudioBlock; i += 32) {
             float I = s_oi[i], Q = s_oq[i];
             if (P.mute && !P.tune) { I = I * 0.0f; Q = Q * 0.0f; }
+            int32_t l = 0;
+            if (loopback) { I = I * P.loop_volume; l = (int32_t)I; }  // arm_scale_f32 by Volume / 50, float -> int32, right = left (:231-236)
             of[2 * i] = I; of[2 * i + 1] = Q;
             ow[2 * i] = (int16_t)(int32_t)I; ow[2 * i + 1] = (int16_t)(int32_t)Q;
+            ol[2 * i] = l; ol[2 * i + 1] = l;
         }
         __syncwarp();
     }
@@ -234,7 +239,7 @@ cudaError_t tx_launch_clear(const TxBuffers& b, const uint8_t* flags_dev, uint32
 cudaError_t tx_launch_audio(const TxBuffers& b, uint32_t n_blocks, cudaStream_t st, int* launches) {
     if (!n_blocks) return cudaSuccess;
     UA3_LAUNCH(tx_audio_kernel, b.n_ch, 32, 0, st, b.mic, n_blocks, b.max_blocks * (uint32_t)kAudioBlock * 2u, b.params, b.state,
-               b.n_ch, b.iq_f, b.iq_w, b.max_blocks * (uint32_t)kAudioBlock);
+               b.n_ch, b.iq_f, b.iq_w, b.loop_out, b.max_blocks * (uint32_t)kAudioBlock);
     if (launches) *launches += 1;
     return cudaGetLastError();
 }

@@ -14,6 +14,7 @@ struct TxBuffers {
     int16_t* mic = nullptr;         // [n_ch][max_blocks * 192][2]  codec samples L, R
     float* iq_f = nullptr;          // [n_ch][max_blocks * 192][2]  I, Q as left in FPGA_Audio_SendBuffer_I/Q
     int16_t* iq_w = nullptr;        // [n_ch][max_blocks * 192][2]  I, Q as FPGA_fpgadata_sendiq() converts them
+    int32_t* loop_out = nullptr;    // [n_ch][max_blocks * 192][2]  TRX_MODE_LOOPBACK: what goes to the codec instead (L, R; audio_processor.c:228-249)
 };
 
 cudaError_t tx_upload_constants(const float* sin_table);

@@ -12,6 +12,7 @@ struct TxParams {
     uint8_t lpf_on, hpf_set, pad[2];
     float amplitude;                      // TRX.RF_Power / 100.0f * MAX_TX_AMPLITUDE (audio_processor.c:65)
     float fm_index;                       // ModulateFM's modulation_index for the channel's Filter_Width (:597-605)
+    float loop_volume;                    // (float32_t)TRX.Volume / 50.0f: the loopback branch's output volume (audio_processor.c:231)
     float lpf_k[kLpfMax], lpf_v[kLpfMax + 1], hpf_k[kHpfStages], hpf_v[kHpfStages + 1];
 };
 

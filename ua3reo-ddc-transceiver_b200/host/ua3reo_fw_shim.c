@@ -10,6 +10,7 @@
  *   initAudioProcessor()                 audio_processor.c:55-59          ua3reo_create + ua3reo_rx_enable + ua3reo_tx_enable
  *   ReinitAudioFilters()                 audio_filters.c:141-339          ua3reo_rx_set / ua3reo_tx_set (tables reselected, states cleared)
  *   InitNotchFilter()                    audio_filters.c:341-346          ua3reo_rx_set_notch (coefficients only)
+ *   dc_filter() / DoAGC() / processNoiseReduction()   audio_filters.c:358-373, agc.c:21-67, noise_reduction.c:25-37   ua3reo_rx_stage
  *   processRxAudio()                     audio_processor.c:275-434        ua3reo_rx_push_frames(192) + ua3reo_rx_read_audio/_usb/_smeter/_cw
  *   processTxAudio()                     audio_processor.c:61-273         ua3reo_tx_process(1) + ua3reo_tx_read_iq
  *   FFT_Init() / FFT_doFFT()             fft.c:185-328                    second one-channel context: ua3reo_rx_push_frames(512) + read_spectra/_waterfall
@@ -32,6 +33,7 @@
 #include "audio_processor.h"
 #include "audio_filters.h"
 #include "agc.h"
+#include "noise_reduction.h"
 #include "cw_decoder.h"
 #include "functions.h"
 #include "usbd_audio_if.h"
@@ -127,11 +129,11 @@ static void gather_tx(ua3reo_tx_settings *s)
     s->mode = (uint8_t)TRX_getMode();
     s->filter_width = (uint16_t)CurrentVFO()->Filter_Width;
     s->ssb_hpf_pass = TRX.SSB_HPF_pass;
-    s->mute = TRX.Mute; s->tune = TRX_tune; s->rf_power = TRX.RF_Power;
+    s->mute = TRX.Mute; s->tune = TRX_tune; s->rf_power = TRX.RF_Power; s->volume = TRX.Volume;
     s->key_down = (TRX_key_serial || TRX_ptt_hard || TRX_key_hard) ? 1 : 0;      /* audio_processor.c:146 */
 }
 
-static bool tx_mode_ok(uint8_t mode) { return mode != TRX_MODE_NO_TX && mode != TRX_MODE_LOOPBACK; }
+static bool tx_mode_ok(uint8_t mode) { (void)mode; return true; }      /* NO_TX and LOOPBACK run the `default:` branch (audio_processor.c:141-213) */
 
 /* full = what TRX_setMode()/ReinitAudioFilters() do; otherwise only the per-call fields, and only when they moved */
 static void apply_rx(bool full)
@@ -189,6 +191,28 @@ void InitAGC(void)                       /* agc.c:14-19: step sizes from TRX.Agc
     rx_last.agc_speed = latched_agc_speed;
 }
 void InitNoiseReduction(void) {}         /* noise_reduction.c:18-23: state is created zeroed with the context */
+
+/* The sub-stages the firmware exports as functions of their own (audio_filters.h:51, agc.h:9, noise_reduction.h:16): on the
+ * caller's buffer, with channel 0's state on the device - the same state processRxAudio() uses, as in the firmware. */
+void dc_filter(float32_t *agcBuffer, int16_t blockSize, uint8_t stateNum)
+{
+    ensure_contexts();
+    CHECK(ua3reo_rx_stage(rx_ctx, 0, UA3_STAGE_DC_FILTER, agcBuffer, NULL, (size_t)blockSize, stateNum));
+}
+
+void DoAGC(float32_t *agcBuffer, int16_t blockSize)
+{
+    ensure_contexts();
+    apply_rx(false);                     /* TRX.AGC and the mode are read on every call (agc.c:46) */
+    CHECK(ua3reo_rx_stage(rx_ctx, 0, UA3_STAGE_AGC, agcBuffer, NULL, (size_t)blockSize, 0));
+}
+
+void processNoiseReduction(float32_t *bufferIn, float32_t *bufferOut)
+{
+    ensure_contexts();
+    apply_rx(false);                     /* `if (!TRX.DNR) return;` (noise_reduction.c:27) */
+    CHECK(ua3reo_rx_stage(rx_ctx, 0, UA3_STAGE_DNR, bufferIn, bufferOut, NOISE_REDUCTION_BLOCK_SIZE, 0));
+}
 
 void InitAudioFilters(void)              /* audio_filters.c:124-139: lattice/biquad instances, then InitNotchFilter() */
 {
@@ -280,10 +304,6 @@ void processTxAudio(void)
         if ((dma_index % 2) == 1) dma_index--;
         readHalfFromCircleBuffer32((uint32_t *)&CODEC_Audio_Buffer_TX[0], (uint32_t *)&Processor_AudioBuffer_A[0], dma_index, CODEC_AUDIO_BUFFER_SIZE);
     }
-    if (!tx_mode_ok((uint8_t)TRX_getMode())) {                    /* loopback / no-TX have no transmit branch in the library */
-        fprintf(stderr, "ua3reo_fw_shim: processTxAudio in mode %d is outside the accelerated path\n", (int)TRX_getMode());
-        abort();
-    }
     static int16_t mic[FPGA_AUDIO_BUFFER_SIZE];
     for (int i = 0; i < FPGA_AUDIO_BUFFER_SIZE; i++) mic[i] = (int16_t)Processor_AudioBuffer_A[i];   /* :88-89 */
     apply_tx(false);
@@ -291,14 +311,27 @@ void processTxAudio(void)
     static float iq[FPGA_AUDIO_BUFFER_SIZE];
     CHECK(ua3reo_tx_read_iq(rx_ctx, NULL, iq, 1));
     CHECK(ua3reo_sync(rx_ctx));
-    const int half = FPGA_Audio_Buffer_State ? FPGA_AUDIO_BUFFER_HALF_SIZE : 0;                       /* :253-270 */
     for (int i = 0; i < FPGA_AUDIO_BUFFER_HALF_SIZE; i++) {
         FPGA_Audio_Buffer_I_tmp[i] = iq[2 * i];
         FPGA_Audio_Buffer_Q_tmp[i] = iq[2 * i + 1];
-        FPGA_Audio_SendBuffer_I[half + i] = iq[2 * i];
-        FPGA_Audio_SendBuffer_Q[half + i] = iq[2 * i + 1];
     }
-    if (FPGA_Audio_Buffer_State) AUDIOPROC_TXA_samples++; else AUDIOPROC_TXB_samples++;
+    if (TRX_getMode() == TRX_MODE_LOOPBACK && !TRX_tune) {        /* :228-249: to the codec instead of the FPGA */
+        CHECK(ua3reo_tx_read_loopback(rx_ctx, Processor_AudioBuffer_A, 1));
+        if (WM8731_DMA_state) {
+            memcpy(&CODEC_Audio_Buffer_RX[FPGA_AUDIO_BUFFER_SIZE], Processor_AudioBuffer_A, sizeof(int32_t) * FPGA_AUDIO_BUFFER_SIZE);
+            AUDIOPROC_TXA_samples++;
+        } else {
+            memcpy(&CODEC_Audio_Buffer_RX[0], Processor_AudioBuffer_A, sizeof(int32_t) * FPGA_AUDIO_BUFFER_SIZE);
+            AUDIOPROC_TXB_samples++;
+        }
+    } else {
+        const int half = FPGA_Audio_Buffer_State ? FPGA_AUDIO_BUFFER_HALF_SIZE : 0;                   /* :253-270 */
+        for (int i = 0; i < FPGA_AUDIO_BUFFER_HALF_SIZE; i++) {
+            FPGA_Audio_SendBuffer_I[half + i] = iq[2 * i];
+            FPGA_Audio_SendBuffer_Q[half + i] = iq[2 * i + 1];
+        }
+        if (FPGA_Audio_Buffer_State) AUDIOPROC_TXA_samples++; else AUDIOPROC_TXB_samples++;
+    }
     Processor_NeedTXBuffer = false;
     Processor_NeedRXBuffer = false;
 }
