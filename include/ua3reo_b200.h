@@ -232,15 +232,17 @@ int ua3reo_rx_read_cw(ua3reo_ctx *ctx, float *dst_host, size_t n_blocks);
  * a 192-sample block - adaptive threshold, 6 ms noise blanker, dit/dah and gap classification against a rolling dit time,
  * Morse table (:172-247).  One call per audio block and channel with that block's ua3reo_rx_read_cw() value and the
  * HAL_GetTick() time in ms (4 ms per block at 48 kHz); decoded characters (a space for a word gap) are written to out
- * (up to out_cap) and their number is returned; `wpm` is CW_Decoder_WPM.  Pure host function, fields named after the
- * firmware's statics. */
+ * (up to out_cap) and their number is returned; `wpm` is CW_Decoder_WPM.  Pure host function. */
 typedef struct ua3reo_cw_decoder {
-    float magnitudelimit, magnitudelimit_low;
-    uint8_t realstate, realstatebefore, filteredstate, filteredstatebefore, stop;
+    float level_hi, level_lo;            /* adaptive keyed / idle magnitude levels (magnitudelimit, magnitudelimit_low) */
+    uint8_t raw, raw_prev;               /* slicer output this block / last block */
+    uint8_t key, key_prev;               /* debounced key state */
+    uint8_t flushed;                     /* the pending letter has been written out after a long silence */
     uint8_t reserved[1];
-    uint16_t wpm;
-    int64_t laststarttime, starttimehigh, highduration, startttimelow, lowduration, hightimesavg, lasthighduration;
-    char code[24];
+    uint16_t wpm;                        /* CW_Decoder_WPM */
+    int64_t t_raw_edge, t_key_down, t_key_up;   /* ms timestamps of the last slicer edge / key-down / key-up */
+    int64_t mark_ms, space_ms, dit_ms;   /* last key-down and key-up durations, rolling dit length */
+    char code[24];                       /* elements of the letter in progress, '.' and '-' */
 } ua3reo_cw_decoder;
 void ua3reo_cw_decoder_init(ua3reo_cw_decoder *st);
 int ua3reo_cw_decoder_step(ua3reo_cw_decoder *st, float magnitude, uint32_t tick_ms, char *out, int out_cap);

@@ -173,11 +173,10 @@ def phrase_from_frequency(freq_hz, lib=None):
 
 class CwDecoder(ctypes.Structure):
     """Host half of the CW decoder (ua3reo_cw_decoder): feed one Goertzel magnitude per 192-sample block (Receiver.read_cw)."""
-    _fields_ = ([("magnitudelimit", ctypes.c_float), ("magnitudelimit_low", ctypes.c_float)] +
-                [(n, ctypes.c_uint8) for n in ("realstate", "realstatebefore", "filteredstate", "filteredstatebefore", "stop", "reserved")] +
+    _fields_ = ([("level_hi", ctypes.c_float), ("level_lo", ctypes.c_float)] +
+                [(n, ctypes.c_uint8) for n in ("raw", "raw_prev", "key", "key_prev", "flushed", "reserved")] +
                 [("wpm", ctypes.c_uint16)] +
-                [(n, ctypes.c_int64) for n in ("laststarttime", "starttimehigh", "highduration", "startttimelow", "lowduration",
-                                               "hightimesavg", "lasthighduration")] +
+                [(n, ctypes.c_int64) for n in ("t_raw_edge", "t_key_down", "t_key_up", "mark_ms", "space_ms", "dit_ms")] +
                 [("code", ctypes.c_char * 24)])
 
     def __init__(self, lib=None):
