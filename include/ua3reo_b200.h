@@ -341,6 +341,36 @@ int ua3reo_tx_read_loopback(ua3reo_ctx *ctx, int32_t *dst_host, size_t n_blocks)
 /* Runs the DUC over the I/Q words of the last ua3reo_tx_process() without leaving the device. */
 int ua3reo_tx_feed_duc(ua3reo_ctx *ctx);
 
+/* ---------------------------------------------------------------------------------------------
+ * Several GPUs from one C host: a bank shards its channels over devices in contiguous slabs (no term of the path couples
+ * two channels) and fans every ADC block out to them.  The fan-out is cudaMemcpyPeerAsync from the ingest
+ * device - copy engines over NVLink, no SM involved, so it runs under the previous block's kernels (a collective KERNEL
+ * cannot: a front CTA owns its whole SM).  Results stay sharded on the devices and are read slab by slab, every device
+ * over its own PCIe link.  (bench.py is the multi-PROCESS form of the same thing, one rank per GPU with an NCCL broadcast,
+ * as its launch contract prescribes.)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ua3reo_bank ua3reo_bank;
+/* n_devices contexts on devices[0..n_devices) (a device may be named twice), n_channels in total, slabs differing by at
+ * most one channel; devices[0] ingests the ADC stream. */
+int ua3reo_bank_create(int n_devices, const int *devices, uint32_t n_channels, uint32_t max_block_samples, ua3reo_bank **out);
+int ua3reo_bank_destroy(ua3reo_bank *bank);
+int ua3reo_bank_n_devices(const ua3reo_bank *bank);
+/* the context of device slot i and its channel slab [*first, *first + *count): every per-channel call of this header
+ * (ua3reo_rx_set, ua3reo_set_fcw, the reads ...) can be made on it with slab-relative channel numbers */
+int ua3reo_bank_context(ua3reo_bank *bank, int i, ua3reo_ctx **ctx, uint32_t *first, uint32_t *count);
+/* bank-wide forms of the calls a host loop needs: tuning words and RX settings by global channel number, push, reads into
+ * [n_channels][...] host arrays (each device writes its slab), sync */
+int ua3reo_bank_set_fcw(ua3reo_bank *bank, uint32_t first, uint32_t n, const uint32_t *fcw22);
+int ua3reo_bank_rx_enable(ua3reo_bank *bank, int enable);
+int ua3reo_bank_rx_set(ua3reo_bank *bank, uint32_t first, uint32_t n, const ua3reo_rx_settings *settings);
+/* adc_host: n samples in host memory (pinned for an asynchronous copy); every device processes all of them for its slab */
+int ua3reo_bank_push(ua3reo_bank *bank, const int16_t *adc_host, size_t n, size_t *frames_out);
+int ua3reo_bank_read_frames(ua3reo_bank *bank, uint8_t *dst_host, size_t n_frames);
+int ua3reo_bank_rx_counts(ua3reo_bank *bank, size_t *audio_blocks, size_t *fft_frames);
+int ua3reo_bank_rx_read_audio(ua3reo_bank *bank, int32_t *dst_host, size_t n_blocks);
+int ua3reo_bank_rx_read_spectra(ua3reo_bank *bank, float *dst_host, size_t n_frames);
+int ua3reo_bank_sync(ua3reo_bank *bank);
+
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline):
  * after ua3reo_profile_begin(ctx, max_blocks) each processed ADC block records an event before and
  * after every kernel; ua3reo_profile_end() waits for the stream and sums the elapsed times per

@@ -68,6 +68,10 @@ static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dp, const void* s, s
     return 0;
 }
 template <class T> static inline cudaError_t cudaMemcpyToSymbol(T& sym, const void* src, size_t n) { memcpy((void*)&sym, src, n); return 0; }
+static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t) { memmove(d, s, n); return 0; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 0; return 0; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return 0; }
+enum { cudaErrorPeerAccessAlreadyEnabled = 704 };
 static inline cudaError_t cudaEventCreate(cudaEvent_t*) { return 0; }
 enum { cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t*, int) { return 0; }

@@ -130,6 +130,19 @@ def _bind(lib):
         "ua3reo_tx_read_iq": (c.c_int, [vp, vp, vp, sz]),
         "ua3reo_tx_read_loopback": (c.c_int, [vp, vp, sz]),
         "ua3reo_tx_feed_duc": (c.c_int, [vp]),
+        "ua3reo_bank_create": (c.c_int, [c.c_int, c.POINTER(c.c_int), u32, u32, c.POINTER(vp)]),
+        "ua3reo_bank_destroy": (c.c_int, [vp]),
+        "ua3reo_bank_n_devices": (c.c_int, [vp]),
+        "ua3reo_bank_context": (c.c_int, [vp, c.c_int, c.POINTER(vp), c.POINTER(u32), c.POINTER(u32)]),
+        "ua3reo_bank_set_fcw": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_bank_rx_enable": (c.c_int, [vp, c.c_int]),
+        "ua3reo_bank_rx_set": (c.c_int, [vp, u32, u32, vp]),
+        "ua3reo_bank_push": (c.c_int, [vp, vp, sz, c.POINTER(sz)]),
+        "ua3reo_bank_read_frames": (c.c_int, [vp, vp, sz]),
+        "ua3reo_bank_rx_counts": (c.c_int, [vp, c.POINTER(sz), c.POINTER(sz)]),
+        "ua3reo_bank_rx_read_audio": (c.c_int, [vp, vp, sz]),
+        "ua3reo_bank_rx_read_spectra": (c.c_int, [vp, vp, sz]),
+        "ua3reo_bank_sync": (c.c_int, [vp]),
         "ua3reo_sync": (c.c_int, [vp]),
         "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_launch_count": (c.c_uint64, [vp]),
@@ -526,6 +539,7 @@ class Receiver:
         assert a.ndim == 3 and a.shape[0] == self.n_channels and a.shape[1] % AUDIO_BLOCK == 0 and a.shape[2] == 2
         nb = a.shape[1] // AUDIO_BLOCK
         self._chk(self.lib.ua3reo_tx_process(self._h, a.ctypes.data, nb))
+        self._tx_blocks = nb
         w = np.empty(a.shape, np.int16)
         f = np.empty(a.shape, np.float32)
         self._chk(self.lib.ua3reo_tx_read_iq(self._h, w.ctypes.data, f.ctypes.data, nb))
@@ -539,7 +553,7 @@ class Receiver:
 
     def tx_feed_duc(self):
         self._chk(self.lib.ua3reo_tx_feed_duc(self._h))
-        self._last_tx = None
+        self._last_tx = getattr(self, "_tx_blocks", 0) * AUDIO_BLOCK
 
     def sync(self):
         self._chk(self.lib.ua3reo_sync(self._h))
@@ -573,6 +587,82 @@ class Receiver:
 
     def launch_count(self):
         return int(self.lib.ua3reo_launch_count(self._h))
+
+
+class Bank:
+    """Channels sharded over several devices from ONE host process (ua3reo_bank_*): the ADC block is fanned out by copy
+    engines (cudaMemcpyPeerAsync), results are read slab by slab into [n_channels, ...] arrays."""
+
+    def __init__(self, devices, n_channels, max_block_samples=1 << 20, _lib_path=None):
+        self.lib = load_library(_lib_path)
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        h = ctypes.c_void_p()
+        self._h = None
+        self._chk(self.lib.ua3reo_bank_create(len(devices), devs, int(n_channels), int(max_block_samples), ctypes.byref(h)))
+        self._h = h
+        self.n_channels = int(n_channels)
+        self.last_frames = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise UA3Error("ua3reo error %d: %s" % (rc, self.lib.ua3reo_last_error().decode()))
+
+    def close(self):
+        if self._h is not None:
+            self.lib.ua3reo_bank_destroy(self._h)
+            self._h = None
+
+    def slabs(self):
+        out = []
+        for i in range(self.lib.ua3reo_bank_n_devices(self._h)):
+            f, n = ctypes.c_uint32(), ctypes.c_uint32()
+            self._chk(self.lib.ua3reo_bank_context(self._h, i, None, ctypes.byref(f), ctypes.byref(n)))
+            out.append((int(f.value), int(n.value)))
+        return out
+
+    def set_fcw(self, fcw, first=0):
+        a = np.ascontiguousarray(fcw, dtype=np.uint32)
+        self._chk(self.lib.ua3reo_bank_set_fcw(self._h, int(first), a.size, a.ctypes.data))
+
+    def rx_enable(self, on=True):
+        self._chk(self.lib.ua3reo_bank_rx_enable(self._h, 1 if on else 0))
+
+    def rx_set(self, settings, first=0):
+        arr = (RxSettings * len(settings))(*settings)
+        self._chk(self.lib.ua3reo_bank_rx_set(self._h, int(first), len(settings), ctypes.cast(arr, ctypes.c_void_p)))
+
+    def push(self, adc):
+        a = np.ascontiguousarray(adc, dtype=np.int16)
+        self._keep = a
+        n = ctypes.c_size_t(0)
+        self._chk(self.lib.ua3reo_bank_push(self._h, a.ctypes.data, a.size, ctypes.byref(n)))
+        self.last_frames = int(n.value)
+        return self.last_frames
+
+    def read_frames(self):
+        out = np.empty((self.n_channels, self.last_frames, FRAME_BYTES), np.uint8)
+        self._chk(self.lib.ua3reo_bank_read_frames(self._h, out.ctypes.data, self.last_frames))
+        return out
+
+    def rx_counts(self):
+        a, f = ctypes.c_size_t(), ctypes.c_size_t()
+        self._chk(self.lib.ua3reo_bank_rx_counts(self._h, ctypes.byref(a), ctypes.byref(f)))
+        return int(a.value), int(f.value)
+
+    def read_audio(self):
+        nb, _ = self.rx_counts()
+        out = np.empty((self.n_channels, nb, 2 * AUDIO_BLOCK), np.int32)
+        self._chk(self.lib.ua3reo_bank_rx_read_audio(self._h, out.ctypes.data, nb))
+        return out
+
+    def read_spectra(self):
+        _, nf = self.rx_counts()
+        out = np.empty((self.n_channels, nf, FFT_BINS), np.float32)
+        self._chk(self.lib.ua3reo_bank_rx_read_spectra(self._h, out.ctypes.data, nf))
+        return out
+
+    def sync(self):
+        self._chk(self.lib.ua3reo_bank_sync(self._h))
 
 
 def frames_to_iq(frames):

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <new>
 #include <string>
 #include <vector>
@@ -1343,6 +1344,212 @@ int ua3reo_tx_feed_duc(ua3reo_ctx* c) {
     UA3_CUDA(duc_launch(c->duc, (uint32_t)n, c->stream, &launches));
     c->launches += (uint64_t)launches;
     c->last_tx = n;
+    return UA3_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// multi-device bank (one host process)
+// ---------------------------------------------------------------------------------------------------------------------
+struct ua3reo_bank {
+    std::vector<ua3reo_ctx*> ctx;
+    std::vector<uint32_t> first, count;
+    uint32_t n_total = 0, max_block = 0;
+    std::vector<int16_t*> adc[2];            // [slot][device slot] block buffers; slot alternates with the push number
+    std::vector<cudaStream_t> fan;           // fan-out stream per device slot (on that device)
+    std::vector<cudaEvent_t> ev_ready[2];    // block has arrived in adc[slot][i]
+    std::vector<cudaEvent_t> ev_free[2];     // the push that read adc[slot][i] has finished
+    std::vector<uint8_t> used[2];
+    cudaEvent_t ev_in[2] = {nullptr, nullptr};   // host -> ingest device copy done
+    uint64_t n_push = 0;
+};
+
+static void bank_slab(uint32_t n_total, int rank, int world, uint32_t* lo, uint32_t* n) {
+    const uint32_t base = n_total / (uint32_t)world, rem = n_total % (uint32_t)world;
+    *lo = (uint32_t)rank * base + std::min<uint32_t>((uint32_t)rank, rem);
+    *n = base + ((uint32_t)rank < rem ? 1u : 0u);
+}
+
+int ua3reo_bank_destroy(ua3reo_bank* b) {
+    if (!b) return UA3_OK;
+    for (size_t i = 0; i < b->ctx.size(); ++i) {
+        if (!b->ctx[i]) continue;
+        cudaSetDevice(b->ctx[i]->device);
+        if (i < b->fan.size() && b->fan[i]) { cudaStreamSynchronize(b->fan[i]); cudaStreamDestroy(b->fan[i]); }
+        for (int s = 0; s < 2; ++s) {
+            if (i < b->adc[s].size() && b->adc[s][i]) cudaFree(b->adc[s][i]);
+            if (i < b->ev_ready[s].size() && b->ev_ready[s][i]) cudaEventDestroy(b->ev_ready[s][i]);
+            if (i < b->ev_free[s].size() && b->ev_free[s][i]) cudaEventDestroy(b->ev_free[s][i]);
+        }
+    }
+    if (!b->ctx.empty() && b->ctx[0]) { cudaSetDevice(b->ctx[0]->device); for (int s = 0; s < 2; ++s) if (b->ev_in[s]) cudaEventDestroy(b->ev_in[s]); }
+    for (ua3reo_ctx* c : b->ctx) ctx_free(c);
+    delete b;
+    return UA3_OK;
+}
+
+int ua3reo_bank_create(int n_devices, const int* devices, uint32_t n_channels, uint32_t max_block_samples, ua3reo_bank** out) {
+    if (!out || !devices || n_devices < 1 || n_channels < (uint32_t)n_devices) return fail(UA3_E_INVAL, "ua3reo_bank_create: bad arguments");
+    *out = nullptr;
+    if (max_block_samples == 0) max_block_samples = 1u << 20;
+    ua3reo_bank* b = new (std::nothrow) ua3reo_bank;
+    if (!b) return fail(UA3_E_INVAL, "out of host memory");
+    b->n_total = n_channels; b->max_block = max_block_samples;
+    b->ctx.assign((size_t)n_devices, nullptr);
+    b->first.assign((size_t)n_devices, 0); b->count.assign((size_t)n_devices, 0);
+    b->fan.assign((size_t)n_devices, nullptr);
+    for (int s = 0; s < 2; ++s) {
+        b->adc[s].assign((size_t)n_devices, nullptr);
+        b->ev_ready[s].assign((size_t)n_devices, nullptr); b->ev_free[s].assign((size_t)n_devices, nullptr);
+        b->used[s].assign((size_t)n_devices, 0);
+    }
+#define UA3_BTRY(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ua3reo_bank_destroy(b); return fail(UA3_E_CUDA, what, e__); } } while (0)
+    for (int i = 0; i < n_devices; ++i) {
+        bank_slab(n_channels, i, n_devices, &b->first[(size_t)i], &b->count[(size_t)i]);
+        const int rc = ua3reo_create(devices[i], b->count[(size_t)i], max_block_samples, &b->ctx[(size_t)i]);
+        if (rc != UA3_OK) { const std::string keep = g_err; ua3reo_bank_destroy(b); g_err = keep; return rc; }
+        UA3_BTRY(cudaSetDevice(devices[i]), "cudaSetDevice");
+        UA3_BTRY(cudaStreamCreateWithFlags(&b->fan[(size_t)i], cudaStreamNonBlocking), "cudaStreamCreate");
+        for (int s = 0; s < 2; ++s) {
+            UA3_BTRY(cudaMalloc((void**)&b->adc[s][(size_t)i], (size_t)max_block_samples * sizeof(int16_t)), "cudaMalloc");
+            UA3_BTRY(cudaEventCreateWithFlags(&b->ev_ready[s][(size_t)i], cudaEventDisableTiming), "cudaEventCreate");
+            UA3_BTRY(cudaEventCreateWithFlags(&b->ev_free[s][(size_t)i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+        if (i > 0 && devices[i] != devices[0]) {            // direct NVLink path for the fan-out; "already enabled" is fine
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) == cudaSuccess && can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[0], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) UA3_BTRY(e, "cudaDeviceEnablePeerAccess");
+                (void)cudaGetLastError();
+            }
+        }
+    }
+    UA3_BTRY(cudaSetDevice(devices[0]), "cudaSetDevice");
+    for (int s = 0; s < 2; ++s) UA3_BTRY(cudaEventCreateWithFlags(&b->ev_in[s], cudaEventDisableTiming), "cudaEventCreate");
+#undef UA3_BTRY
+    *out = b;
+    return UA3_OK;
+}
+
+int ua3reo_bank_n_devices(const ua3reo_bank* b) { return b ? (int)b->ctx.size() : 0; }
+
+int ua3reo_bank_context(ua3reo_bank* b, int i, ua3reo_ctx** ctx, uint32_t* first, uint32_t* count) {
+    if (!b || i < 0 || (size_t)i >= b->ctx.size()) return fail(UA3_E_INVAL, "ua3reo_bank_context: device slot");
+    if (ctx) *ctx = b->ctx[(size_t)i];
+    if (first) *first = b->first[(size_t)i];
+    if (count) *count = b->count[(size_t)i];
+    return UA3_OK;
+}
+
+// applies fn(ctx, slab-relative first, n, global offset) to the part of [first, first + n) each device owns
+static int bank_route(ua3reo_bank* b, uint32_t first, uint32_t n, const std::function<int(ua3reo_ctx*, uint32_t, uint32_t, uint32_t)>& fn) {
+    if (!b || first > b->n_total || n > b->n_total - first) return fail(UA3_E_INVAL, "bank: channel range");
+    for (size_t i = 0; i < b->ctx.size(); ++i) {
+        const uint32_t lo = std::max(first, b->first[i]), hi = std::min(first + n, b->first[i] + b->count[i]);
+        if (lo >= hi) continue;
+        const int rc = fn(b->ctx[i], lo - b->first[i], hi - lo, lo - first);
+        if (rc != UA3_OK) return rc;
+    }
+    return UA3_OK;
+}
+
+int ua3reo_bank_set_fcw(ua3reo_bank* b, uint32_t first, uint32_t n, const uint32_t* fcw22) {
+    if (!fcw22) return fail(UA3_E_INVAL, "ua3reo_bank_set_fcw: null argument");
+    return bank_route(b, first, n, [&](ua3reo_ctx* c, uint32_t f, uint32_t m, uint32_t off) { return ua3reo_set_fcw(c, f, m, fcw22 + off); });
+}
+
+int ua3reo_bank_rx_enable(ua3reo_bank* b, int enable) {
+    if (!b) return fail(UA3_E_INVAL, "null bank");
+    for (ua3reo_ctx* c : b->ctx) { const int rc = ua3reo_rx_enable(c, enable); if (rc != UA3_OK) return rc; }
+    return UA3_OK;
+}
+
+int ua3reo_bank_rx_set(ua3reo_bank* b, uint32_t first, uint32_t n, const ua3reo_rx_settings* settings) {
+    if (!settings) return fail(UA3_E_INVAL, "ua3reo_bank_rx_set: null argument");
+    return bank_route(b, first, n, [&](ua3reo_ctx* c, uint32_t f, uint32_t m, uint32_t off) { return ua3reo_rx_set(c, f, m, settings + off); });
+}
+
+int ua3reo_bank_push(ua3reo_bank* b, const int16_t* adc_host, size_t n, size_t* frames_out) {
+    if (!b || (!adc_host && n)) return fail(UA3_E_INVAL, "ua3reo_bank_push: null argument");
+    if (n > b->max_block) return fail(UA3_E_TOOBIG, "ua3reo_bank_push: block exceeds max_block_samples");
+    const int s = (int)(b->n_push & 1);
+    const size_t bytes = n * sizeof(int16_t);
+    ua3reo_ctx* c0 = b->ctx[0];
+    // ingest: host -> device 0, on device 0's fan-out stream, once the push that last read this slot is through
+    UA3_CUDA(cudaSetDevice(c0->device));
+    if (b->used[s][0]) UA3_CUDA(cudaStreamWaitEvent(b->fan[0], b->ev_free[s][0], 0));
+    if (n) UA3_CUDA(cudaMemcpyAsync(b->adc[s][0], adc_host, bytes, cudaMemcpyHostToDevice, b->fan[0]));
+    UA3_CUDA(cudaEventRecord(b->ev_in[s], b->fan[0]));
+    UA3_CUDA(cudaEventRecord(b->ev_ready[s][0], b->fan[0]));
+    // fan-out: copy engines, device 0 -> device i, each on the destination's own stream
+    for (size_t i = 1; i < b->ctx.size(); ++i) {
+        UA3_CUDA(cudaSetDevice(b->ctx[i]->device));
+        UA3_CUDA(cudaStreamWaitEvent(b->fan[i], b->ev_in[s], 0));
+        if (b->used[s][i]) UA3_CUDA(cudaStreamWaitEvent(b->fan[i], b->ev_free[s][i], 0));
+        if (n) UA3_CUDA(cudaMemcpyPeerAsync(b->adc[s][i], b->ctx[i]->device, b->adc[s][0], c0->device, bytes, b->fan[i]));
+        UA3_CUDA(cudaEventRecord(b->ev_ready[s][i], b->fan[i]));
+    }
+    // every device runs the chain for its slab over the whole block (zero copy when it is whole frames)
+    size_t nf = 0;
+    for (size_t i = 0; i < b->ctx.size(); ++i) {
+        ua3reo_ctx* c = b->ctx[i];
+        UA3_CUDA(cudaSetDevice(c->device));
+        UA3_CUDA(cudaStreamWaitEvent(c->stream, b->ev_ready[s][i], 0));
+        size_t f = 0;
+        const int rc = ua3reo_ddc_push_device(c, b->adc[s][i], n, &f);
+        if (rc != UA3_OK) return rc;
+        UA3_CUDA(cudaEventRecord(b->ev_free[s][i], c->stream));
+        b->used[s][i] = 1;
+        if (i == 0) nf = f; else if (f != nf) return fail(UA3_E_STATE, "ua3reo_bank_push: devices disagree on the frame count");
+    }
+    // device 0's copy of the slot also feeds the peers: it is free when its own push AND their copies are done
+    UA3_CUDA(cudaSetDevice(c0->device));
+    for (size_t i = 1; i < b->ctx.size(); ++i) UA3_CUDA(cudaStreamWaitEvent(c0->stream, b->ev_ready[s][i], 0));
+    UA3_CUDA(cudaEventRecord(b->ev_free[s][0], c0->stream));
+    b->n_push++;
+    if (frames_out) *frames_out = nf;
+    return UA3_OK;
+}
+
+int ua3reo_bank_read_frames(ua3reo_bank* b, uint8_t* dst, size_t n_frames) {
+    if (!b || (!dst && n_frames)) return fail(UA3_E_INVAL, "ua3reo_bank_read_frames: null argument");
+    for (size_t i = 0; i < b->ctx.size(); ++i) {            // every device starts its copy, then all are awaited
+        const int rc = ua3reo_ddc_read_frames_async(b->ctx[i], dst + (size_t)b->first[i] * n_frames * UA3_FRAME_BYTES, n_frames);
+        if (rc != UA3_OK) return rc;
+    }
+    return ua3reo_bank_sync(b);
+}
+
+int ua3reo_bank_rx_counts(ua3reo_bank* b, size_t* audio_blocks, size_t* fft_frames) {
+    if (!b) return fail(UA3_E_INVAL, "null bank");
+    return ua3reo_rx_counts(b->ctx[0], audio_blocks, fft_frames);
+}
+
+int ua3reo_bank_rx_read_audio(ua3reo_bank* b, int32_t* dst, size_t n_blocks) {
+    if (!b || (!dst && n_blocks)) return fail(UA3_E_INVAL, "ua3reo_bank_rx_read_audio: null argument");
+    for (size_t i = 0; i < b->ctx.size(); ++i) {
+        const int rc = ua3reo_rx_read_audio_async(b->ctx[i], dst + (size_t)b->first[i] * n_blocks * 2 * UA3_AUDIO_BLOCK, n_blocks);
+        if (rc != UA3_OK) return rc;
+    }
+    return ua3reo_bank_sync(b);
+}
+
+int ua3reo_bank_rx_read_spectra(ua3reo_bank* b, float* dst, size_t n_frames) {
+    if (!b || (!dst && n_frames)) return fail(UA3_E_INVAL, "ua3reo_bank_rx_read_spectra: null argument");
+    for (size_t i = 0; i < b->ctx.size(); ++i) {
+        const int rc = ua3reo_rx_read_spectra_async(b->ctx[i], dst + (size_t)b->first[i] * n_frames * UA3_FFT_BINS, n_frames);
+        if (rc != UA3_OK) return rc;
+    }
+    return ua3reo_bank_sync(b);
+}
+
+int ua3reo_bank_sync(ua3reo_bank* b) {
+    if (!b) return fail(UA3_E_INVAL, "null bank");
+    for (size_t i = 0; i < b->ctx.size(); ++i) {
+        UA3_CUDA(cudaSetDevice(b->ctx[i]->device));
+        UA3_CUDA(cudaStreamSynchronize(b->fan[i]));
+        const int rc = ua3reo_sync(b->ctx[i]);
+        if (rc != UA3_OK) return rc;
+    }
     return UA3_OK;
 }
 
