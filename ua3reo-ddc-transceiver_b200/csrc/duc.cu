@@ -48,11 +48,12 @@ duc_kernel(const int16_t* __restrict__ iq_in, uint32_t n_in, uint32_t in_ch_stri
     {
         const uint4* src = reinterpret_cast<const uint4*>(nco_tab);
         uint4* dst = reinterpret_cast<uint4*>(s_tab);
-        for (int i = threadIdx.x; i < (int)(kDucSmemBytes / 16); i += 32 * kDucWarps) dst[i] = src[i];
+        for (int i = threadIdx.x; i < (int)(kDucSmemBytes / 16); i += (int)blockDim.x) dst[i] = src[i];
     }
     __syncthreads();
-    const uint32_t ch_raw = (blockIdx.x * (uint32_t)kDucWarps + (uint32_t)warp) * 16u + (uint32_t)pair;
-    if ((blockIdx.x * (uint32_t)kDucWarps + (uint32_t)warp) * 16u >= n_ch) return;     // whole warp beyond the bank (no barriers below)
+    const uint32_t cta_warps = blockDim.x >> 5;                 // 1, 2 or 4: chosen by duc_launch so that the warps spread over the SMs
+    const uint32_t ch_raw = (blockIdx.x * cta_warps + (uint32_t)warp) * 16u + (uint32_t)pair;
+    if ((blockIdx.x * cta_warps + (uint32_t)warp) * 16u >= n_ch) return;     // whole warp beyond the bank (no barriers below)
     const bool live = ch_raw < n_ch;
     const uint32_t ch = live ? ch_raw : (n_ch - 1u);
     DucState& S = state[ch];
@@ -156,8 +157,16 @@ cudaError_t duc_upload_constants() {
 
 cudaError_t duc_launch(const DucBuffers& b, uint32_t n_in, cudaStream_t st, int* launches) {
     if (!n_in) return cudaSuccess;
-    const uint32_t per_cta = 16u * (uint32_t)kDucWarps;
-    UA3_LAUNCH(duc_kernel, (b.n_ch + per_cta - 1u) / per_cta, 32 * kDucWarps, kDucSmemBytes, st, b.iq_in, n_in, b.max_in * 2u, b.nco_tab, b.fcw, b.state, b.n_ch,
+    // The chain is a strict recurrence per channel, so a warp (16 channels) is latency bound: spread the warps over as many
+    // SMs as there are (two CTAs fit an SM, 104 KB of NCO table each) before stacking them - 1, 2 or 4 warps per CTA.
+    int sm_count = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t n_warps = (b.n_ch + 15u) / 16u;
+    uint32_t cta_warps = (uint32_t)kDucWarps;
+    while (cta_warps > 1u && (n_warps + cta_warps - 1u) / cta_warps < 2u * (uint32_t)sm_count) cta_warps >>= 1;
+    const uint32_t per_cta = 16u * cta_warps;
+    UA3_LAUNCH(duc_kernel, (b.n_ch + per_cta - 1u) / per_cta, 32 * cta_warps, kDucSmemBytes, st, b.iq_in, n_in, b.max_in * 2u, b.nco_tab, b.fcw, b.state, b.n_ch,
                b.dac, (size_t)b.max_in * 1024u);
     if (launches) *launches += 1;
     return cudaGetLastError();
