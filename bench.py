@@ -355,8 +355,9 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
             rx.read_frames_async(frames_host[k[0] & 1])
             if full:                                   # pipelined reads of the STM32 results of this push
                 rx.read_audio_async(audio_host[k[0] & 1])
-                if gather_spectra is None:             # (N>1: the spectra go to rank 0 through the gather instead)
-                    rx.read_spectra_async(spec_host[k[0] & 1])
+                # every rank sinks its own spectra into host memory over its own PCIe link; at N>1 the NCCL gather
+                # additionally assembles all of them in rank 0's HBM (for a consumer on that device)
+                rx.read_spectra_async(spec_host[k[0] & 1])
             k[0] += 1
         t_host = time.perf_counter()
         if bc is None:
@@ -364,7 +365,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                 rx.push(host_np[i % NB])               # numpy view of the pinned blocks: ua3reo_ddc_push (H2D inside)
                 pull()
         else:
-            run_steps(n, host_blocks, after_push=pull, to_host=True)
+            run_steps(n, host_blocks, after_push=pull, to_host=False)
         host_enqueue_ms[0] = 1e3 * (time.perf_counter() - t_host) / max(n, 1)     # host time to enqueue one step
         rx.sync()
         if gather_spectra is not None:
@@ -554,7 +555,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
         if full:
             workload_s = ("BASELINE configs[4]: full per-channel RX chain for %d channels per GPU - " % n_ch) + workload_s.split(": ", 1)[1] + \
                          "; then processRxAudio + FFT_doFFT per channel (modes LSB/USB/CW_U/AM/NFM round-robin, DNR + notch on half)" + \
-                         ("; spectra NCCL-gathered to rank 0 every step" if world > 1 else "")
+                         ("; spectra NCCL-gathered into rank 0's HBM every step, host copies per rank" if world > 1 else "")
         issue = (static["sass_instructions_per_unit"] * float(n_ch) * block / front_s / int32_peak) \
             if static.get("sass_instructions_per_unit") and front_s > 0 and int32_peak else None
         line = {
