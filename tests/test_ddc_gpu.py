@@ -154,6 +154,58 @@ def test_front_kernel_variants_agree(pkg, oracle, monkeypatch):
     assert np.array_equal(outs["2"][pick], oracle.golden_frames(adc, fcw[pick])[:, :outs["2"].shape[1]])
 
 
+def test_tensor_core_front_kernel_is_exact(pkg, oracle, monkeypatch):
+    """ddc_front_tc_kernel (tcgen05 int8 MMAs for the integrators, FP32-pipe mixer) against the CUDA-core big-table
+    kernel and the golden model: 300 channels (a partly filled 128-channel warpgroup), ragged pushes, tuning words
+    that park the NCO on sin = -1 / cos = -1, and ADC samples of -2048 - the one product, (-2048) * (-2048) = 2^22,
+    that wraps the 23-bit mixer register - both in flagged chunks and next to unflagged ones."""
+    n_ch, pushes = 300, [1024 * 37, 1024 * 5 + 7, 1017, 1024 * 64]
+    adc = oracle.synth_adc(sum(pushes), seed=79)
+    adc[100:110] = -2048
+    adc[5000] = -2048
+    adc[1024 * 40:1024 * 41] = -2048
+    adc[1024 * 50:1024 * 50 + 512] = 2047
+    fcw = _fcws(n_ch, 79)
+    fcw[0] = 0                      # phase stays 0: cos = +max, sin = 0
+    fcw[1] = 1 << 20                # 0, 1/4, 1/2, 3/4 of a turn: sin and cos visit -1
+    fcw[2] = 1 << 21                # 0, 1/2 turn
+    fcw[3] = 3 << 20
+    fcw[299] = (1 << 22) - 1
+    outs = {}
+    for variant in ("2", "3"):
+        monkeypatch.setenv("UA3REO_FRONT_VARIANT", variant)
+        rx = pkg.Receiver(n_ch, 1 << 16)
+        rx.set_fcw(fcw)
+        got, off = [], 0
+        for n in pushes:
+            rx.push(adc[off:off + n]); off += n
+            got.append(rx.read_frames())
+        rx.close()
+        outs[variant] = np.concatenate(got, axis=1)
+    assert np.array_equal(outs["2"], outs["3"])
+    pick = [0, 1, 2, 3, 31, 127, 128, 255, 256, 299]
+    assert np.array_equal(outs["3"][pick], oracle.golden_frames(adc, fcw[pick])[:, :outs["3"].shape[1]])
+
+
+def test_tensor_core_front_kernel_small_and_odd_banks(pkg, oracle, monkeypatch):
+    """Forced onto banks it is not the default for: 1, 33 and 129 channels (idle lanes in the MMA's 128 rows, a second
+    warpgroup tile with one live channel), a 512-sample push (one chunk) and a long one."""
+    monkeypatch.setenv("UA3REO_FRONT_VARIANT", "3")
+    for n_ch in (1, 33, 129):
+        n = 1024 * 48
+        adc = oracle.synth_adc(n, seed=n_ch)
+        adc[::97] = -2048
+        fcw = _fcws(n_ch, n_ch)
+        rx = pkg.Receiver(n_ch, 1 << 15)
+        rx.set_fcw(fcw)
+        got = []
+        for a, b in [(0, 1024), (1024, 1024 * 30), (1024 * 30, n)]:
+            rx.push(adc[a:b])
+            got.append(rx.read_frames())
+        rx.close()
+        assert np.array_equal(np.concatenate(got, axis=1), oracle.golden_frames(adc, fcw)), n_ch
+
+
 def test_async_frame_reads_overlap_pushes(pkg, oracle):
     """ua3reo_ddc_read_frames_async: results of push k are copied while push k+1 runs; pinned host buffers."""
     import torch

@@ -221,7 +221,22 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
         UA3_TRY(cudaMemcpyAsync(b.big_tab, bt.data(), bt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
         UA3_TRY(cudaStreamSynchronize(c->stream));
     }
-    if (const char* v = std::getenv("UA3REO_FRONT_VARIANT")) b.front_variant = std::atoi(v);   // 1 small table, 2 big table
+#if !defined(UA3_HOST_EMU)
+    {
+        std::vector<uint32_t> th((size_t)kNcoBigTabWords);
+        std::vector<uint8_t> tw((size_t)kTcWeightPlaneBytes);
+        build_nco_half_table(th.data());
+        build_tc_weight_planes(tw.data(), b.tc_fix);
+        UA3_TRY(dev_alloc(c, &b.tab_h, (size_t)kNcoBigTabWords));
+        UA3_TRY(dev_alloc(c, &b.tc_w, (size_t)kTcWeightPlaneBytes));
+        UA3_TRY(dev_alloc(c, &b.adc_h, (size_t)max_block_samples + 8));
+        UA3_TRY(dev_alloc(c, &b.wrap_flag, (size_t)b.max_chunks + 4));
+        UA3_TRY(cudaMemcpyAsync(b.tab_h, th.data(), th.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        UA3_TRY(cudaMemcpyAsync(b.tc_w, tw.data(), tw.size(), cudaMemcpyHostToDevice, c->stream));
+        UA3_TRY(cudaStreamSynchronize(c->stream));
+    }
+#endif
+    if (const char* v = std::getenv("UA3REO_FRONT_VARIANT")) b.front_variant = std::atoi(v);   // 1 small table, 2 big table (CUDA cores), 3 tensor cores
     UA3_TRY(dev_alloc(c, &b.fcw, c->n_ch_pad));
     UA3_TRY(dev_alloc(c, &b.phase, c->n_ch_pad));
     UA3_TRY(dev_alloc(c, &b.L, (size_t)c->n_ch_pad * b.l_ch_stride));

@@ -13,6 +13,9 @@
 #include "ddc_launch.h"
 #include "ddc_front.cuh"
 #include "ddc_back.cuh"
+#if !defined(UA3_HOST_EMU)
+#include <cuda_fp16.h>
+#endif
 #include "tables_ddc.inc"
 
 namespace ua3 {
@@ -126,6 +129,42 @@ adc_expand_kernel(const int16_t* __restrict__ adc, uint32_t n8, int32_t* __restr
     dst[2 * v] = lo;
     dst[2 * v + 1] = hi;
 }
+
+#if !defined(UA3_HOST_EMU)
+// int16 ADC block -> binary16 (12-bit integers are exact) for the tensor-core front kernel, plus one flag per 512-sample
+// chunk: "contains -2048", the only sample value whose product with the NCO can wrap the 23-bit mixer register.
+__global__ void __launch_bounds__(256)
+adc_prepare_tc_kernel(const int16_t* __restrict__ adc, uint32_t n8, uint16_t* __restrict__ adc_h, uint8_t* __restrict__ wrap_flag,
+                      uint32_t* __restrict__ tile_counter) {
+    __shared__ uint32_t s_any[8];
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0) *tile_counter = 0;
+    bool hit = false;
+    if (v < n8) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(adc) + v);
+        const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const short lo = (short)(ws[k] & 0xFFFFu), hi = (short)(ws[k] >> 16);
+            hit |= (lo == -2048) | (hi == -2048);
+            o[k] = (uint32_t)__half_as_ushort(__short2half_rn(lo)) | ((uint32_t)__half_as_ushort(__short2half_rn(hi)) << 16);
+        }
+        reinterpret_cast<uint4*>(adc_h)[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    const uint32_t any = __ballot_sync(0xFFFFFFFFu, hit);
+    if ((threadIdx.x & 31) == 0) s_any[threadIdx.x >> 5] = any;
+    __syncthreads();
+    if (threadIdx.x < 4) {                                   // 64 threads = 512 samples = one chunk
+        const uint32_t chunk = blockIdx.x * 4u + threadIdx.x;
+        if (chunk * 64u < n8) wrap_flag[chunk] = (s_any[2 * threadIdx.x] | s_any[2 * threadIdx.x + 1]) ? 1 : 0;
+    }
+}
+#endif
+
+}  // namespace ua3
+#include "ddc_front_tc.cuh"
+namespace ua3 {
 
 __global__ void __launch_bounds__(kBtThreads, 1)
 ddc_front_bt_kernel(const int16_t* __restrict__ adc, const int32_t* __restrict__ adc9, uint32_t n_chunks,
@@ -505,8 +544,47 @@ void build_nco_big_table(uint32_t* tab /* kBigTabWords */) {
         }
 }
 
+// binary16 image of the big table for the tensor-core kernel: sin in the high half, cos in the low half
+static uint32_t half_bits_of(int32_t v) {              // binary16 encoding of an integer, |v| <= 2048 (exact)
+    if (v == 0) return 0;
+    const uint32_t sign = v < 0 ? 0x8000u : 0u;
+    const uint32_t m = (uint32_t)(v < 0 ? -v : v);
+    int e = 0;
+    while ((m >> (e + 1)) != 0) ++e;                       // m = 1.f * 2^e, e <= 11
+    const uint32_t frac = e <= 10 ? (m << (10 - e)) : (m >> (e - 10));
+    return sign | ((uint32_t)(e + 15) << 10) | (frac & 0x3FFu);
+}
+
+void build_nco_half_table(uint32_t* tab /* kBigTabWords */) {
+    build_nco_big_table(tab);
+    for (int i = 0; i < kBigTabWords; ++i) {
+        const int32_t s12 = (int32_t)tab[i] >> 16, c12 = (int32_t)(int16_t)(tab[i] & 0xFFFFu);
+        tab[i] = (half_bits_of(s12) << 16) | half_bits_of(c12);
+    }
+}
+static_assert(kTcWeightBytes == kTcWeightPlaneBytes, "ddc_launch.h");
+
+// byte planes of C(511 - t, k), k = 0..4, in the canonical K-major no-swizzle layout the MMA's shared-memory descriptor
+// walks: one 512-byte block per 32-sample slice, [16-sample half][8-column group][column][sample]
+void build_tc_weight_planes(uint8_t* w /* kTcWeightBytes */, uint64_t fix[5]) {
+    for (int i = 0; i < kTcWeightBytes; ++i) w[i] = 0;
+    for (int k = 0; k < 5; ++k) fix[k] = 0;
+    for (int t = 0; t < kCicR; ++t) {
+        const int s = t / 32, kk = t % 32;
+        int col = 0;
+        for (int k = 0; k < 5; ++k) {
+            const uint64_t wt = binom_u64((uint64_t)(kCicR - 1 - t), k);
+            fix[k] += wt * 16384ull;
+            for (int p = 0; p < tc_planes_of(k); ++p, ++col)
+                w[(size_t)s * kTcN * 32 + (kk / 16) * 256 + (col / 8) * 128 + (col % 8) * 16 + (kk % 16)] = (uint8_t)(wt >> (8 * p));
+        }
+    }
+}
+
 cudaError_t ddc_prepare_kernels() {
 #if !defined(UA3_HOST_EMU)
+    cudaError_t e = cudaFuncSetAttribute(ddc_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ddc_front_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmemBytes);
 #else
     return cudaSuccess;
@@ -546,7 +624,26 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
     if (ev && ((ev_mask >> 0) & 1u)) cudaEventRecord(ev[0], st);
     // big-table kernel when a CTA tile (256 channels x 4 chunks) can be filled; the 8 KB-table kernel otherwise
     const bool big = b.front_variant != 1 && b.big_tab && (b.front_variant == 2 || ((b.n_ch_pad >> 5) >= (uint32_t)kBtCG && n_chunks >= (uint32_t)kBtTG));
-    if (big) {
+#if !defined(UA3_HOST_EMU)
+    // tensor-core kernel: same threshold as the big-table kernel (a bank that fills the SMs' 128-channel warpgroups)
+    const bool tcore = b.tab_h && (b.front_variant == 3 || (b.front_variant == 0 && big));
+#else
+    const bool tcore = false;
+#endif
+    if (tcore) {
+#if !defined(UA3_HOST_EMU)
+        const uint32_t n8 = n_chunks * (uint32_t)kCicR / 8u;
+        UA3_LAUNCH(adc_prepare_tc_kernel, (n8 + 255u) / 256u, 256, 0, st, adc_dev, n8, b.adc_h, b.wrap_flag, b.tile_counter);
+        if (launches) *launches += 1;
+        if (ev && ((ev_mask >> 1) & 1u)) cudaEventRecord(ev[1], st);
+        const uint32_t n_tiles = ((b.n_ch_pad + 127u) / 128u) * n_chunks;
+        const uint32_t grid = (uint32_t)min((uint64_t)(n_tiles + kTcWg - 1) / kTcWg, (uint64_t)sm_count);
+        TcFix fix;
+        for (int k = 0; k < 5; ++k) fix.c[k] = b.tc_fix[k];
+        UA3_LAUNCH(ddc_front_tc_kernel, grid, kTcThreads, kTcSmemBytes, st, b.adc_h, b.wrap_flag, n_chunks, b.tab_h, b.fcw, b.phase, b.n_ch_pad,
+                   b.tc_w, b.L, b.l_ch_stride, b.tile_counter, fix);
+#endif
+    } else if (big) {
         const uint32_t n_tiles = (((b.n_ch_pad >> 5) + kBtCG - 1) / kBtCG) * ((n_chunks + kBtTG - 1) / kBtTG);
         // Tiles all take the same time, so the kernel lasts ceil(n_tiles / grid) tile times: of the SMs it may use it takes
         // only as many as that number of rounds needs (2048 tiles: 137 CTAs do 15 rounds exactly like 146 would) and

@@ -12,7 +12,13 @@ struct DdcBuffers {
     uint32_t* big_tab = nullptr;   // [2048 * 26] packed (sin12, cos12) by (coarse address, fine-sine value)
     uint32_t* tile_counter = nullptr;   // work counter of the persistent front kernel (zeroed by adc_expand_kernel)
     int32_t* adc9 = nullptr;       // [max_block] the current ADC block widened to int32 and pre-shifted << 9 (adc_expand_kernel)
-    int front_variant = 0;         // 0 auto, 1 force the 8 KB-table kernel, 2 force the big-table kernel
+    int front_variant = 0;         // 0 auto, 1 force the 8 KB-table kernel, 2 force the big-table CUDA-core kernel, 3 force the tensor-core kernel
+    // tensor-core front kernel (ddc_front_tc.cuh)
+    uint32_t* tab_h = nullptr;     // [2048 * 26] the big table as (sin, cos) binary16 pairs
+    uint8_t* tc_w = nullptr;       // [8192] byte planes of the integrator weights C(511 - t, k), MMA B-operand layout
+    uint64_t tc_fix[5] = {0, 0, 0, 0, 0};   // per-stage offset removed in the recombination (build_tc_weight_planes)
+    uint16_t* adc_h = nullptr;     // [max_block] the current ADC block as binary16 (adc_prepare_tc_kernel)
+    uint8_t* wrap_flag = nullptr;  // [max_chunks] chunk contains an ADC sample of -2048
     uint32_t* fcw = nullptr;       // [n_ch_pad] 22-bit tuning words
     uint32_t* phase = nullptr;     // [n_ch_pad] 22-bit phase at the start of the next block
     uint64_t* L = nullptr;         // [n_ch_pad][kLHalo + max_chunks][2][5]
@@ -34,6 +40,9 @@ struct DdcBuffers {
 void build_cic_weights(uint64_t G[25]);
 void build_nco_table(uint32_t tab[2048]);
 void build_nco_big_table(uint32_t* tab);
+void build_nco_half_table(uint32_t* tab);
+void build_tc_weight_planes(uint8_t* w, uint64_t fix[5]);
+constexpr int kTcWeightPlaneBytes = 8192;
 cudaError_t ddc_prepare_kernels();
 constexpr int kNcoBigTabWords = 2048 * 26;
 cudaError_t ddc_upload_constants();
