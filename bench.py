@@ -381,6 +381,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
     finish_device()
     barrier()
     int32_peak = pkg.measure_int32_peak(local)
+    lds_peak = pkg.measure_lds_peak(local)
     barrier()
 
     sampler = ClockSampler(local).start() if rank == 0 else None
@@ -532,7 +533,8 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                     cpu["hdl_translation_single_core"] = {"value": hdl, "unit": "channel*samples/s",
                                                           "note": "the reference's VHDL filters translated to C (oracle/_ref/libua3_hdl.so), one core"}
         variant = os.environ.get("UA3REO_FRONT_VARIANT", "0")
-        front_name = "ddc_front_kernel" if (variant == "1" or n_ch < 256) else "ddc_front_bt_kernel"
+        front_name = "ddc_front_kernel" if (variant == "1" or (n_ch < 256 and variant not in ("2", "3"))) else \
+            ("ddc_front_bt_kernel" if variant == "2" else "ddc_front_tc_kernel")
         static = {}
         try:
             static = json.load(open(os.path.join(ROOT, "profiles", "front_kernel_static.json"))).get(front_name, {})
@@ -558,6 +560,55 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                          ("; spectra NCCL-gathered into rank 0's HBM every step, host copies per rank" if world > 1 else "")
         issue = (static["sass_instructions_per_unit"] * float(n_ch) * block / front_s / int32_peak) \
             if static.get("sass_instructions_per_unit") and front_s > 0 and int32_peak else None
+        units = float(n_ch) * block
+        common = {"kernel": front_name, "units_per_launch": units, "kernel_ms": front_s * 1e3,
+                  "kernel_share_of_step": front_s * 1e3 / (ms / K),
+                  "traffic": static.get("traffic_bytes_per_launch") if (n_ch, block) == (1024, 1 << 20) else None,
+                  "traffic_ratio": (static["traffic_bytes_per_launch"] / (2.0 * block + 8.0 * n_ch * (block // 1024))
+                                    if static.get("traffic_bytes_per_launch") and (n_ch, block) == (1024, 1 << 20) else None),
+                  "executed_instructions_per_unit": static.get("sass_instructions_per_unit"),
+                  "issue_frac": issue, "static_source": static.get("source"),
+                  "all_kernels_ms_per_step": {k: v / max(n_all, 1) for k, v in kms_all.items()},
+                  "all_kernels_note": "per-kernel times from a separate pass of %d steps right after the timed region "
+                                      "(events around every kernel); kernel_ms is from the timed region itself" % n_break,
+                  "hbm": {"algorithmic_gbs": step_bytes / (ms / K * 1e-3) / 1e9,
+                          "peak_gbs": peaks.get("hbm_gbs"), "note": "HBM is not the bound (SURVEY.md 8d)"}}
+        if front_name == "ddc_front_tc_kernel":
+            # The tensor-core kernel is bound by the shared-memory pipe: one NCO table look-up per channel-sample, 32 lanes at 32
+            # unrelated addresses.  A gather of 32 uniformly random words needs as many wavefronts as its fullest bank holds
+            # words: E[max load of 32 balls in 32 bins], a property of the access pattern and not of the code.
+            rng = np.random.default_rng(1)
+            e_max = float(np.mean([np.bincount(rng.integers(0, 32, 32), minlength=32).max() for _ in range(20000)]))
+            alg = units * e_max / 32.0 / front_s if front_s > 0 else 0.0
+            executed = (static["lsu_wavefronts_per_unit"] * units / front_s) if static.get("lsu_wavefronts_per_unit") and front_s > 0 else None
+            roofline = dict(common, **{
+                "bound": "smem", "achieved": alg / 1e9, "peak": lds_peak / 1e9, "unit": "G wavefronts/s (shared-memory pipe)",
+                "frac": (alg / lds_peak) if lds_peak else None,
+                "algorithmic_wavefronts_per_unit": e_max / 32.0, "expected_max_bank_load": e_max,
+                "executed_wavefronts_per_unit": static.get("lsu_wavefronts_per_unit"),
+                "pipe_busy_frac": (executed / lds_peak) if executed and lds_peak else None,
+                "pipe_busy_ncu_pct": static.get("lsu_pipe_pct_ncu"),
+                "tensor": {"mma_per_unit": 4.0 / (32 * 128), "shape": "M128 N16 K32 kind::i8", "tensor_pipe_pct_ncu": static.get("tensor_pipe_pct_ncu"),
+                           "note": "the integrators are an exact int8 GEMM (ddc_front_tc.cuh); the tensor pipe idles - the NCO look-ups bound the kernel"},
+                "int32_equivalent": {"ops_per_unit": A_INT_OPS, "top_s": achieved / 1e12, "int32_peak_top_s": int32_peak / 1e12,
+                                     "note": "the 41 INT32 ops per channel-sample of the HDL-literal formulation (SURVEY.md 8d) against the "
+                                             "CUDA-core peak: above 1 because 30 of them (the integrator adds) now run as int8 MMAs"},
+                "note": "achieved = channel-samples x E[max bank load]/32 wavefronts (the conflict-limited gather of one table word per "
+                        "channel-sample) / kernel time; pipe_busy_frac adds the ADC broadcasts and the record stores "
+                        "(executed_wavefronts_per_unit, from ncu); issue_frac = executed warp instructions x 32 / CUDA-core peak",
+                "peak_source": "ua3reo_measure_lds_peak (conflict-free LDS.32 streams, 1024 threads per SM), measured live on this GPU; "
+                               "MEASURED_PEAKS.json has no shared-memory peak"})
+        else:
+            roofline = dict(common, **{
+                "bound": "int32_alu", "achieved": achieved / 1e12, "peak": int32_peak / 1e12,
+                "unit": "TOP/s (INT32)", "frac": (achieved / int32_peak) if int32_peak else None,
+                "note": "achieved counts the 41 algorithmic INT32 ops per channel-sample of the HDL-literal formulation "
+                        "(SURVEY.md 8d), which is why frac can exceed 1: the kernel executes executed_instructions_per_unit "
+                        "of them (table-driven NCO output stage, shifts fused into adds); issue_frac = executed ops / peak "
+                        "is the fraction to judge the kernel by",
+                "ops_per_unit": A_INT_OPS,
+                "peak_source": "ua3reo_measure_int32_peak (IMAD+LOP3+IADD3 chains), measured live on this GPU; "
+                               "MEASURED_PEAKS.json has no integer peak"})
         line = {
             "metric": "rx_chain_channel_adc_samples_per_s" if full else "ddc_channel_adc_samples_per_s", "value": value,
             "unit": "channel*samples/s",
@@ -576,28 +627,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
             "parity": {"ddc_ranks_ok": int(oks[0]), "ranks": world, "channels_checked_per_rank": len(picks),
                        "ddc_check": "frames of one more block (NCCL-broadcast at N>1) == golden model, bit for bit",
                        "stm32_ranks_ok": (int(oks[1]) if full and audio_ok is not None else None), "stm32_check": audio_note},
-            "roofline": {"bound": "int32_alu", "kernel": front_name, "achieved": achieved / 1e12, "peak": int32_peak / 1e12,
-                         "unit": "TOP/s (INT32)", "frac": (achieved / int32_peak) if int32_peak else None,
-                         "traffic": static.get("traffic_bytes_per_launch") if (n_ch, block) == (1024, 1 << 20) else None,
-                         "traffic_ratio": (static["traffic_bytes_per_launch"] / (2.0 * block + 8.0 * n_ch * (block // 1024))
-                                           if static.get("traffic_bytes_per_launch") and (n_ch, block) == (1024, 1 << 20) else None),
-                         "executed_ops_per_unit": static.get("sass_instructions_per_unit"),
-                         "issue_frac": issue,
-                         "static_source": static.get("source"),
-                         "note": "achieved counts the 41 algorithmic INT32 ops per channel-sample of the HDL-literal formulation "
-                                 "(SURVEY.md 8d), which is why frac can exceed 1: the kernel executes executed_ops_per_unit "
-                                 "of them (table-driven NCO output stage, shifts fused into adds); issue_frac = executed ops / peak "
-                                 "is the fraction to judge the kernel by",
-                         "ops_per_unit": A_INT_OPS, "units_per_launch": float(n_ch) * block,
-                         "kernel_ms": front_s * 1e3,
-                         "kernel_share_of_step": front_s * 1e3 / (ms / K),
-                         "all_kernels_ms_per_step": {k: v / max(n_all, 1) for k, v in kms_all.items()},
-                         "all_kernels_note": "per-kernel times from a separate pass of %d steps right after the timed region "
-                                             "(events around every kernel); kernel_ms is from the timed region itself" % n_break,
-                         "peak_source": "ua3reo_measure_int32_peak (IMAD+LOP3+IADD3 chains), measured live on this GPU; "
-                                        "MEASURED_PEAKS.json has no integer peak",
-                         "hbm": {"algorithmic_gbs": step_bytes / (ms / K * 1e-3) / 1e9,
-                                 "peak_gbs": peaks.get("hbm_gbs"), "note": "HBM is not the bound (SURVEY.md 8d)"}},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
         }

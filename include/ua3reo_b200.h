@@ -387,6 +387,9 @@ int ua3reo_profile_end(ua3reo_ctx *ctx, double *kernel_ms, uint32_t n_kernels, u
 /* Dependent-free INT32 issue-rate microbenchmark (IADD3 + IMAD interleaved) used as the roofline
  * denominator: returns integer operations per second summed over the whole device. */
 int ua3reo_measure_int32_peak(int device, double *ops_per_s);
+/* Shared-memory wavefront rate (conflict-free LDS.32 streams, 1024 threads per SM): the roofline denominator of the
+ * tensor-core front kernel, whose NCO table look-ups saturate that pipe.  Wavefronts per second over the whole device. */
+int ua3reo_measure_lds_peak(int device, double *wavefronts_per_s);
 
 #ifdef __cplusplus
 }

@@ -19,10 +19,11 @@ def test_static_json_matches_the_built_library():
         pytest.skip("library not built")
     rec = json.load(open(front_static.OUT))
     now = front_static.sass_counts()
-    for kernel in ("ddc_front_bt_kernel", "ddc_front_kernel"):
+    for kernel in ("ddc_front_tc_kernel", "ddc_front_bt_kernel", "ddc_front_kernel"):
         assert now[kernel]["hot_loop_sass_instructions"] == rec[kernel]["hot_loop_sass_instructions"], \
             "%s changed: re-profile and run tools/front_static.py update" % kernel
         # the ncu-measured executed instructions per unit must sit just above the hot loop's static count
         static = now[kernel]["hot_loop_sass_instructions_per_unit"]
         assert static <= rec[kernel]["sass_instructions_per_unit"] <= 1.12 * static
         assert rec[kernel]["traffic_bytes_per_launch"] > 1e8 and "source" in rec[kernel]
+    assert 0.11 < rec["ddc_front_tc_kernel"]["lsu_wavefronts_per_unit"] < 0.2      # >= E[max bank load] / 32 of the table gather

@@ -9,7 +9,8 @@
            instruction count recorded there, i.e. when the JSON has gone stale.
 
 Hot loop = the largest innermost backward-branch body of the kernel; ddc_front_bt_kernel's processes one 16-sample sub-block of one
-channel per lane and iteration (ddc_front.cuh: kSub), so loop instructions / 16 = executed instructions per channel-sample."""
+channel per lane and iteration (ddc_front.cuh: kSub), so loop instructions / 16 = executed instructions per channel-sample;
+ddc_front_tc_kernel's processes one 32-sample MMA slice (the larger of its two copies, the one that masks the mixer wrap)."""
 import collections
 import csv
 import json
@@ -21,7 +22,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "ua3reo-ddc-transceiver_b200", "lib", "libua3reo_b200.so")
 OUT = os.path.join(ROOT, "profiles", "front_kernel_static.json")
-KERNELS = {"ddc_front_bt_kernel": 16, "ddc_front_kernel": 16}       # samples per hot-loop iteration and lane (kSub)
+# samples per hot-loop iteration and lane: kSub for the CUDA-core kernels, one 32-sample MMA slice for the tensor-core kernel
+KERNELS = {"ddc_front_tc_kernel": 32, "ddc_front_bt_kernel": 16, "ddc_front_kernel": 16}
 UNITS = 1024 * (1 << 20)                                             # channel-samples per launch of the profiled bench
 
 
@@ -91,6 +93,13 @@ def update(csv_path, lib=LIB):
         rec = data.setdefault(name, {})
         rec["traffic_bytes_per_launch"] = f("dram__bytes_read.sum") + f("dram__bytes_write.sum")
         rec["sass_instructions_per_unit"] = f("smsp__inst_executed.sum") * 32.0 / UNITS
+        if "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg" in rows:      # per-SM average x SMs = wavefronts per launch
+            n_sm = f("device__attribute_multiprocessor_count")
+            rec["lsu_wavefronts_per_unit"] = f("SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg") * n_sm / UNITS
+            rec["lsu_wavefronts_shared_per_unit"] = f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") / UNITS
+            rec["lsu_pipe_pct_ncu"] = f("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")
+        if "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed" in rows:
+            rec["tensor_pipe_pct_ncu"] = f("sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed")
         rec["source"] = "ncu --set full of `python bench.py`, summarised in profiles/%s by tools/summarize_ncu.py; " \
                         "1024 channels x 2^20 samples per launch" % os.path.basename(csv_path)
     for k, v in sass.items():

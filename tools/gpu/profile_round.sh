@@ -9,7 +9,7 @@ python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/${R}_bench_re
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${R}_launches_bench.csv \
     python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-sustained > /dev/null 2>&1
 # --set full of one launch of each kernel of the DDC workload (after warm-up) ...
-ncu --set full --clock-control none --import-source on -k regex:"ddc_front_bt|ddc_ciccomp|ddc_hilb" -s 12 -c 3 -f -o gpurun_out/${R}_ddc_kernels \
+ncu --set full --clock-control none --import-source on -k regex:"ddc_front_tc|ddc_ciccomp|ddc_hilb" -s 12 -c 3 -f -o gpurun_out/${R}_ddc_kernels \
     python bench.py --workload ddc --steps 4 --warmup 3 --no-cpu-baseline --no-sustained > /dev/null 2>&1
 # ... of the STM32 stage (1024 channels, mode mix) ...
 ncu --set full --clock-control none --import-source on -k regex:"rx_audio_kernel|rx_fft_pre|rx_fft_kernel" -s 3 -c 3 -f -o gpurun_out/${R}_stm32_kernels \

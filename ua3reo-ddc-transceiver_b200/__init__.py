@@ -150,6 +150,7 @@ def _bind(lib):
         "ua3reo_profile_begin_kernel": (c.c_int, [vp, u32, u32]),
         "ua3reo_profile_end": (c.c_int, [vp, c.POINTER(c.c_double), u32, c.POINTER(u32)]),
         "ua3reo_measure_int32_peak": (c.c_int, [c.c_int, c.POINTER(c.c_double)]),
+        "ua3reo_measure_lds_peak": (c.c_int, [c.c_int, c.POINTER(c.c_double)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
@@ -671,6 +672,15 @@ def frames_to_iq(frames):
     w = (f[..., 0::2].astype(np.uint16) << 8) | f[..., 1::2].astype(np.uint16)
     w = w.astype(np.int16)
     return {"spec_q": w[..., 0], "spec_i": w[..., 1], "voice_q": w[..., 2], "voice_i": w[..., 3]}
+
+
+def measure_lds_peak(device=0, lib=None):
+    lib = lib or load_library()
+    v = ctypes.c_double(0.0)
+    rc = lib.ua3reo_measure_lds_peak(int(device), ctypes.byref(v))
+    if rc != 0:
+        raise UA3Error("ua3reo error %d: %s" % (rc, lib.ua3reo_last_error().decode()))
+    return float(v.value)
 
 
 def measure_int32_peak(device=0, lib=None):

@@ -1625,4 +1625,16 @@ int ua3reo_measure_int32_peak(int device, double* ops_per_s) {
     return UA3_OK;
 }
 
+int ua3reo_measure_lds_peak(int device, double* wavefronts_per_s) {
+    if (!wavefronts_per_s) return fail(UA3_E_INVAL, "null argument");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail(UA3_E_NODEV, "no CUDA device");
+    if (device < 0 || device >= n_dev) return fail(UA3_E_INVAL, "device index out of range");
+    UA3_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    UA3_CUDA(cudaGetDeviceProperties(&prop, device));
+    UA3_CUDA(measure_lds_peak(prop.multiProcessorCount, nullptr, wavefronts_per_s));
+    return UA3_OK;
+}
+
 }  // extern "C"

@@ -30,6 +30,7 @@
 // 3.6 bank wavefronts per lookup - not the issue slots (13.8 instructions per sample and channel instead of 24.3).
 #pragma once
 #include "ddc_front.cuh"
+#include <type_traits>
 
 namespace ua3 {
 
@@ -90,6 +91,9 @@ __device__ __forceinline__ uint64_t recombine(const uint32_t* lo, const uint32_t
 }
 
 // 32 samples of one channel -> the four A byte planes of a slice
+// (The slice's ADC samples are the same for every lane: a broadcast LDG.128 costs the load/store pipe four wavefronts per
+// eight samples.  Loading 16 bytes per lane once and passing them round by warp shuffles was measured slower - 0.630 against
+// 0.600 ms - although shuffles do not count as data wavefronts; tools/exp/lsu_wavefronts.cu.)
 template <bool WRAP>
 __device__ __forceinline__ void slice_planes(const uint32_t* __restrict__ s_tab, const uint4* __restrict__ a8, uint32_t& P, uint32_t F, float magic,
                                              uint32_t (&ilo)[8], uint32_t (&ihi)[8], uint32_t (&qlo)[8], uint32_t (&qhi)[8]) {
@@ -177,20 +181,24 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
             uint32_t P = (phase[chl] << 10) + F * (chunk * (uint32_t)kCicR);
             const uint4* a8 = reinterpret_cast<const uint4*>(adc_h + (size_t)chunk * kCicR);
             const bool wrap = wrap_flag[chunk] != 0;
+            auto slices = [&](auto wrap_tag) {                            // the chunk's 16 slices; two copies of the loop, with and without the mask
+                constexpr bool kWrap = decltype(wrap_tag)::value;
 #pragma unroll 1
-            for (int s = 0; s < kTcSlices; ++s, ++n_done) {
-                const int b = s & 1;
-                uint32_t ilo[8], ihi[8], qlo[8], qhi[8];
-                if (wrap) tc::slice_planes<true>(s_tab, a8 + s * 4, P, F, magic, ilo, ihi, qlo, qhi);
-                else tc::slice_planes<false>(s_tab, a8 + s * 4, P, F, magic, ilo, ihi, qlo, qhi);
-                if (n_done >= 2) { mbar_wait(&bar_free[b], par_free[b]); par_free[b] ^= 1; }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_col = col0 + lane_off + 64 + 32 * b;
-                tc::tmem_st8(a_col + 0, ilo); tc::tmem_st8(a_col + 8, ihi); tc::tmem_st8(a_col + 16, qlo); tc::tmem_st8(a_col + 24, qhi);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                tc::mbar_arrive(&bar_full[b]);
-            }
+                for (int s = 0; s < kTcSlices; ++s, ++n_done) {
+                    const int b = s & 1;
+                    uint32_t ilo[8], ihi[8], qlo[8], qhi[8];
+                    tc::slice_planes<kWrap>(s_tab, a8 + s * 4, P, F, magic, ilo, ihi, qlo, qhi);
+                    if (n_done >= 2) { mbar_wait(&bar_free[b], par_free[b]); par_free[b] ^= 1; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_col = col0 + lane_off + 64 + 32 * b;
+                    tc::tmem_st8(a_col + 0, ilo); tc::tmem_st8(a_col + 8, ihi); tc::tmem_st8(a_col + 16, qlo); tc::tmem_st8(a_col + 24, qhi);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    tc::mbar_arrive(&bar_full[b]);
+                }
+            };
+            if (wrap) slices(std::true_type{});
+            else slices(std::false_type{});
             mbar_wait(bar_acc_ready, par_acc); par_acc ^= 1;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t d_ilo[16], d_ihi[16], d_qlo[16], d_qhi[16];

@@ -52,5 +52,6 @@ constexpr int kDdcKernels = 5;   // profile slots in launch order: adc_expand, f
 cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32_t n_samples, uint32_t ring_start,
                              int sm_count, cudaStream_t st, int* launches, cudaEvent_t* ev, uint32_t ev_mask = 0xFFFFFFFFu);
 cudaError_t measure_int32_peak(int sm_count, cudaStream_t st, double* ops_per_s);
+cudaError_t measure_lds_peak(int sm_count, cudaStream_t st, double* wavefronts_per_s);
 
 }  // namespace ua3
