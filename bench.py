@@ -245,7 +245,7 @@ def run_reference(args):
                 line = fc
             else:
                 line["full_chain"] = fc
-    print(json.dumps(line))
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -347,13 +347,15 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
     def step_e2e_n(n):
         """Same steps through the host-facing C ABI: every step copies the ADC block from pinned host memory (H2D inside the
         timed region; at N>1 rank 0 ingests and the others receive the broadcast) and reads every frame back to pinned host
-        memory (D2H); full chain: audio and spectra too.  The copies of step i are enqueued asynchronously so that they
+        memory (D2H); full chain: the codec audio words and the spectra instead (the frames never leave the device there).  The copies of step i are enqueued asynchronously so that they
         overlap the kernels of step i+1; the final sync is inside the timed region."""
         k = [0]
 
         def pull():
-            rx.read_frames_async(frames_host[k[0] & 1])
-            if full:                                   # pipelined reads of the STM32 results of this push
+            if not full:
+                rx.read_frames_async(frames_host[k[0] & 1])
+            else:                                      # the frames are consumed on the device by the STM32 stage; what a full-chain
+                                                       # user reads are its results: pipelined reads of this push's audio and spectra
                 rx.read_audio_async(audio_host[k[0] & 1])
                 # every rank sinks its own spectra into host memory over its own PCIe link; at N>1 the NCCL gather
                 # additionally assembles all of them in rank 0's HBM (for a consumer on that device)
@@ -415,6 +417,20 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
     e1.record(ext)
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    # what the box's host side can take: every rank copies 4 x 64 MB device -> pinned host at the same time (the ceiling of e2e
+    # at N>1 is this aggregate, not the GPUs: DESIGN.md 6)
+    link_dev = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    link_host = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    link_host.copy_(link_dev, non_blocking=True)
+    barrier()
+    lk0, lk1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lk0.record()
+    for _ in range(4):
+        link_host.copy_(link_dev, non_blocking=True)
+    lk1.record()
+    barrier()
+    ms_link = lk0.elapsed_time(lk1)
+    del link_dev, link_host
 
     # sustained: >= args.sustained_seconds of back-to-back steps, clocks sampled
     sustained = None
@@ -496,7 +512,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
         ms_duc = e0.elapsed_time(e1)
         tx_duc = [ms_duc, reps, n_tx, rx.launch_count() - l0]
 
-    red = [ms, ms_e2e, sustained[0] if sustained else 0.0, tx_duc[0] if tx_duc else 0.0]
+    red = [ms, ms_e2e, sustained[0] if sustained else 0.0, tx_duc[0] if tx_duc else 0.0, ms_link]
     oks = [1.0 if ddc_ok else 0.0, 1.0 if audio_ok else 0.0]
     if world > 1:
         t = torch.tensor(red, device="cuda", dtype=torch.float64)
@@ -549,7 +565,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
         step_bytes = 2.0 * block * (n_ch // 32) + 2 * rec_bytes * n_ch * (block // 512) + 8.0 * n_ch * (block // 1024)
         d2h = n_ch * (block // 1024) * 8
         if full:
-            d2h += int(n_ch * (block / 1024.0 / 192.0) * 384 * 4 + n_ch * (block / 1024.0 / 512.0) * 256 * 4)
+            d2h = int(n_ch * (block / 1024.0 / 192.0) * 384 * 4 + n_ch * (block / 1024.0 / 512.0) * 256 * 4)
         workload_s = ("BASELINE configs[2]/[3]: %d independent DDC channels per GPU (random tuning words, seed %d) "
                       "over one shared synthetic 12-bit ADC stream, blocks of %d samples; full FPGA RX chain "
                       "(NCO+mixer+CIC/512+compensator FIR+Hilbert FIR+Q delay+8-byte frames); "
@@ -622,7 +638,11 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                        "l2": "per-step working set ~%.0f MB (chunk records + frames) exceeds the 126 MB L2; no flush needed"
                              % (step_bytes / 1e6)},
             "e2e": {"value": e2e, "unit": "channel*samples/s", "h2d_bytes_per_step": 2 * block,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "host_enqueue_ms_per_step": host_enqueue_ms[0]},
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K, "host_enqueue_ms_per_step": host_enqueue_ms[0],
+                    "host_d2h_aggregate_gbs": world * 4.0 * (64 << 20) / (red[4] * 1e-3) / 1e9 if red[4] > 0 else None,
+                    "d2h_gbs_needed_at_device_rate": d2h * world / (ms / K * 1e-3) / 1e9,
+                    "note": "bytes are per rank; host_d2h_aggregate_gbs = all ranks copying device -> pinned host at once "
+                            "(4 x 64 MB each), the box's ceiling for results leaving the GPUs"},
             "gpu_launches": int(launches),
             "parity": {"ddc_ranks_ok": int(oks[0]), "ranks": world, "channels_checked_per_rank": len(picks),
                        "ddc_check": "frames of one more block (NCCL-broadcast at N>1) == golden model, bit for bit",
@@ -695,13 +715,32 @@ def run_ours(args):
             else:
                 line["full_chain"] = fc
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """the ONE line on stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
+    # stdout carries the JSON line and nothing else: libraries that print there (NCCL's version banner when the box sets
+    # NCCL_DEBUG=VERSION, a stray warning) are sent to stderr at the file-descriptor level for the whole run
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
