@@ -371,8 +371,11 @@ static int rx_run_stage(ua3reo_ctx* c, cudaEvent_t* ev, int* launches) {
     c->rx.audio_out = c->rx_audio2[set]; c->rx.spectra = c->rx_spec2[set]; c->rx.waterfall = c->rx_wf2[set]; c->rx.cw_mag = c->rx_cw2[set];
     c->rx_last_slot = set;
     // processRxAudio and FFT_doFFT touch disjoint state and outputs: their kernels run on two streams side by side
-    // (serialised on one stream only while per-kernel profiling events are being recorded)
-    cudaStream_t fft_st = ev ? c->rx_stream : c->rx_stream2;
+    // (serialised on one stream only while profiling events are being recorded AROUND THEM - not when the profile covers a
+    // DDC kernel only, as bench.py's timed region does: round 2 measured a 1024-channel step at 1.05 ms instead of 0.81 because
+    // of exactly that)
+    const bool prof_rx = ev && (((c->prof_mask >> kDdcKernels) & 7u) != 0u);
+    cudaStream_t fft_st = prof_rx ? c->rx_stream : c->rx_stream2;
     UA3_CUDA(cudaEventRecord(c->ev_frames, c->stream));
     UA3_CUDA(cudaStreamWaitEvent(c->rx_stream, c->ev_frames, 0));
     if (fft_st != c->rx_stream) UA3_CUDA(cudaStreamWaitEvent(fft_st, c->ev_frames, 0));
