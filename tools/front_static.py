@@ -69,7 +69,9 @@ def sass_counts(lib=LIB):
     res = {}
     for mangled, ins in functions(lib).items():
         for k, per in KERNELS.items():
-            if ("%d%sE" % (len(k), k)) in mangled:
+            # plain kernels mangle as <len><name>E...; the tensor-core kernel is a template <bool STAGE> - the instantiation
+            # that ships as the default is <true> (ILb1E)
+            if ("%d%sE" % (len(k), k)) in mangled or ("%d%sILb1E" % (len(k), k)) in mangled:
                 n, hist = hot_loop(ins)
                 res[k] = {"hot_loop_sass_instructions": n, "samples_per_iteration": per,
                           "hot_loop_sass_instructions_per_unit": n / per, "hot_loop_opcodes": hist,
@@ -84,7 +86,7 @@ def update(csv_path, lib=LIB):
     sass = sass_counts(lib)
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for c, full_name in enumerate(rows["Kernel Name"][2:], start=2):
-        name = full_name.split("(")[0]
+        name = full_name.split("(")[0].split("<")[0].replace("void ", "").strip()
         if name not in KERNELS:
             continue
 

@@ -583,7 +583,9 @@ void build_tc_weight_planes(uint8_t* w /* kTcWeightBytes */, uint64_t fix[5]) {
 
 cudaError_t ddc_prepare_kernels() {
 #if !defined(UA3_HOST_EMU)
-    cudaError_t e = cudaFuncSetAttribute(ddc_front_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(ddc_front_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ddc_front_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTcSmemBytes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ddc_front_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBtSmemBytes);
 #else
@@ -640,8 +642,12 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
         const uint32_t grid = (uint32_t)min((uint64_t)(n_tiles + kTcWg - 1) / kTcWg, (uint64_t)sm_count);
         TcFix fix;
         for (int k = 0; k < 5; ++k) fix.c[k] = b.tc_fix[k];
-        UA3_LAUNCH(ddc_front_tc_kernel, grid, kTcThreads, kTcSmemBytes, st, b.adc_h, b.wrap_flag, n_chunks, b.tab_h, b.fcw, b.phase, b.n_ch_pad,
-                   b.tc_w, b.L, b.l_ch_stride, b.tile_counter, fix);
+        if (b.tc_adc_stage)
+            UA3_LAUNCH(ddc_front_tc_kernel<true>, grid, kTcThreads, kTcSmemBytes, st, b.adc_h, b.wrap_flag, n_chunks, b.tab_h, b.fcw, b.phase,
+                       b.n_ch_pad, b.tc_w, b.L, b.l_ch_stride, b.tile_counter, fix);
+        else
+            UA3_LAUNCH(ddc_front_tc_kernel<false>, grid, kTcThreads, kTcSmemBytes, st, b.adc_h, b.wrap_flag, n_chunks, b.tab_h, b.fcw, b.phase,
+                       b.n_ch_pad, b.tc_w, b.L, b.l_ch_stride, b.tile_counter, fix);
 #endif
     } else if (big) {
         const uint32_t n_tiles = (((b.n_ch_pad >> 5) + kBtCG - 1) / kBtCG) * ((n_chunks + kBtTG - 1) / kBtTG);

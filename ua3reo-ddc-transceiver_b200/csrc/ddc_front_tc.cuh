@@ -39,7 +39,8 @@ constexpr int kTcSlices = kCicR / 32;             // K = 32 samples per MMA
 constexpr int kTcWg = 4;                          // warpgroups per CTA: 4 x 128 TMEM columns
 constexpr int kTcThreads = kTcWg * 128 + kTcWg * 32;
 constexpr int kTcWeightBytes = kTcSlices * kTcN * 32;
-constexpr size_t kTcSmemBytes = (size_t)kBigTabWords * 4 + kTcWeightBytes + 256;   // table + weights + 24 barriers (192 B) + 16 words
+constexpr int kTcAdcStageBytes = kTcWg * 2 * kCicR * 2;                             // per warpgroup two chunks of binary16 samples
+constexpr size_t kTcSmemBytes = (size_t)kBigTabWords * 4 + kTcWeightBytes + kTcAdcStageBytes + 256;   // table + weights + ADC chunks + 25 barriers + 10 words
 UA3_HD constexpr int tc_planes_of(int k) { return k == 0 ? 1 : (k == 1 ? 2 : (k == 2 ? 3 : 4)); }   // bytes of C(511, k)
 
 struct TcFix { uint64_t c[5]; };                  // 16384 * sum_t C(511 - t, k): the +64 of the high byte planes
@@ -90,33 +91,42 @@ __device__ __forceinline__ uint64_t recombine(const uint32_t* lo, const uint32_t
     return acc;
 }
 
-// 32 samples of one channel -> the four A byte planes of a slice
-// (The slice's ADC samples are the same for every lane: a broadcast LDG.128 costs the load/store pipe four wavefronts per
-// eight samples.  Loading 16 bytes per lane once and passing them round by warp shuffles was measured slower - 0.630 against
-// 0.600 ms - although shuffles do not count as data wavefronts; tools/exp/lsu_wavefronts.cu.)
-template <bool WRAP>
-__device__ __forceinline__ void slice_planes(const uint32_t* __restrict__ s_tab, const uint4* __restrict__ a8, uint32_t& P, uint32_t F, float magic,
+// 32 samples of one channel -> the four A byte planes of a slice.  The slice's ADC samples are the same for every lane:
+// STAGE = false reads them with broadcast LDG.128 (four load/store-pipe wavefronts per eight samples), STAGE = true from the
+// chunk copy in shared memory with broadcast LDS.64 (one wavefront per four samples; tools/exp/lsu_wavefronts.cu).  Passing
+// them round by warp shuffles was measured slower (0.630 against 0.600 ms) although shuffles are not data wavefronts.
+template <bool WRAP, bool STAGE>
+__device__ __forceinline__ void slice_planes(const uint32_t* __restrict__ s_tab, const void* __restrict__ src, uint32_t& P, uint32_t F, float magic,
                                              uint32_t (&ilo)[8], uint32_t (&ihi)[8], uint32_t (&qlo)[8], uint32_t (&qhi)[8]) {
+    uint4 av4 = make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        const uint4 av = __ldg(a8 + v);
-        const uint32_t ap[4] = {av.x, av.y, av.z, av.w};
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            uint32_t w[4], fi[4], fq[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { w[e] = s_tab[nco_bigtab_index(P >> 21, nco_fine_level(P))]; P += F; }
-            mix4(ap[2 * h], ap[2 * h + 1], w, fi, fq, magic);
-            const uint32_t i01 = __byte_perm(fi[0], fi[1], 0x6251), i23 = __byte_perm(fi[2], fi[3], 0x6251);
-            const uint32_t q01 = __byte_perm(fq[0], fq[1], 0x6251), q23 = __byte_perm(fq[2], fq[3], 0x6251);
-            ilo[2 * v + h] = __byte_perm(i01, i23, 0x5410); ihi[2 * v + h] = __byte_perm(i01, i23, 0x7632);
-            qlo[2 * v + h] = __byte_perm(q01, q23, 0x5410); qhi[2 * v + h] = __byte_perm(q01, q23, 0x7632);
-            if (WRAP) { ihi[2 * v + h] &= 0x7F7F7F7Fu; qhi[2 * v + h] &= 0x7F7F7F7Fu; }
+    for (int q = 0; q < 8; ++q) {                                    // four samples per step
+        uint32_t a01, a23;
+        if (STAGE) {
+            const uint2 av = reinterpret_cast<const uint2*>(src)[q];
+            a01 = av.x; a23 = av.y;
+        } else {
+            if ((q & 1) == 0) av4 = __ldg(reinterpret_cast<const uint4*>(src) + (q >> 1));
+            a01 = (q & 1) ? av4.z : av4.x; a23 = (q & 1) ? av4.w : av4.y;
         }
+        uint32_t w[4], fi[4], fq[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { w[e] = s_tab[nco_bigtab_index(P >> 21, nco_fine_level(P))]; P += F; }
+        mix4(a01, a23, w, fi, fq, magic);
+        const uint32_t i01 = __byte_perm(fi[0], fi[1], 0x6251), i23 = __byte_perm(fi[2], fi[3], 0x6251);
+        const uint32_t q01 = __byte_perm(fq[0], fq[1], 0x6251), q23 = __byte_perm(fq[2], fq[3], 0x6251);
+        ilo[q] = __byte_perm(i01, i23, 0x5410); ihi[q] = __byte_perm(i01, i23, 0x7632);
+        qlo[q] = __byte_perm(q01, q23, 0x5410); qhi[q] = __byte_perm(q01, q23, 0x7632);
+        if (WRAP) { ihi[q] &= 0x7F7F7F7Fu; qhi[q] &= 0x7F7F7F7Fu; }
     }
 }
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 }  // namespace tc
 
+template <bool STAGE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restrict__ wrap_flag, uint32_t n_chunks, const uint32_t* __restrict__ tab_h,
                     const uint32_t* __restrict__ fcw, const uint32_t* __restrict__ phase, uint32_t n_ch_pad, const uint8_t* __restrict__ wplanes,
@@ -124,8 +134,9 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
     extern __shared__ __align__(128) uint8_t s_dyn[];
     uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_dyn);
     uint8_t* s_w = s_dyn + (size_t)kBigTabWords * 4;
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_w + kTcWeightBytes);              // [g][6]: full0 full1 free0 free1 acc_ready acc_free
-    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + kTcWg * 6);                 // [0] TMEM base, [1 + g] tile of warpgroup g, [8] 1.5 * 2^23
+    uint8_t* s_adc = s_w + kTcWeightBytes;                                            // [g][2][512] binary16: this tile's and the next tile's chunk
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_adc + kTcAdcStageBytes);          // [g][6]: full0 full1 free0 free1 acc_ready acc_free
+    uint32_t* s_misc = reinterpret_cast<uint32_t*>(s_bar + kTcWg * 6);                 // [0] TMEM base, [1 + 2g + (it & 1)] tile slots, [9] 1.5 * 2^23
     uint64_t* s_tabbar = reinterpret_cast<uint64_t*>(s_misc + 10);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
 
@@ -136,7 +147,7 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
             mbar_init(&s_bar[g * 6 + 5], 128);
         }
         mbar_init(s_tabbar, 1);
-        s_misc[8] = 0x4B400000u;
+        s_misc[9] = 0x4B400000u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(s_tabbar, (uint32_t)kBigTabWords * 4u + (uint32_t)kTcWeightBytes);
         for (uint32_t off = 0; off < (uint32_t)kBigTabWords * 4u; off += 16384u)
@@ -167,19 +178,30 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
         uint32_t par_free[2] = {0, 0}, par_acc = 0;
         uint32_t n_done = 0;                                              // slices stored so far (first use of each A buffer needs no wait)
         float magic;                                                      // a LOADED value: ptxas re-materialises a constant before every FMA
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(magic) : "r"(smem_u32(&s_misc[8])));
-        for (;;) {
-            if (tg == 0) s_misc[1 + g] = atomicAdd(tile_counter, 1u);
-            tc::named_bar(1 + g, 160);
-            const uint32_t tile = s_misc[1 + g];
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(magic) : "r"(smem_u32(&s_misc[9])));
+        // Tiles are fetched one ahead (two slots per warpgroup) so that the NEXT tile's ADC chunk can be copied into shared
+        // memory (cp.async, 8 bytes per thread) while the current one is computed.
+        uint32_t* s_tile = &s_misc[1 + 2 * g];
+        uint8_t* adc_buf = s_adc + (size_t)g * (2 * kCicR * 2);
+        if (tg == 0) { s_tile[0] = atomicAdd(tile_counter, 1u); s_tile[1] = atomicAdd(tile_counter, 1u); }
+        tc::named_bar(1 + g, 160);
+        if (STAGE) {
+            const uint32_t first = s_tile[0];
+            if (first < n_tiles) tc::cp_async8(adc_buf + tg * 8, adc_h + (size_t)(first / n_cg) * kCicR + tg * 4);
+            tc::cp_async_wait_all();
+            tc::named_bar(5 + g, 128);
+        }
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t tile = s_tile[it & 1u], next = s_tile[(it + 1u) & 1u];
             if (tile >= n_tiles) break;
+            if (STAGE && next < n_tiles) tc::cp_async8(adc_buf + ((it + 1u) & 1u) * (kCicR * 2) + tg * 8, adc_h + (size_t)(next / n_cg) * kCicR + tg * 4);
             const uint32_t cg = tile % n_cg, chunk = tile / n_cg;         // channel group fastest: neighbours share the ADC chunk in L1/L2
             const uint32_t ch = cg * 128u + (uint32_t)tg;
             const bool live = ch < n_ch_pad;
             const uint32_t chl = live ? ch : n_ch_pad - 1u;
             const uint32_t F = fcw[chl] << 10;
             uint32_t P = (phase[chl] << 10) + F * (chunk * (uint32_t)kCicR);
-            const uint4* a8 = reinterpret_cast<const uint4*>(adc_h + (size_t)chunk * kCicR);
+            const uint8_t* a_src = STAGE ? adc_buf + (it & 1u) * (kCicR * 2) : reinterpret_cast<const uint8_t*>(adc_h + (size_t)chunk * kCicR);
             const bool wrap = wrap_flag[chunk] != 0;
             auto slices = [&](auto wrap_tag) {                            // the chunk's 16 slices; two copies of the loop, with and without the mask
                 constexpr bool kWrap = decltype(wrap_tag)::value;
@@ -187,7 +209,7 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
                 for (int s = 0; s < kTcSlices; ++s, ++n_done) {
                     const int b = s & 1;
                     uint32_t ilo[8], ihi[8], qlo[8], qhi[8];
-                    tc::slice_planes<kWrap>(s_tab, a8 + s * 4, P, F, magic, ilo, ihi, qlo, qhi);
+                    tc::slice_planes<kWrap, STAGE>(s_tab, a_src + s * 64, P, F, magic, ilo, ihi, qlo, qhi);
                     if (n_done >= 2) { mbar_wait(&bar_free[b], par_free[b]); par_free[b] ^= 1; }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_col = col0 + lane_off + 64 + 32 * b;
@@ -200,6 +222,9 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
             if (wrap) slices(std::true_type{});
             else slices(std::false_type{});
             mbar_wait(bar_acc_ready, par_acc); par_acc ^= 1;
+            // every thread of the warpgroup and the issuer have read this tile's slot (their arrivals / MMAs precede acc_ready):
+            // it now takes the tile after next
+            if (tg == 0) s_tile[it & 1u] = atomicAdd(tile_counter, 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             uint32_t d_ilo[16], d_ihi[16], d_qlo[16], d_qhi[16];
             tc::tmem_ld16(col0 + lane_off + 0, d_ilo); tc::tmem_ld16(col0 + lane_off + 16, d_ihi);
@@ -220,15 +245,18 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
 #pragma unroll
                 for (int k = 0; k < 5; ++k) d2[k] = make_ulonglong2(out[2 * k], out[2 * k + 1]);
             }
+            if (STAGE) tc::cp_async_wait_all();
+            tc::named_bar(1 + g, 160);                                    // publishes the new slot and the next chunk's samples
         }
     } else {
         // instruction descriptor: D int32, A and B unsigned 8 bit, both K-major, N = 16, M = 128
         const uint32_t idesc = (2u << 4) | ((uint32_t)(kTcN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         uint32_t par_full[2] = {0, 0}, par_acc_free = 0;
         uint32_t n_tiles_done = 0;
-        for (;;) {
-            tc::named_bar(1 + g, 160);
-            const uint32_t tile = s_misc[1 + g];
+        const uint32_t* s_tile = &s_misc[1 + 2 * g];
+        tc::named_bar(1 + g, 160);
+        for (uint32_t it = 0;; ++it) {
+            const uint32_t tile = s_tile[it & 1u];
             if (tile >= n_tiles) break;
             if (lane == 0) {
                 for (int s = 0; s < kTcSlices; ++s) {
@@ -251,6 +279,7 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
             }
             ++n_tiles_done;
             __syncwarp();
+            tc::named_bar(1 + g, 160);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
