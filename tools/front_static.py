@@ -97,7 +97,11 @@ def update(csv_path, lib=LIB):
         rec["sass_instructions_per_unit"] = f("smsp__inst_executed.sum") * 32.0 / UNITS
         if "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg" in rows:      # per-SM average x SMs = wavefronts per launch
             n_sm = f("device__attribute_multiprocessor_count")
-            rec["lsu_wavefronts_per_unit"] = f("SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg") * n_sm / UNITS
+            if rows["SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg"][c] != "no data":
+                per_sm = f("SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg")
+            else:                                   # ncu sometimes drops the triage counter: busy fraction x elapsed cycles (1 wavefront/clk/SM)
+                per_sm = f("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed") / 100.0 * f("sm__cycles_elapsed.avg")
+            rec["lsu_wavefronts_per_unit"] = per_sm * n_sm / UNITS
             rec["lsu_wavefronts_shared_per_unit"] = f("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum") / UNITS
             rec["lsu_pipe_pct_ncu"] = f("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")
         if "sm__ops_path_tensor_op_utcimma_src_int8_sparsity_off.avg.pct_of_peak_sustained_elapsed" in rows:

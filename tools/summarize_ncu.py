@@ -17,7 +17,7 @@ KEEP = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
-        'sm__cycles_elapsed.max', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
+        'sm__cycles_elapsed.max', 'sm__cycles_elapsed.avg', 'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio',
