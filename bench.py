@@ -57,6 +57,9 @@ def parse():
     ap.add_argument("--workload", default="all", choices=["all", "ddc", "full_chain"])
     ap.add_argument("--comm-sms", type=int, default=None,
                     help="N>1: SMs the front kernel leaves to the NCCL broadcast kernel (default 1; NCCL is held to as many channels)")
+    ap.add_argument("--adc-transport", default="nccl", choices=["auto", "ipc", "nccl"],
+                    help="N>1: how the ADC block reaches the ranks: ipc = ua3reo_fanout_* (copy engines over CUDA IPC mappings, "
+                         "no SM), nccl = NCCL broadcast on a side stream (one SM set aside); auto = ipc, nccl if it cannot be set up")
     return ap.parse_args()
 
 
@@ -261,9 +264,29 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
     fcw_all = synth.random_fcw(n_ch * world, SEED)
     my_fcw = fcw_all[rank * n_ch:(rank + 1) * n_ch]                      # channels sharded by rank, contiguous slabs
     rx.set_fcw(my_fcw)
-    if world > 1:
-        rx.reserve_sms(args.comm_sms if args.comm_sms is not None else 1)      # the broadcast of block i+1 runs UNDER the kernels of block i
     ext = torch.cuda.ExternalStream(rx.stream(), device=local)
+    # N>1: rank 0's ADC blocks reach every rank over NVLink, block i+1 while block i is computed.  Preferred: ua3reo_fanout_*
+    # (sharding.AdcFanout: the ingest rank's copy engines write into every rank's slot through CUDA IPC mappings, the consumer
+    # streams wait on a flag word - no kernel, no SM).  Fallback: an NCCL broadcast on a side stream (sharding.AdcBroadcaster:
+    # two buffers, events both ways); its kernel cannot share an SM with a front CTA, so one SM is set aside for it.
+    bc, transport = None, "none"
+    if world > 1 and args.adc_transport in ("auto", "ipc"):
+        try:
+            bc = pkg.sharding.AdcFanout(rx.lib, block, local, rx.stream(), src=0, dist=dist)
+            transport = "cuda-ipc copy engines (ua3reo_fanout_*)"
+        except pkg.UA3Error as e:
+            if args.adc_transport == "ipc":
+                raise
+            if rank == 0:
+                print("bench.py: %s - falling back to the NCCL broadcast" % e, file=sys.stderr)
+    if world > 1 and bc is None:
+        bc = pkg.sharding.AdcBroadcaster(block, torch.device("cuda", local), src=0, dist=dist, consumer_stream=ext)
+        transport = "nccl broadcast"
+    # SMs kept out of the front kernel for NCCL kernels: the broadcast, and in the full chain the spectra gather
+    comm_sms = args.comm_sms if args.comm_sms is not None else \
+        (1 if world > 1 and (transport == "nccl broadcast" or workload == "full_chain") else 0)
+    if world > 1:
+        rx.reserve_sms(comm_sms)
     audio_host = spec_host = None
     if full:
         # the STM32 stage for every channel; it runs on its own stream one push behind the DDC
@@ -316,10 +339,6 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    # N>1: rank 0 broadcasts every ADC block over NVLink (NCCL); the broadcast of block i+1 runs on a side stream while
-    # the context's stream computes block i (sharding.AdcBroadcaster: two buffers, events both ways)
-    bc = pkg.sharding.AdcBroadcaster(block, torch.device("cuda", local), src=0, dist=dist, consumer_stream=ext) if world > 1 else None
 
     def run_steps(n, src_blocks, after_push=None, to_host=False):
         if bc is not None:
@@ -569,7 +588,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
         workload_s = ("BASELINE configs[2]/[3]: %d independent DDC channels per GPU (random tuning words, seed %d) "
                       "over one shared synthetic 12-bit ADC stream, blocks of %d samples; full FPGA RX chain "
                       "(NCO+mixer+CIC/512+compensator FIR+Hilbert FIR+Q delay+8-byte frames); "
-                      "N>1: channels sharded by rank, ADC block NCCL-broadcast from rank 0" % (n_ch, SEED, block))
+                      "N>1: channels sharded by rank, ADC block sent from rank 0 (config.adc_transport)" % (n_ch, SEED, block))
         if full:
             workload_s = ("BASELINE configs[4]: full per-channel RX chain for %d channels per GPU - " % n_ch) + workload_s.split(": ", 1)[1] + \
                          "; then processRxAudio + FFT_doFFT per channel (modes LSB/USB/CW_U/AM/NFM round-robin, DNR + notch on half)" + \
@@ -634,7 +653,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                        "channels_total": n_ch * world, "channels_per_gpu": n_ch, "block_samples": block,
                        "real_time_channels": value / 49152000.0,
                        "clocking_class": "B/3/129 (the board's most frequent frame alignment, DESIGN.md 2)",
-                       "comm_sms": (args.comm_sms if args.comm_sms is not None else 1) if world > 1 else 0,
+                       "comm_sms": comm_sms, "adc_transport": transport,
                        "l2": "per-step working set ~%.0f MB (chunk records + frames) exceeds the 126 MB L2; no flush needed"
                              % (step_bytes / 1e6)},
             "e2e": {"value": e2e, "unit": "channel*samples/s", "h2d_bytes_per_step": 2 * block,
@@ -645,7 +664,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                             "(4 x 64 MB each), the box's ceiling for results leaving the GPUs"},
             "gpu_launches": int(launches),
             "parity": {"ddc_ranks_ok": int(oks[0]), "ranks": world, "channels_checked_per_rank": len(picks),
-                       "ddc_check": "frames of one more block (NCCL-broadcast at N>1) == golden model, bit for bit",
+                       "ddc_check": "frames of one more block (received from rank 0 at N>1) == golden model, bit for bit",
                        "stm32_ranks_ok": (int(oks[1]) if full and audio_ok is not None else None), "stm32_check": audio_note},
             "roofline": roofline,
             "cpu_baseline": cpu,
@@ -673,6 +692,8 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
         del gather_spectra, spec_dev, spec_all, spec_all_host, cstream, gstream, ev_spec, ev_gdone, gather_pg
         gc.collect()
     torch.cuda.synchronize()
+    if bc is not None and hasattr(bc, "close"):
+        bc.close()                                     # collective: peers unmapped, barrier, arenas freed
     del bc
     rx.close()
     return line

@@ -256,6 +256,9 @@ int ua3reo_adc_stats(ua3reo_ctx *ctx, int16_t *adc_min, int16_t *adc_max, uint32
  * the two values FPGA_fpgadata_getparam() (fpga.c:222-284) decodes from them - TRX_ADC_MINAMPLITUDE sign-extended,
  * TRX_ADC_MAXAMPLITUDE not (a firmware quirk, kept).  ADC_OTR (bit 0) = a sample reached a rail since the last read;
  * DAC_OTR (bit 1) = dac_otr as given by the caller (e.g. a change of ua3reo_duc_read_otr()); key/encoder bits are 0.
+ * Byte 4 carries bits 7:5 of byte 3, as on the wire: the state machine assigns only DATA_BUS_OUT[4:0] there (k == 204) and
+ * the firmware masks them off.  (Bits 7:6 of byte 0 are likewise left over on the board - from the last byte of whatever
+ * command came before, so they are not part of this packet's definition and are returned as 0.)
  * packet and either amplitude pointer may be NULL. */
 int ua3reo_get_params(ua3reo_ctx *ctx, uint8_t packet[5], int16_t *adc_min_amplitude, int16_t *adc_max_amplitude, int dac_otr);
 /* TRX_DoAutoGain() (trx_manager.c:268-356, called every 100 ms from stm32f4xx_it.c:422): the ATT / preamp decision
@@ -370,6 +373,38 @@ int ua3reo_bank_rx_counts(ua3reo_bank *bank, size_t *audio_blocks, size_t *fft_f
 int ua3reo_bank_rx_read_audio(ua3reo_bank *bank, int32_t *dst_host, size_t n_blocks);
 int ua3reo_bank_rx_read_spectra(ua3reo_bank *bank, float *dst_host, size_t n_frames);
 int ua3reo_bank_sync(ua3reo_bank *bank);
+
+/* ---------------------------------------------------------------------------------------------
+ * The same fan-out for one PROCESS per GPU (the torch.distributed launch; a C host with one process per device): no
+ * collective kernel and no SM.  Every rank creates its end, the 64-byte handles are exchanged by whatever transport the
+ * host has (bench.py: one all_gather at start-up), and from then on a block travels as
+ *     ingest rank:  ua3reo_fanout_send(f, block)                    copy engines write the block into every rank's slot over
+ *                                                                   NVLink (CUDA IPC mappings) and then store its number there
+ *     every rank:   ua3reo_fanout_acquire(f, stream, &blk)           `stream` waits for that number (cuStreamWaitValue32)
+ *                   ua3reo_ddc_push_device(ctx, blk, n, &frames)     consumed in place (DEVICE PUSH CONTRACT above)
+ *                   ua3reo_fanout_release(f, stream)                 the slot's credit goes back behind the push's kernels
+ * Nothing here orders the processes' HOST threads: the waits are executed by the streams.  Sends run `n_buffers` - 1 blocks
+ * ahead of the slowest consumer.  The reference has one board = one ADC = one channel (fpga.c:286-401 reads it frame by
+ * frame); this is the path's only exchange when its channels are spread over devices.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ua3reo_fanout ua3reo_fanout;
+#define UA3_FANOUT_HANDLE_BYTES 64u
+/* rank of world, `src` ingests; slots of block_samples int16 each, 2 <= n_buffers <= 16.  world == 1 needs no connect. */
+int ua3reo_fanout_create(int device, int rank, int world, int src, size_t block_samples, int n_buffers, ua3reo_fanout **out);
+/* Tear-down in two steps, because an arena must outlive its peers' mappings: every rank disconnects (waits for its own
+ * fan-out streams, unmaps its peers) once all ranks' consumer streams are idle, then - after a host barrier - destroys. */
+int ua3reo_fanout_disconnect(ua3reo_fanout *f);
+int ua3reo_fanout_destroy(ua3reo_fanout *f);
+/* this rank's handle (UA3_FANOUT_HANDLE_BYTES) / all ranks' handles in rank order (world x UA3_FANOUT_HANDLE_BYTES) */
+int ua3reo_fanout_handle(ua3reo_fanout *f, void *handle64);
+int ua3reo_fanout_connect(ua3reo_fanout *f, const void *handles);
+/* ingest rank only; block: block_samples int16 in device or pinned host memory, valid until the copy has run; asynchronous */
+int ua3reo_fanout_send(ua3reo_fanout *f, const int16_t *block, size_t n);
+int ua3reo_fanout_acquire(ua3reo_fanout *f, void *consumer_stream, const int16_t **block_dev);
+int ua3reo_fanout_release(ua3reo_fanout *f, void *consumer_stream);
+int ua3reo_fanout_sync(ua3reo_fanout *f);      /* waits for this rank's send and credit streams */
+/* direct_remote_store: 1 if the driver stores flag words straight onto peer mappings, 0 if they are staged through a copy */
+int ua3reo_fanout_info(const ua3reo_fanout *f, int *direct_remote_store, uint64_t *n_sent, uint64_t *n_acquired);
 
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline):
  * after ua3reo_profile_begin(ctx, max_blocks) each processed ADC block records an event before and

@@ -26,7 +26,11 @@ static uint32_t bus_read(void) { const uint32_t v = ua3_bus_frame[ua3_bus_pos & 
 static uint32_t zero_read(void) { return 0; }
 GPIO_TypeDef ua3_gpio_a = {.idr_fn = bus_read}, ua3_gpio_b = {.idr_fn = zero_read}, ua3_gpio_c = {.idr_fn = zero_read},
              ua3_gpio_d = {.idr_fn = zero_read}, ua3_gpio_e = {.idr_fn = zero_read};
-void HAL_GPIO_Init(GPIO_TypeDef *g, GPIO_InitTypeDef *i) { (void)g; (void)i; }
+void HAL_GPIO_Init(GPIO_TypeDef *g, GPIO_InitTypeDef *i)            /* the direction bits only: bus_hdl.c resolves the bus with them */
+{
+    for (uint32_t p = 0; p < 16; p++)
+        if (i->Pin & (1u << p)) g->MODER = (g->MODER & ~(3u << (2 * p))) | ((i->Mode & 3u) << (2 * p));
+}
 void HAL_GPIO_WritePin(GPIO_TypeDef *g, uint16_t p, GPIO_PinState s) { (void)g; (void)p; (void)s; }
 GPIO_PinState HAL_GPIO_ReadPin(GPIO_TypeDef *g, uint16_t p) { (void)g; (void)p; return GPIO_PIN_RESET; }
 

@@ -24,12 +24,24 @@ typedef enum { GPIO_PIN_RESET = 0, GPIO_PIN_SET } GPIO_PinState;
 #define HAL_MAX_DELAY 0xFFFFFFFFU
 
 typedef struct ua3_gpio {
-    __IO uint32_t MODER, OTYPER, OSPEEDR, PUPDR;
+    __IO uint32_t moder_slot[1], OTYPER, OSPEEDR, PUPDR;   /* MODER: see BSRR below */
     uint32_t (*idr_fn)(void);            /* stands in for the IDR register: see IDR below */
-    __IO uint32_t ODR, BSRR, LCKR;
+    __IO uint32_t ODR, bsrr_slot[1], LCKR;   /* BSRR: see below */
     __IO uint32_t AFR[2];
 } GPIO_TypeDef;
 #define IDR idr_fn()
+/* BSRR is write-only set/reset.  Plain builds keep the last word written.  With -DUA3_BUS_HDL (fpga.c linked against the
+ * reference's own stm32_interface.v, oracle/ref_harness/bus_hdl.c) every store `GPIOx->BSRR = v` first calls the hook, which
+ * applies the PREVIOUS store to the pins (and clocks the Verilog model on a rising FPGA_CLK edge) - the index expression is
+ * evaluated before the store, so the pin writes reach the model one by one, in program order. */
+#ifdef UA3_BUS_HDL
+int ua3_bsrr_hook(void);
+#define BSRR bsrr_slot[ua3_bsrr_hook()]
+#define MODER moder_slot[ua3_bsrr_hook()]   /* a direction change must not overtake the pin write before it */
+#else
+#define BSRR bsrr_slot[0]
+#define MODER moder_slot[0]
+#endif
 typedef struct { uint32_t Pin, Mode, Pull, Speed, Alternate; } GPIO_InitTypeDef;
 extern GPIO_TypeDef ua3_gpio_a, ua3_gpio_b, ua3_gpio_c, ua3_gpio_d, ua3_gpio_e;
 #define GPIOA (&ua3_gpio_a)

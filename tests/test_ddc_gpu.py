@@ -256,7 +256,7 @@ def test_get_params_packet(pkg, oracle):
     lo, hi = int(adc.min()), int(adc.max())
     assert lo < 0 < hi
     assert pkt[0] == 0                                    # no sample at a rail, no DAC overflow, no keys
-    assert pkt[1] == (((lo & 0xFFF) >> 8) << 4 | ((hi & 0xFFF) >> 8)) and pkt[2] == (lo & 0xFF) and pkt[3] == (hi & 0xFF) and pkt[4] == 0
+    assert pkt[1] == (((lo & 0xFFF) >> 8) << 4 | ((hi & 0xFFF) >> 8)) and pkt[2] == (lo & 0xFF) and pkt[3] == (hi & 0xFF) and pkt[4] == (hi & 0xE0)
     assert (mn, mx) == (lo, hi)
     assert rx.adc_stats() == (2000, -2000, 0)             # the read reset the extremes (ADC_MINMAX_RESET, k == 203)
     rx.push(np.full(1 << 12, -7, np.int16))
@@ -267,6 +267,22 @@ def test_get_params_packet(pkg, oracle):
     rx.push(rail)
     pkt, mn, mx = rx.get_params()
     assert pkt[0] == 1 and (mn, mx) == (0, 2047)          # ADC_OTR
+    rx.close()
+
+
+def test_get_params_equals_the_executed_bus(pkg):
+    """ua3reo_get_params against tests/golden/bus_cases.npz: the five bytes the firmware's own FPGA_fpgadata_getparam() read
+    from the reference's stm32_interface.v (executed from its source, tools/gen_golden_bus.py) for the same ADC samples, and
+    the two amplitudes it decoded."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bus_cases.npz"))
+    rx = pkg.Receiver(2, 1 << 12)
+    for adc, (otr, dac), packet, decoded in zip(g["gp_adc"], g["gp_flags"], g["gp_packet"], g["gp_decoded"]):
+        rx.get_params()                                   # the read before: ADC_MINMAX_RESET
+        rx.push(adc)
+        pkt, mn, mx = rx.get_params(dac_otr=bool(dac))
+        assert np.array_equal(pkt, packet), (pkt, packet)
+        assert (mn, mx) == (int(np.int16(decoded[0])), int(np.int16(decoded[1])))
+        assert (pkt[0] & 1) == otr
     rx.close()
 
 

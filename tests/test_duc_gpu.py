@@ -1,4 +1,6 @@
 """Transmit DUC on the GPU against the golden model: bit-exact 14-bit DAC words."""
+import os
+
 import numpy as np
 import pytest
 
@@ -76,3 +78,22 @@ def test_duc_wire_order_entry(pkg, oracle):
     assert np.array_equal(out[0], out[1])
     ref, _ = oracle.GoldenDUC(fcw[0]).push(iq[0, :, 0], iq[0, :, 1])
     assert np.array_equal(out[1][0], ref)
+
+
+def test_duc_wire_entry_equals_the_executed_bus(pkg, oracle):
+    """tests/golden/bus_cases.npz: the command-3 bytes as the firmware's own FPGA_fpgadata_sendiq() put them on the bus and the
+    TX_I / TX_Q that the reference's stm32_interface.v (executed from its source text) latched from them.  The product's
+    wire-order entry fed those bytes must produce the DAC stream of the golden DUC fed the latched words."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bus_cases.npz"))
+    wire, latched = g["tx_wire"][:32], g["tx_latched"][:32]
+    assert np.array_equal(latched, g["tx_iq"][:32])
+    fcw = np.array([620407, 1234567], np.uint32)
+    rx = pkg.Receiver(2, 1 << 14)
+    rx.set_fcw(fcw)
+    rx.duc_enable(32)
+    rx.duc_push_wire(np.broadcast_to(wire, (2,) + wire.shape).copy())
+    dac = rx.duc_read_dac()
+    rx.close()
+    for c in range(2):
+        ref, _ = oracle.GoldenDUC(int(fcw[c])).push(latched[:, 0], latched[:, 1])
+        assert np.array_equal(dac[c], ref)

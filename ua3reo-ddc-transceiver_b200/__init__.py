@@ -32,6 +32,14 @@ class UA3Error(RuntimeError):
     pass
 
 
+class DeviceBlock:
+    """n int16 ADC samples at device address ptr, already ordered for the context's stream (Receiver.push takes it as is)."""
+    __slots__ = ("ptr", "n")
+
+    def __init__(self, ptr, n):
+        self.ptr, self.n = int(ptr), int(n)
+
+
 # trx_manager.h:11-24
 MODE_LSB, MODE_USB, MODE_IQ, MODE_CW_L, MODE_CW_U, MODE_DIGI_L, MODE_DIGI_U, MODE_NO_TX, MODE_NFM, MODE_WFM, MODE_AM, \
     MODE_LOOPBACK = range(12)
@@ -143,6 +151,16 @@ def _bind(lib):
         "ua3reo_bank_rx_read_audio": (c.c_int, [vp, vp, sz]),
         "ua3reo_bank_rx_read_spectra": (c.c_int, [vp, vp, sz]),
         "ua3reo_bank_sync": (c.c_int, [vp]),
+        "ua3reo_fanout_create": (c.c_int, [c.c_int, c.c_int, c.c_int, c.c_int, sz, c.c_int, c.POINTER(vp)]),
+        "ua3reo_fanout_destroy": (c.c_int, [vp]),
+        "ua3reo_fanout_disconnect": (c.c_int, [vp]),
+        "ua3reo_fanout_handle": (c.c_int, [vp, vp]),
+        "ua3reo_fanout_connect": (c.c_int, [vp, vp]),
+        "ua3reo_fanout_send": (c.c_int, [vp, vp, sz]),
+        "ua3reo_fanout_acquire": (c.c_int, [vp, vp, c.POINTER(vp)]),
+        "ua3reo_fanout_release": (c.c_int, [vp, vp]),
+        "ua3reo_fanout_sync": (c.c_int, [vp]),
+        "ua3reo_fanout_info": (c.c_int, [vp, c.POINTER(c.c_int), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]),
         "ua3reo_sync": (c.c_int, [vp]),
         "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_launch_count": (c.c_uint64, [vp]),
@@ -284,7 +302,9 @@ class Receiver:
         assume_ordered: the caller has already ordered the library stream after the tensor's producer and keeps the
         tensor alive and unchanged until the push completes (sharding.AdcBroadcaster does)."""
         n = ctypes.c_size_t(0)
-        if isinstance(adc, np.ndarray):
+        if isinstance(adc, DeviceBlock):       # a raw device block whose ordering the producer took care of (sharding.AdcFanout)
+            self._chk(self.lib.ua3reo_ddc_push_device(self._h, adc.ptr, adc.n, ctypes.byref(n)))
+        elif isinstance(adc, np.ndarray):
             a = np.ascontiguousarray(adc, dtype=np.int16)
             self._keep = a
             self._chk(self.lib.ua3reo_ddc_push(self._h, a.ctypes.data, a.size, ctypes.byref(n)))

@@ -24,6 +24,8 @@ static constexpr int kRxReserveSmall = 5, kRxReserveLarge = 4;   // at least; th
 static constexpr int kProfEvents = kDdcKernels + 3;   // 5 DDC kernels, rx_audio, rx_fft: 8 event points per block
 static thread_local std::string g_err;
 
+void ua3_set_last_error(const char* what) { g_err = what; }   // for the other translation units (fanout.cu)
+
 static int fail(int code, const char* what, cudaError_t e = cudaSuccess) {
     g_err = what;
     if (e != cudaSuccess) { g_err += ": "; g_err += cudaGetErrorString(e); }
@@ -1005,7 +1007,9 @@ int ua3reo_get_params(ua3reo_ctx* c, uint8_t packet[5], int16_t* adc_min_amplitu
     b[1] = (uint8_t)(((min12 >> 8) << 4) | (max12 >> 8));
     b[2] = (uint8_t)(min12 & 0xFFu);
     b[3] = (uint8_t)(max12 & 0xFFu);
-    b[4] = 0;
+    // k == 204 assigns DATA_BUS_OUT[4:0] only (encoder = 0, no key): bits 7:5 still carry those of the byte before
+    // (found by running fpga.c against the executed stm32_interface.v; tests/golden/bus_cases.npz)
+    b[4] = (uint8_t)(b[3] & 0xE0u);
     if (packet) std::memcpy(packet, b, 5);
     // decode as the firmware does: the minimum is sign-extended through <<4, /16; the maximum is NOT (fpga.c:247-270)
     int16_t dmin = 0, dmax = 0;

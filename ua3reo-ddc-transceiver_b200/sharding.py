@@ -111,6 +111,112 @@ class AdcBroadcaster:
         return self.acquire()
 
 
+class AdcFanout:
+    """The same pipeline as AdcBroadcaster without a collective kernel: ua3reo_fanout_* (csrc/fanout.cu) - the ingest rank's
+    copy engines write every block into each rank's slot over NVLink (CUDA IPC mappings) and the consumer STREAMS wait on
+    a flag word, so no SM has to be kept free for the transfer and the ranks' host threads never meet.  Same calls:
+
+        fo.prefetch(block)            # rank `src` passes its block (device tensor, pinned host tensor or numpy view), the others None
+        buf = fo.acquire()            # DeviceBlock; the consumer stream now waits for that block's flag
+        rx.push(buf)
+        fo.release(buf)               # the slot's credit returns behind the push
+
+    Construction is collective (one all_gather of the 64-byte handles); it raises UA3Error on EVERY rank when any rank
+    could not map its peers, so that the caller can fall back to AdcBroadcaster on all of them."""
+
+    def __init__(self, lib, block_samples, device_index, consumer_stream, src=0, dist=None, n_buffers=3, group=None):
+        import ctypes
+        import torch
+        from . import UA3Error, DeviceBlock
+        self._ct, self._DeviceBlock, self._err = ctypes, DeviceBlock, UA3Error
+        self.lib, self.dist, self.group, self.src = lib, dist, group, src
+        self.block = int(block_samples)
+        self.world = 1 if dist is None else dist.get_world_size(group)
+        self.rank = 0 if dist is None else dist.get_rank(group)
+        self.consumer = ctypes.c_void_p(int(consumer_stream))
+        self.n_buffers = int(n_buffers)
+        self.n_filled = self.n_taken = 0
+        self._keep = []
+        h = ctypes.c_void_p()
+        rc = lib.ua3reo_fanout_create(int(device_index), self.rank, self.world, int(src), self.block, self.n_buffers, ctypes.byref(h))
+        msg = "" if rc == 0 else lib.ua3reo_last_error().decode()
+        self._h = h if rc == 0 else None
+        if rc == 0 and self.world > 1:
+            mine = (ctypes.c_uint8 * 64)()
+            rc = lib.ua3reo_fanout_handle(self._h, mine)
+            if rc != 0:
+                msg = lib.ua3reo_last_error().decode()
+        if self.world > 1:
+            # handles travel as CPU-side objects over the process group's store-backed path (tiny, once)
+            payload = [None] * self.world
+            dist.all_gather_object(payload, bytes(mine) if rc == 0 else None, group=group)
+            if rc == 0 and all(p is not None for p in payload):
+                allh = (ctypes.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(payload))
+                rc = lib.ua3reo_fanout_connect(self._h, allh)
+                if rc != 0:
+                    msg = lib.ua3reo_last_error().decode()
+            elif rc == 0:
+                rc, msg = -5, "a peer rank could not create its fan-out end"
+            oks = [None] * self.world
+            dist.all_gather_object(oks, (rc == 0, msg), group=group)
+            bad = [(r, m) for r, (ok, m) in enumerate(oks) if not ok]
+            if bad:                                    # every rank sees the same verdict: unmap, meet, free
+                if self._h is not None:
+                    lib.ua3reo_fanout_disconnect(self._h)
+                dist.barrier(group=group)
+                if self._h is not None:
+                    lib.ua3reo_fanout_destroy(self._h)
+                    self._h = None
+                raise UA3Error("AdcFanout: rank %d: %s" % bad[0])
+        elif rc != 0:
+            raise UA3Error("AdcFanout: %s" % msg)
+        self._torch = torch
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise self._err("ua3reo fan-out error %d: %s" % (rc, self.lib.ua3reo_last_error().decode()))
+
+    def prefetch(self, local_block=None):
+        assert self.n_filled - self.n_taken < self.n_buffers, "AdcFanout: every slot holds a block that was not acquired yet"
+        if self.rank == self.src:
+            ptr = local_block.ctypes.data if isinstance(local_block, np.ndarray) else local_block.data_ptr()
+            n = local_block.size if isinstance(local_block, np.ndarray) else local_block.numel()
+            self._keep = self._keep[-2 * self.n_buffers:] + [local_block]        # the copy reads it later
+            self._chk(self.lib.ua3reo_fanout_send(self._h, ptr, n))
+        self.n_filled += 1
+
+    def acquire(self):
+        assert self.n_taken < self.n_filled, "AdcFanout.acquire without a prefetch"
+        p = self._ct.c_void_p()
+        self._chk(self.lib.ua3reo_fanout_acquire(self._h, self.consumer, self._ct.byref(p)))
+        self.n_taken += 1
+        return self._DeviceBlock(p.value, self.block)
+
+    def release(self, buf=None):
+        self._chk(self.lib.ua3reo_fanout_release(self._h, self.consumer))
+
+    def next_block(self, local_block=None):
+        self.prefetch(local_block)
+        return self.acquire()
+
+    def info(self):
+        d, s, a = self._ct.c_int(), self._ct.c_uint64(), self._ct.c_uint64()
+        self._chk(self.lib.ua3reo_fanout_info(self._h, self._ct.byref(d), self._ct.byref(s), self._ct.byref(a)))
+        return {"direct_remote_store": bool(d.value), "sent": s.value, "acquired": a.value}
+
+    def close(self):
+        """COLLECTIVE: every rank calls it once its consumer stream is idle.  Peers are unmapped first, the arenas are freed
+        only after a barrier (an arena must outlive the mappings of it)."""
+        if self._h is not None:
+            if self.world > 1:
+                self.dist.barrier(group=self.group)          # every rank's last push has been synchronised by its caller
+            self.lib.ua3reo_fanout_disconnect(self._h)
+            if self.world > 1:
+                self.dist.barrier(group=self.group)
+            self.lib.ua3reo_fanout_destroy(self._h)
+            self._h = None
+
+
 def gather_rows(local_rows, n_total, dist):
     """All ranks contribute their slab's rows ([n_local, ...] tensors); rank 0 gets [n_total, ...] back (others None)."""
     import torch
