@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--workload", default="all", choices=["all", "ddc", "full_chain"])
     ap.add_argument("--comm-sms", type=int, default=None,
                     help="N>1: SMs the front kernel leaves to the NCCL broadcast kernel (default 1; NCCL is held to as many channels)")
-    ap.add_argument("--adc-transport", default="nccl", choices=["auto", "ipc", "nccl"],
+    ap.add_argument("--adc-transport", default="auto", choices=["auto", "ipc", "nccl"],
                     help="N>1: how the ADC block reaches the ranks: ipc = ua3reo_fanout_* (copy engines over CUDA IPC mappings, "
                          "no SM), nccl = NCCL broadcast on a side stream (one SM set aside); auto = ipc, nccl if it cannot be set up")
     return ap.parse_args()

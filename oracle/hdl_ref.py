@@ -107,6 +107,18 @@ def rx_chain(x_i, x_q, t_rx=0, delay_length=130):
     q_in = comp_seen("q", t_c2_abs)
     voice_q = np.zeros_like(q_in)
     voice_q[delay_length - 1:] = q_in[:q_in.size - (delay_length - 1)]              # after c2 edge j: in[j-(N-1)]
+    if delay_length == 130:
+        # ... and the same from data_delay.v itself (translated by tools/verilog_eval.py with the schematic's parameters)
+        from . import vlog_ref
+        if vlog_ref.available():
+            d = vlog_ref.VModule("data_delay_q")
+            executed = np.zeros_like(q_in)
+            for j, v in enumerate(q_in):
+                d["data_in"] = int(v)
+                d.clock("clk_in")
+                executed[j] = d.signed("data_out")
+            assert np.array_equal(executed, voice_q), "data_delay.v disagrees with its restatement"
+            voice_q = executed
 
     def hilb_seen(t_abs):
         k = np.searchsorted(t_c1_abs, t_abs, side="left") - 1

@@ -94,6 +94,8 @@ struct ua3reo_ctx {
     std::vector<RxParams> h_par;
     uint8_t* rx_flags = nullptr;        // device scratch for rx_set's state-clear flags
     float* stage_buf = nullptr;         // device scratch of ua3reo_rx_stage: 2 x 4096 floats
+    float* usb_undo = nullptr;          // device scratch of ua3reo_rx_read_audio_usb: per-channel volume undo ...
+    int16_t* usb_out = nullptr;         // ... and the packed int16 words of the largest push
     int32_t* adc_stats = nullptr;       // device: min, max, samples at the rails (since the last reset)
     bool adc_stats_on = false;
     size_t last_audio_blocks = 0, last_fft_frames = 0;
@@ -116,6 +118,20 @@ static cudaError_t dev_alloc(ua3reo_ctx* c, T** p, size_t n) {
     c->allocs.push_back(*p);
     return cudaMemsetAsync(*p, 0, n * sizeof(T), c->stream);
 }
+
+// Set-up calls (rx_allocate, ua3reo_duc_enable, ua3reo_tx_enable) allocate many buffers; when one of them fails the
+// buffers this call already took are given back, so that a retry does not leak and no half-built stage is left behind.
+struct AllocScope {
+    ua3reo_ctx* c;
+    size_t mark;
+    bool ok = false;
+    explicit AllocScope(ua3reo_ctx* c_) : c(c_), mark(c_->allocs.size()) {}
+    ~AllocScope() {
+        if (ok) return;
+        cudaStreamSynchronize(c->stream);                 // the memsets of dev_alloc
+        while (c->allocs.size() > mark) { cudaFree(c->allocs.back()); c->allocs.pop_back(); }
+    }
+};
 
 extern "C" {
 
@@ -571,6 +587,7 @@ static int rx_upload_order(ua3reo_ctx* c) {
 
 static int rx_allocate(ua3reo_ctx* c) {
     if (c->rx_alloc) return UA3_OK;
+    AllocScope scope(c);
     RxBuffers& r = c->rx;
     r.n_ch = c->n_ch;
     r.frames = c->b.frames; r.ring_mask = c->b.ring_mask; r.frame_ch_stride = c->b.frame_ch_stride;
@@ -620,7 +637,7 @@ static int rx_allocate(ua3reo_ctx* c) {
     UA3_CUDA(cudaStreamSynchronize(c->stream));
     const int rc = rx_upload_order(c);
     if (rc != UA3_OK) return rc;
-    c->rx_alloc = true;
+    c->rx_alloc = scope.ok = true;
     return UA3_OK;
 }
 
@@ -885,19 +902,28 @@ int ua3reo_rx_read_audio_usb(ua3reo_ctx* c, int16_t* dst, size_t n_blocks) {
     { const int qrc = rx_quiesce(c); if (qrc != UA3_OK) return qrc; }
     if (!n_blocks) return UA3_OK;
     const size_t n_words = n_blocks * 2 * UA3_AUDIO_BLOCK;
+    // audio_processor.c:420 undoes the volume with 1 / volume * 100.  Volume 0 makes that inf and the word 0 * inf = NaN, whose
+    // conversion to int16 is undefined in C; here a muted-by-volume channel reads as silence.
     std::vector<float> undo(c->n_ch);
-    for (uint32_t i = 0; i < c->n_ch; ++i) undo[i] = 1.0f / (float)c->h_set[i].volume * 100.0f;   // audio_processor.c:420
-    float* undo_dev = nullptr;
-    int16_t* out_dev = nullptr;
-    UA3_CUDA(cudaMalloc(&undo_dev, sizeof(float) * c->n_ch));
-    cudaError_t e = cudaMalloc(&out_dev, sizeof(int16_t) * c->n_ch * n_words);
-    if (e != cudaSuccess) { cudaFree(undo_dev); return fail(UA3_E_CUDA, "cudaMalloc", e); }
+    for (uint32_t i = 0; i < c->n_ch; ++i) undo[i] = c->h_set[i].volume ? 1.0f / (float)c->h_set[i].volume * 100.0f : 0.0f;
+    // scratch of the call, allocated once for the largest push (the firmware shim calls this for every 192-sample block:
+    // a cudaMalloc / cudaFree pair per call would synchronise the device each time)
+    if (!c->usb_undo) {
+        AllocScope scope(c);
+        float* u = nullptr;
+        int16_t* o = nullptr;
+        UA3_CUDA(dev_alloc(c, &u, (size_t)c->n_ch));
+        UA3_CUDA(dev_alloc(c, &o, (size_t)c->n_ch * c->rx.max_audio_blocks * 2 * UA3_AUDIO_BLOCK));
+        c->usb_undo = u; c->usb_out = o;
+        scope.ok = true;
+    }
+    float* undo_dev = c->usb_undo;
+    int16_t* out_dev = c->usb_out;
     int launches = 0;
-    e = cudaMemcpyAsync(undo_dev, undo.data(), sizeof(float) * c->n_ch, cudaMemcpyHostToDevice, c->stream);
+    cudaError_t e = cudaMemcpyAsync(undo_dev, undo.data(), sizeof(float) * c->n_ch, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = rx_launch_usb_pack(c->rx, (uint32_t)n_blocks, undo_dev, out_dev, c->stream, &launches);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dst, out_dev, sizeof(int16_t) * c->n_ch * n_words, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(undo_dev); cudaFree(out_dev);
     c->launches += (uint64_t)launches;
     if (e != cudaSuccess) return fail(UA3_E_CUDA, "ua3reo_rx_read_audio_usb", e);
     return UA3_OK;
@@ -1142,6 +1168,7 @@ int ua3reo_duc_enable(ua3reo_ctx* c, uint32_t max_tx_samples) {
     if (!c || max_tx_samples == 0) return fail(UA3_E_INVAL, "ua3reo_duc_enable: bad arguments");
     if (c->duc_alloc) return (max_tx_samples <= c->duc.max_in) ? UA3_OK : fail(UA3_E_STATE, "ua3reo_duc_enable: already enabled with a smaller block");
     UA3_CUDA(cudaSetDevice(c->device));
+    AllocScope scope(c);
     DucBuffers& d = c->duc;
     d.n_ch = c->n_ch; d.max_in = max_tx_samples; d.fcw = c->b.fcw;
     {
@@ -1158,7 +1185,7 @@ int ua3reo_duc_enable(ua3reo_ctx* c, uint32_t max_tx_samples) {
     UA3_CUDA(dev_alloc(c, &d.dac, (size_t)c->n_ch * max_tx_samples * 1024));
     UA3_CUDA(duc_upload_constants());
     UA3_CUDA(cudaStreamSynchronize(c->stream));
-    c->duc_alloc = true;
+    c->duc_alloc = scope.ok = true;
     return UA3_OK;
 }
 
@@ -1239,6 +1266,7 @@ int ua3reo_tx_enable(ua3reo_ctx* c, uint32_t max_blocks) {
     if (!c || max_blocks == 0) return fail(UA3_E_INVAL, "ua3reo_tx_enable: bad arguments");
     if (c->tx_alloc) return (max_blocks <= c->tx.max_blocks) ? UA3_OK : fail(UA3_E_STATE, "ua3reo_tx_enable: already enabled with fewer blocks");
     UA3_CUDA(cudaSetDevice(c->device));
+    AllocScope scope(c);
     TxBuffers& t = c->tx;
     t.n_ch = c->n_ch; t.max_blocks = max_blocks;
     const size_t per_ch = (size_t)max_blocks * UA3_AUDIO_BLOCK * 2;
@@ -1266,7 +1294,7 @@ int ua3reo_tx_enable(ua3reo_ctx* c, uint32_t max_blocks) {
     }
     UA3_CUDA(cudaMemcpyAsync(t.params, c->h_txpar.data(), sizeof(TxParams) * c->n_ch, cudaMemcpyHostToDevice, c->stream));
     UA3_CUDA(cudaStreamSynchronize(c->stream));
-    c->tx_alloc = true;
+    c->tx_alloc = scope.ok = true;
     return UA3_OK;
 }
 
