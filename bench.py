@@ -282,11 +282,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
     if world > 1 and bc is None:
         bc = pkg.sharding.AdcBroadcaster(block, torch.device("cuda", local), src=0, dist=dist, consumer_stream=ext)
         transport = "nccl broadcast"
-    # SMs kept out of the front kernel for NCCL kernels: the broadcast, and in the full chain the spectra gather
-    comm_sms = args.comm_sms if args.comm_sms is not None else \
-        (1 if world > 1 and (transport == "nccl broadcast" or workload == "full_chain") else 0)
-    if world > 1:
-        rx.reserve_sms(comm_sms)
+    gather_transport = "nccl gather" if (full and world > 1) else "none"
     audio_host = spec_host = None
     if full:
         # the STM32 stage for every channel; it runs on its own stream one push behind the DDC
@@ -312,8 +308,34 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
         ev_spec = [torch.cuda.Event() for _ in range(GS)]
         ev_gdone = [torch.cuda.Event() for _ in range(GS)]
         g_used = [False] * GS
+        # preferred: ua3reo_gather_* - every rank's copy engine writes its slab into rank 0's buffer (CUDA IPC), no NCCL kernel
+        slab_gather, gathered_view = None, [None]
+        if transport.startswith("cuda-ipc"):
+            try:
+                slab_gather = pkg.sharding.SlabGather(rx.lib, n_ch * nf_step * 256 * 4, local, root=0, dist=dist, n_buffers=GS)
+                gather_transport = "cuda-ipc copy engines (ua3reo_gather_*)"
+            except pkg.UA3Error as e:
+                if rank == 0:
+                    print("bench.py: %s - the spectra gather stays on NCCL" % e, file=sys.stderr)
 
-        def gather_spectra(i, to_host):
+        class _Raw:                                    # a device range as a torch tensor (zero copy)
+            def __init__(self, ptr, nbytes):
+                self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+        def gather_spectra_ce(i, to_host):
+            b = i % GS
+            nf = rx.read_spectra_async(spec_dev[b])            # device-to-device, on the library's copy stream ...
+            assert nf == nf_step
+            slab_gather.send(spec_dev[b].data_ptr(), rx.copy_stream())     # ... and so is the send: ordered behind it
+            if rank == 0:
+                ptr, stride = slab_gather.acquire(gstream.cuda_stream)      # gstream waits for every rank's arrival word
+                if to_host:
+                    with torch.cuda.stream(gstream):
+                        allr = torch.as_tensor(_Raw(ptr, world * stride), device="cuda").view(world, stride)
+                        gathered_view[0] = allr[:, :n_ch * nf_step * 256 * 4].contiguous().view(torch.float32).view(world, n_ch, nf_step, 256).cpu()
+                slab_gather.release(gstream.cuda_stream)
+
+        def gather_spectra_nccl(i, to_host):
             b = i % GS
             if g_used[b]:
                 cstream.wait_event(ev_gdone[b])        # the gather that last used slot b has read spec_dev[b]
@@ -327,6 +349,16 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                     spec_all_host[b].copy_(spec_all[b], non_blocking=True)
                 ev_gdone[b].record(gstream)
             g_used[b] = True
+            if to_host and rank == 0:
+                gathered_view[0] = spec_all_host[b].view(world, n_ch, nf_step, 256)
+
+        gather_spectra = gather_spectra_ce if slab_gather is not None else gather_spectra_nccl
+
+    # SMs kept out of the front kernel for NCCL kernels (a front CTA owns its SM): the broadcast, the spectra gather
+    comm_sms = args.comm_sms if args.comm_sms is not None else \
+        (1 if world > 1 and (transport == "nccl broadcast" or gather_transport == "nccl gather") else 0)
+    if world > 1:
+        rx.reserve_sms(comm_sms)
 
     # synthetic ADC: NB distinct blocks generated once on the host (pinned); rank 0 is the ingest rank
     NB = 4
@@ -512,6 +544,20 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
         else:
             audio_note = "oracle/_ref/fw_rx not present: STM32-stage parity not checked in this run"
 
+    # N>1: the gather itself - rank 0's buffer must hold every rank's spectra of this push (CRC of each slab against the CRC
+    # its owner computed from its own host read)
+    gather_ok = None
+    if gather_spectra is not None:
+        import zlib
+        mine = np.ascontiguousarray(rx.read_spectra())
+        gather_spectra(0, True)
+        gstream.synchronize()
+        crcs = [None] * world
+        dist.all_gather_object(crcs, zlib.crc32(mine.tobytes()))
+        if rank == 0:
+            got_all = gathered_view[0].numpy()
+            gather_ok = all(zlib.crc32(np.ascontiguousarray(got_all[r]).tobytes()) == crcs[r] for r in range(world)) and bool(np.abs(got_all).max() > 0)
+
     # TX DUC (configs[4] "plus TX DUC interpolation"): n_tx 48 kHz I/Q samples per channel -> n_tx * 1024 DAC words
     tx_duc = None
     if full:
@@ -653,7 +699,7 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                        "channels_total": n_ch * world, "channels_per_gpu": n_ch, "block_samples": block,
                        "real_time_channels": value / 49152000.0,
                        "clocking_class": "B/3/129 (the board's most frequent frame alignment, DESIGN.md 2)",
-                       "comm_sms": comm_sms, "adc_transport": transport,
+                       "comm_sms": comm_sms, "adc_transport": transport, "spectra_gather": gather_transport,
                        "l2": "per-step working set ~%.0f MB (chunk records + frames) exceeds the 126 MB L2; no flush needed"
                              % (step_bytes / 1e6)},
             "e2e": {"value": e2e, "unit": "channel*samples/s", "h2d_bytes_per_step": 2 * block,
@@ -665,7 +711,8 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
             "gpu_launches": int(launches),
             "parity": {"ddc_ranks_ok": int(oks[0]), "ranks": world, "channels_checked_per_rank": len(picks),
                        "ddc_check": "frames of one more block (received from rank 0 at N>1) == golden model, bit for bit",
-                       "stm32_ranks_ok": (int(oks[1]) if full and audio_ok is not None else None), "stm32_check": audio_note},
+                       "stm32_ranks_ok": (int(oks[1]) if full and audio_ok is not None else None), "stm32_check": audio_note,
+                       "spectra_gather_ok": gather_ok},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
@@ -683,13 +730,17 @@ def measure(args, pkg, torch, dist, workload, n_ch, world, rank, local, want_cpu
                                       "(ua3reo_duc_push, host I/Q in); the board is half duplex, so this is timed on its own"}
     if (world > 1 and oks[0] != world) or (world == 1 and not ddc_ok):
         raise SystemExit("bench.py: PARITY FAILURE - CUDA frames differ from the golden model on %d of %d ranks" % (world - int(oks[0]), world))
+    if gather_ok is False:
+        raise SystemExit("bench.py: PARITY FAILURE - the spectra gathered on rank 0 differ from what the ranks computed")
     if full and audio_ok is not None and int(oks[1]) != world:
         raise SystemExit("bench.py: PARITY FAILURE - STM32-stage results outside tolerance (%s)" % audio_note)
     # tensors that were used on the library's streams must be released while those streams still exist
     if gather_spectra is not None:
         import gc
         torch.cuda.synchronize()
-        del gather_spectra, spec_dev, spec_all, spec_all_host, cstream, gstream, ev_spec, ev_gdone, gather_pg
+        if slab_gather is not None:
+            slab_gather.close()                        # collective
+        del gather_spectra, gather_spectra_ce, gather_spectra_nccl, slab_gather, spec_dev, spec_all, spec_all_host, cstream, gstream, ev_spec, ev_gdone, gather_pg
         gc.collect()
     torch.cuda.synchronize()
     if bc is not None and hasattr(bc, "close"):

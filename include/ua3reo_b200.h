@@ -406,6 +406,24 @@ int ua3reo_fanout_sync(ua3reo_fanout *f);      /* waits for this rank's send and
 /* direct_remote_store: 1 if the driver stores flag words straight onto peer mappings, 0 if they are staged through a copy */
 int ua3reo_fanout_info(const ua3reo_fanout *f, int *direct_remote_store, uint64_t *n_sent, uint64_t *n_acquired);
 
+/* The opposite direction, same means: every rank's slab of results (bench.py: the spectra of a push, which north_star wants
+ * back on one device) lands in ONE buffer on the root rank - each rank's copy engine writes its slab into its place of the
+ * root's slot and stores an arrival number there; the root's consumer stream waits for all of them; credits flow back when the
+ * root has consumed the slot.  No collective kernel.
+ *     every rank:  ua3reo_gather_send(g, slab_dev, stream)          enqueued ON `stream`, behind whatever produced the slab
+ *     root rank:   ua3reo_gather_acquire(g, stream, &all, &stride)   all + r * stride = rank r's slab; `stream` waits for all ranks
+ *                  ... use it on `stream` ...
+ *                  ua3reo_gather_release(g, stream) */
+typedef struct ua3reo_gather ua3reo_gather;
+int ua3reo_gather_create(int device, int rank, int world, int root, size_t slab_bytes, int n_buffers, ua3reo_gather **out);
+int ua3reo_gather_disconnect(ua3reo_gather *g);   /* two-step tear-down as for the fan-out */
+int ua3reo_gather_destroy(ua3reo_gather *g);
+int ua3reo_gather_handle(ua3reo_gather *g, void *handle64);
+int ua3reo_gather_connect(ua3reo_gather *g, const void *handles);
+int ua3reo_gather_send(ua3reo_gather *g, const void *slab_dev, void *producer_stream);
+int ua3reo_gather_acquire(ua3reo_gather *g, void *consumer_stream, const void **all_dev, size_t *rank_stride);
+int ua3reo_gather_release(ua3reo_gather *g, void *consumer_stream);
+
 /* Per-kernel device timing with CUDA events on the context's stream (bench.py's roofline):
  * after ua3reo_profile_begin(ctx, max_blocks) each processed ADC block records an event before and
  * after every kernel; ua3reo_profile_end() waits for the stream and sums the elapsed times per

@@ -96,3 +96,57 @@ def test_single_rank_fanout_is_a_plain_ring(pkg, oracle):
     with pytest.raises(pkg.UA3Error):
         pkg.sharding.AdcFanout(rx.lib, BLOCK, 0, rx.stream(), n_buffers=1)
     rx.close()
+
+
+def _gather_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ua3reo_loader
+    pkg = ua3reo_loader.load()
+    torch.cuda.set_device(0)
+    lib = pkg.load_library()
+    n_words, n_steps = 5000, 11                                  # more steps than slots: credits come back from the root
+    g = pkg.sharding.SlabGather(lib, n_words * 4, 0, root=0, dist=dist, n_buffers=3)
+    st = torch.cuda.Stream()
+    got = []
+    srcs = [torch.empty(n_words, dtype=torch.int32, device="cuda") for _ in range(2)]
+
+    class Raw:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+    for s in range(n_steps):
+        with torch.cuda.stream(st):
+            srcs[s & 1].copy_(torch.arange(n_words, dtype=torch.int32, device="cuda") * (rank + 1) + 1000 * s)
+        g.send(srcs[s & 1].data_ptr(), st.cuda_stream)
+        if rank == 0:
+            ptr, stride = g.acquire(st.cuda_stream)
+            with torch.cuda.stream(st):
+                allr = torch.as_tensor(Raw(ptr, world * stride), device="cuda").view(world, stride)[:, :n_words * 4]
+                got.append(allr.contiguous().view(torch.int32).view(world, n_words).cpu().numpy().copy())
+            g.release(st.cuda_stream)
+            if s == 4:
+                import time
+                time.sleep(0.3)                                  # a slow root: the senders must wait for their credits
+    torch.cuda.synchronize()
+    g.close()
+    if rank == 0:
+        np.save(os.path.join(out_dir, "gathered.npy"), np.stack(got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_process_gather(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_gather_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = np.load(str(tmp_path / "gathered.npy"))
+    assert got.shape == (11, 2, 5000)
+    base = np.arange(5000, dtype=np.int64)
+    for s in range(11):
+        for r in range(2):
+            assert np.array_equal(got[s, r], base * (r + 1) + 1000 * s), (s, r)

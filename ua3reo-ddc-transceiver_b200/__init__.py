@@ -161,6 +161,14 @@ def _bind(lib):
         "ua3reo_fanout_release": (c.c_int, [vp, vp]),
         "ua3reo_fanout_sync": (c.c_int, [vp]),
         "ua3reo_fanout_info": (c.c_int, [vp, c.POINTER(c.c_int), c.POINTER(c.c_uint64), c.POINTER(c.c_uint64)]),
+        "ua3reo_gather_create": (c.c_int, [c.c_int, c.c_int, c.c_int, c.c_int, sz, c.c_int, c.POINTER(vp)]),
+        "ua3reo_gather_disconnect": (c.c_int, [vp]),
+        "ua3reo_gather_destroy": (c.c_int, [vp]),
+        "ua3reo_gather_handle": (c.c_int, [vp, vp]),
+        "ua3reo_gather_connect": (c.c_int, [vp, vp]),
+        "ua3reo_gather_send": (c.c_int, [vp, vp, vp]),
+        "ua3reo_gather_acquire": (c.c_int, [vp, vp, c.POINTER(vp), c.POINTER(sz)]),
+        "ua3reo_gather_release": (c.c_int, [vp, vp]),
         "ua3reo_sync": (c.c_int, [vp]),
         "ua3reo_stream": (c.c_int, [vp, c.POINTER(vp)]),
         "ua3reo_launch_count": (c.c_uint64, [vp]),

@@ -112,35 +112,26 @@ int ua3reo_fanout_destroy(ua3reo_fanout* f) {
     return UA3_OK;
 }
 
-int ua3reo_fanout_create(int device, int rank, int world, int src, size_t block_samples, int n_buffers, ua3reo_fanout** out) {
-    if (!out || world < 1 || rank < 0 || rank >= world || src < 0 || src >= world || block_samples == 0 || n_buffers < 2 || n_buffers > 16)
-        return ffail(UA3_E_INVAL, "ua3reo_fanout_create: bad arguments");
-    *out = nullptr;
-    UA3_FCUDA(cudaSetDevice(device));
-    ua3reo_fanout* f = new (std::nothrow) ua3reo_fanout;
-    if (!f) return ffail(UA3_E_STATE, "ua3reo_fanout_create: out of host memory");
-    f->device = device; f->rank = rank; f->world = world; f->src = src; f->n_buf = n_buffers; f->block = block_samples;
-    f->slot_bytes = round_up(block_samples * sizeof(int16_t));
-    f->ready_off = f->slot_bytes * (size_t)n_buffers;
-    f->credit_off = f->ready_off + round_up((size_t)n_buffers * 128);
-    f->arena_bytes = f->credit_off + round_up((size_t)world * (size_t)n_buffers * 128);
+// what both directions share: the entry points of the stream memory operations, the arena, the local words, the streams
+static int link_create(ua3reo_fanout* f, int device, int rank, int world, int src, size_t arena_bytes) {
+    f->device = device; f->rank = rank; f->world = world; f->src = src;
+    f->arena_bytes = arena_bytes;
     f->peer.assign((size_t)world, nullptr);
     f->opened.assign((size_t)world, false);
-#define UA3_FTRY(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ua3reo_fanout_destroy(f); return ffail(UA3_E_CUDA, what, e__); } } while (0)
+#define UA3_FTRY(call, what) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return ffail(UA3_E_CUDA, what, e__); } while (0)
+    UA3_FTRY(cudaSetDevice(device), "cudaSetDevice");
     cudaDriverEntryPointQueryResult q1, q2;
     void *p1 = nullptr, *p2 = nullptr;
     UA3_FTRY(cudaGetDriverEntryPoint("cuStreamWaitValue32", &p1, cudaEnableDefault, &q1), "cudaGetDriverEntryPoint(cuStreamWaitValue32)");
     UA3_FTRY(cudaGetDriverEntryPoint("cuStreamWriteValue32", &p2, cudaEnableDefault, &q2), "cudaGetDriverEntryPoint(cuStreamWriteValue32)");
-    if (!p1 || !p2 || q1 != cudaDriverEntryPointSuccess || q2 != cudaDriverEntryPointSuccess) {
-        ua3reo_fanout_destroy(f);
-        return ffail(UA3_E_STATE, "ua3reo_fanout_create: the driver has no stream memory operations");
-    }
+    if (!p1 || !p2 || q1 != cudaDriverEntryPointSuccess || q2 != cudaDriverEntryPointSuccess)
+        return ffail(UA3_E_STATE, "the driver has no stream memory operations");
     f->wait32 = (WaitValue32Fn)p1;
     f->write32 = (WriteValue32Fn)p2;
-    UA3_FTRY(cudaMalloc((void**)&f->arena, f->arena_bytes), "cudaMalloc(fan-out arena)");
-    UA3_FTRY(cudaMemset(f->arena, 0, f->arena_bytes), "cudaMemset(fan-out arena)");
+    UA3_FTRY(cudaMalloc((void**)&f->arena, f->arena_bytes), "cudaMalloc(arena)");
+    UA3_FTRY(cudaMemset(f->arena, 0, f->arena_bytes), "cudaMemset(arena)");
     f->n_stage = 4096;
-    UA3_FTRY(cudaMalloc((void**)&f->stage_words, f->n_stage * sizeof(uint32_t)), "cudaMalloc(fan-out words)");
+    UA3_FTRY(cudaMalloc((void**)&f->stage_words, f->n_stage * sizeof(uint32_t)), "cudaMalloc(words)");
     UA3_FTRY(cudaStreamCreateWithFlags(&f->send_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     UA3_FTRY(cudaStreamCreateWithFlags(&f->credit_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     UA3_FTRY(cudaEventCreateWithFlags(&f->ev_consumed, cudaEventDisableTiming), "cudaEventCreate");
@@ -148,6 +139,21 @@ int ua3reo_fanout_create(int device, int rank, int world, int src, size_t block_
 #undef UA3_FTRY
     f->peer[(size_t)rank] = f->arena;
     if (world == 1) f->connected = true;
+    return UA3_OK;
+}
+
+int ua3reo_fanout_create(int device, int rank, int world, int src, size_t block_samples, int n_buffers, ua3reo_fanout** out) {
+    if (!out || world < 1 || rank < 0 || rank >= world || src < 0 || src >= world || block_samples == 0 || n_buffers < 2 || n_buffers > 16)
+        return ffail(UA3_E_INVAL, "ua3reo_fanout_create: bad arguments");
+    *out = nullptr;
+    ua3reo_fanout* f = new (std::nothrow) ua3reo_fanout;
+    if (!f) return ffail(UA3_E_STATE, "ua3reo_fanout_create: out of host memory");
+    f->n_buf = n_buffers; f->block = block_samples;
+    f->slot_bytes = round_up(block_samples * sizeof(int16_t));
+    f->ready_off = f->slot_bytes * (size_t)n_buffers;
+    f->credit_off = f->ready_off + round_up((size_t)n_buffers * 128);
+    const int rc = link_create(f, device, rank, world, src, f->credit_off + round_up((size_t)world * (size_t)n_buffers * 128));
+    if (rc != UA3_OK) { ua3reo_fanout_destroy(f); return rc; }       // (the message of the failure is kept: destroy sets none)
     *out = f;
     return UA3_OK;
 }
@@ -249,6 +255,112 @@ int ua3reo_fanout_info(const ua3reo_fanout* f, int* direct_remote_store, uint64_
     if (direct_remote_store) *direct_remote_store = f->direct_remote_store ? 1 : 0;
     if (n_sent) *n_sent = f->n_sent;
     if (n_acquired) *n_acquired = f->n_acquired;
+    return UA3_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------------------
+// the opposite direction: every rank's slab of results into one buffer on the root rank (ua3reo_gather_*).  Arena layout,
+// flags first so that their offsets do not depend on the rank: ARRIVE[rank][slot] (used in the root's arena, stored by
+// `rank` behind its copy), CREDIT[slot] (used in every rank's arena, stored by the root once it has consumed the slot), and -
+// on the root only - the data: n_buffers x world x slab bytes.
+// -----------------------------------------------------------------------------------------------------------------------
+struct ua3reo_gather {
+    ua3reo_fanout link;                // arena, mappings, entry points, streams (src = the root)
+    size_t slab = 0, slab_pad = 0, arrive_off = 0, credit_off = 0, data_off = 0;
+    uint64_t n_sent = 0, n_acquired = 0, n_released = 0;
+    uint32_t* arrive(uint8_t* base, int r, int slot) const { return (uint32_t*)(base + arrive_off) + (r * link.n_buf + slot) * 32; }
+    uint32_t* credit(uint8_t* base, int slot) const { return (uint32_t*)(base + credit_off) + slot * 32; }
+    uint8_t* data(uint8_t* base, int slot, int r) const { return base + data_off + ((size_t)slot * link.world + r) * slab_pad; }
+};
+
+int ua3reo_gather_destroy(ua3reo_gather* g) {
+    if (!g) return UA3_OK;
+    ua3reo_fanout_disconnect(&g->link);
+    ua3reo_fanout* f = &g->link;
+    if (f->ev_consumed) cudaEventDestroy(f->ev_consumed);
+    if (f->send_stream) cudaStreamDestroy(f->send_stream);
+    if (f->credit_stream) cudaStreamDestroy(f->credit_stream);
+    if (f->stage_words) cudaFree(f->stage_words);
+    if (f->arena) cudaFree(f->arena);
+    delete g;
+    return UA3_OK;
+}
+
+int ua3reo_gather_disconnect(ua3reo_gather* g) { return g ? ua3reo_fanout_disconnect(&g->link) : UA3_OK; }
+
+int ua3reo_gather_create(int device, int rank, int world, int root, size_t slab_bytes, int n_buffers, ua3reo_gather** out) {
+    if (!out || world < 1 || rank < 0 || rank >= world || root < 0 || root >= world || slab_bytes == 0 || n_buffers < 2 || n_buffers > 16)
+        return ffail(UA3_E_INVAL, "ua3reo_gather_create: bad arguments");
+    *out = nullptr;
+    ua3reo_gather* g = new (std::nothrow) ua3reo_gather;
+    if (!g) return ffail(UA3_E_STATE, "ua3reo_gather_create: out of host memory");
+    g->link.n_buf = n_buffers;
+    g->slab = slab_bytes;
+    g->slab_pad = round_up(slab_bytes);
+    g->arrive_off = 0;
+    g->credit_off = round_up((size_t)world * (size_t)n_buffers * 128);
+    g->data_off = g->credit_off + round_up((size_t)n_buffers * 128);
+    const size_t bytes = g->data_off + (rank == root ? (size_t)n_buffers * (size_t)world * g->slab_pad : 0);
+    const int rc = link_create(&g->link, device, rank, world, root, bytes);
+    if (rc != UA3_OK) { ua3reo_gather_destroy(g); return rc; }
+    *out = g;
+    return UA3_OK;
+}
+
+int ua3reo_gather_handle(ua3reo_gather* g, void* handle64) { return g ? ua3reo_fanout_handle(&g->link, handle64) : ffail(UA3_E_INVAL, "null gather"); }
+int ua3reo_gather_connect(ua3reo_gather* g, const void* handles) { return g ? ua3reo_fanout_connect(&g->link, handles) : ffail(UA3_E_INVAL, "null gather"); }
+
+int ua3reo_gather_send(ua3reo_gather* g, const void* slab_dev, void* producer_stream) {
+    if (!g || !slab_dev) return ffail(UA3_E_INVAL, "ua3reo_gather_send: null argument");
+    ua3reo_fanout* f = &g->link;
+    if (!f->connected) return ffail(UA3_E_STATE, "ua3reo_gather_send: not connected");
+    UA3_FCUDA(cudaSetDevice(f->device));
+    cudaStream_t st = (cudaStream_t)producer_stream;       // everything in the producer's stream: the slab is read in stream order
+    const uint64_t s = g->n_sent;
+    const int slot = (int)(s % (uint64_t)f->n_buf);
+    uint8_t* root = f->peer[(size_t)f->src];
+    const bool remote = f->rank != f->src;
+    int rc;
+    if (s >= (uint64_t)f->n_buf && (rc = wait_word(f, st, g->credit(f->arena, slot), (uint32_t)(s - f->n_buf + 1))) != UA3_OK) return rc;
+    UA3_FCUDA(cudaMemcpyAsync(g->data(root, slot, f->rank), slab_dev, g->slab, cudaMemcpyDefault, st));
+    if ((rc = signal_word(f, st, g->arrive(root, f->rank, slot), (uint32_t)(s + 1), remote)) != UA3_OK) return rc;
+    g->n_sent = s + 1;
+    return UA3_OK;
+}
+
+int ua3reo_gather_acquire(ua3reo_gather* g, void* consumer_stream, const void** all_dev, size_t* rank_stride) {
+    if (!g || !all_dev) return ffail(UA3_E_INVAL, "ua3reo_gather_acquire: null argument");
+    ua3reo_fanout* f = &g->link;
+    if (f->rank != f->src) return ffail(UA3_E_STATE, "ua3reo_gather_acquire: only the root rank receives");
+    if (!f->connected) return ffail(UA3_E_STATE, "ua3reo_gather_acquire: not connected");
+    if (g->n_acquired != g->n_released) return ffail(UA3_E_STATE, "ua3reo_gather_acquire: the previous slot was not released");
+    UA3_FCUDA(cudaSetDevice(f->device));
+    const uint64_t s = g->n_acquired;
+    const int slot = (int)(s % (uint64_t)f->n_buf);
+    for (int r = 0; r < f->world; ++r) {
+        const int rc = wait_word(f, (cudaStream_t)consumer_stream, g->arrive(f->arena, r, slot), (uint32_t)(s + 1));
+        if (rc != UA3_OK) return rc;
+    }
+    *all_dev = g->data(f->arena, slot, 0);
+    if (rank_stride) *rank_stride = g->slab_pad;
+    g->n_acquired = s + 1;
+    return UA3_OK;
+}
+
+int ua3reo_gather_release(ua3reo_gather* g, void* consumer_stream) {
+    if (!g) return ffail(UA3_E_INVAL, "ua3reo_gather_release: null argument");
+    ua3reo_fanout* f = &g->link;
+    if (g->n_released + 1 != g->n_acquired) return ffail(UA3_E_STATE, "ua3reo_gather_release without an acquired slot");
+    UA3_FCUDA(cudaSetDevice(f->device));
+    const uint64_t s = g->n_released;
+    const int slot = (int)(s % (uint64_t)f->n_buf);
+    UA3_FCUDA(cudaEventRecord(f->ev_consumed, (cudaStream_t)consumer_stream));
+    UA3_FCUDA(cudaStreamWaitEvent(f->credit_stream, f->ev_consumed, 0));
+    for (int r = 0; r < f->world; ++r) {
+        const int rc = signal_word(f, f->credit_stream, g->credit(f->peer[(size_t)r], slot), (uint32_t)(s + 1), r != f->rank);
+        if (rc != UA3_OK) return rc;
+    }
+    g->n_released = s + 1;
     return UA3_OK;
 }
 

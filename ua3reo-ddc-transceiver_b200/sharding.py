@@ -111,6 +111,61 @@ class AdcBroadcaster:
         return self.acquire()
 
 
+def _ipc_open(lib, kind, create_args, dist, group):
+    """Collective set-up of one ua3reo_fanout / ua3reo_gather end per rank: create, all_gather of the 64-byte handles,
+    connect, and a second all_gather of the outcome so that EVERY rank either returns a handle or raises UA3Error."""
+    import ctypes
+    from . import UA3Error
+    fn = lambda name: getattr(lib, "ua3reo_%s_%s" % (kind, name))
+    world = 1 if dist is None else dist.get_world_size(group)
+    h = ctypes.c_void_p()
+    rc = fn("create")(*create_args, ctypes.byref(h))
+    msg = "" if rc == 0 else lib.ua3reo_last_error().decode()
+    handle = h if rc == 0 else None
+    if world == 1:
+        if rc != 0:
+            raise UA3Error("%s: %s" % (kind, msg))
+        return handle
+    mine = (ctypes.c_uint8 * 64)()
+    if rc == 0:
+        rc = fn("handle")(handle, mine)
+        if rc != 0:
+            msg = lib.ua3reo_last_error().decode()
+    payload = [None] * world
+    dist.all_gather_object(payload, bytes(mine) if rc == 0 else None, group=group)     # tiny, once
+    if rc == 0 and all(p is not None for p in payload):
+        allh = (ctypes.c_uint8 * (64 * world)).from_buffer_copy(b"".join(payload))
+        rc = fn("connect")(handle, allh)
+        if rc != 0:
+            msg = lib.ua3reo_last_error().decode()
+    elif rc == 0:
+        rc, msg = -5, "a peer rank could not create its end"
+    oks = [None] * world
+    dist.all_gather_object(oks, (rc == 0, msg), group=group)
+    bad = [(r, m) for r, (ok, m) in enumerate(oks) if not ok]
+    if bad:                                        # every rank sees the same verdict: unmap, meet, free
+        if handle is not None:
+            fn("disconnect")(handle)
+        dist.barrier(group=group)
+        if handle is not None:
+            fn("destroy")(handle)
+        raise UA3Error("%s: rank %d: %s" % ((kind,) + bad[0]))
+    return handle
+
+
+def _ipc_close(lib, kind, handle, dist, group):
+    """COLLECTIVE tear-down: peers are unmapped first, the arenas are freed only after a barrier."""
+    if handle is None:
+        return
+    multi = dist is not None and dist.get_world_size(group) > 1
+    if multi:
+        dist.barrier(group=group)                  # every rank's streams have been synchronised by its caller
+    getattr(lib, "ua3reo_%s_disconnect" % kind)(handle)
+    if multi:
+        dist.barrier(group=group)
+    getattr(lib, "ua3reo_%s_destroy" % kind)(handle)
+
+
 class AdcFanout:
     """The same pipeline as AdcBroadcaster without a collective kernel: ua3reo_fanout_* (csrc/fanout.cu) - the ingest rank's
     copy engines write every block into each rank's slot over NVLink (CUDA IPC mappings) and the consumer STREAMS wait on
@@ -126,7 +181,6 @@ class AdcFanout:
 
     def __init__(self, lib, block_samples, device_index, consumer_stream, src=0, dist=None, n_buffers=3, group=None):
         import ctypes
-        import torch
         from . import UA3Error, DeviceBlock
         self._ct, self._DeviceBlock, self._err = ctypes, DeviceBlock, UA3Error
         self.lib, self.dist, self.group, self.src = lib, dist, group, src
@@ -137,40 +191,7 @@ class AdcFanout:
         self.n_buffers = int(n_buffers)
         self.n_filled = self.n_taken = 0
         self._keep = []
-        h = ctypes.c_void_p()
-        rc = lib.ua3reo_fanout_create(int(device_index), self.rank, self.world, int(src), self.block, self.n_buffers, ctypes.byref(h))
-        msg = "" if rc == 0 else lib.ua3reo_last_error().decode()
-        self._h = h if rc == 0 else None
-        if rc == 0 and self.world > 1:
-            mine = (ctypes.c_uint8 * 64)()
-            rc = lib.ua3reo_fanout_handle(self._h, mine)
-            if rc != 0:
-                msg = lib.ua3reo_last_error().decode()
-        if self.world > 1:
-            # handles travel as CPU-side objects over the process group's store-backed path (tiny, once)
-            payload = [None] * self.world
-            dist.all_gather_object(payload, bytes(mine) if rc == 0 else None, group=group)
-            if rc == 0 and all(p is not None for p in payload):
-                allh = (ctypes.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(payload))
-                rc = lib.ua3reo_fanout_connect(self._h, allh)
-                if rc != 0:
-                    msg = lib.ua3reo_last_error().decode()
-            elif rc == 0:
-                rc, msg = -5, "a peer rank could not create its fan-out end"
-            oks = [None] * self.world
-            dist.all_gather_object(oks, (rc == 0, msg), group=group)
-            bad = [(r, m) for r, (ok, m) in enumerate(oks) if not ok]
-            if bad:                                    # every rank sees the same verdict: unmap, meet, free
-                if self._h is not None:
-                    lib.ua3reo_fanout_disconnect(self._h)
-                dist.barrier(group=group)
-                if self._h is not None:
-                    lib.ua3reo_fanout_destroy(self._h)
-                    self._h = None
-                raise UA3Error("AdcFanout: rank %d: %s" % bad[0])
-        elif rc != 0:
-            raise UA3Error("AdcFanout: %s" % msg)
-        self._torch = torch
+        self._h = _ipc_open(lib, "fanout", (int(device_index), self.rank, self.world, int(src), self.block, self.n_buffers), dist, group)
 
     def _chk(self, rc):
         if rc != 0:
@@ -205,16 +226,49 @@ class AdcFanout:
         return {"direct_remote_store": bool(d.value), "sent": s.value, "acquired": a.value}
 
     def close(self):
-        """COLLECTIVE: every rank calls it once its consumer stream is idle.  Peers are unmapped first, the arenas are freed
-        only after a barrier (an arena must outlive the mappings of it)."""
-        if self._h is not None:
-            if self.world > 1:
-                self.dist.barrier(group=self.group)          # every rank's last push has been synchronised by its caller
-            self.lib.ua3reo_fanout_disconnect(self._h)
-            if self.world > 1:
-                self.dist.barrier(group=self.group)
-            self.lib.ua3reo_fanout_destroy(self._h)
-            self._h = None
+        """COLLECTIVE: every rank calls it once its consumer stream is idle."""
+        _ipc_close(self.lib, "fanout", self._h, self.dist, self.group)
+        self._h = None
+
+
+class SlabGather:
+    """Every rank's slab of results into one buffer on the root rank without a collective kernel (ua3reo_gather_*):
+
+        g.send(slab_ptr, stream)                 # every rank, enqueued on the stream that produced the slab
+        ptr, stride = g.acquire(stream)          # root: `stream` waits for all ranks; rank r's slab is at ptr + r * stride
+        ...
+        g.release(stream)                        # root: credits return behind the work on `stream`
+
+    Construction and close() are collective, as for AdcFanout."""
+
+    def __init__(self, lib, slab_bytes, device_index, root=0, dist=None, n_buffers=4, group=None):
+        import ctypes
+        from . import UA3Error
+        self._ct, self._err = ctypes, UA3Error
+        self.lib, self.dist, self.group, self.root = lib, dist, group, root
+        self.world = 1 if dist is None else dist.get_world_size(group)
+        self.rank = 0 if dist is None else dist.get_rank(group)
+        self.slab_bytes = int(slab_bytes)
+        self._h = _ipc_open(lib, "gather", (int(device_index), self.rank, self.world, int(root), self.slab_bytes, int(n_buffers)), dist, group)
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise self._err("ua3reo gather error %d: %s" % (rc, self.lib.ua3reo_last_error().decode()))
+
+    def send(self, slab_ptr, stream):
+        self._chk(self.lib.ua3reo_gather_send(self._h, self._ct.c_void_p(int(slab_ptr)), self._ct.c_void_p(int(stream))))
+
+    def acquire(self, stream):
+        p, stride = self._ct.c_void_p(), self._ct.c_size_t()
+        self._chk(self.lib.ua3reo_gather_acquire(self._h, self._ct.c_void_p(int(stream)), self._ct.byref(p), self._ct.byref(stride)))
+        return p.value, stride.value
+
+    def release(self, stream):
+        self._chk(self.lib.ua3reo_gather_release(self._h, self._ct.c_void_p(int(stream))))
+
+    def close(self):
+        _ipc_close(self.lib, "gather", self._h, self.dist, self.group)
+        self._h = None
 
 
 def gather_rows(local_rows, n_total, dist):
