@@ -255,6 +255,7 @@ int ua3reo_create(int device, uint32_t n_channels, uint32_t max_block_samples, u
     }
 #endif
     if (const char* v = std::getenv("UA3REO_TC_ADC_STAGE")) b.tc_adc_stage = std::atoi(v);
+    if (const char* v = std::getenv("UA3REO_PDL")) b.pdl = std::atoi(v);
     if (const char* v = std::getenv("UA3REO_FRONT_VARIANT")) b.front_variant = std::atoi(v);   // 1 small table, 2 big table (CUDA cores), 3 tensor cores
     UA3_TRY(dev_alloc(c, &b.fcw, c->n_ch_pad));
     UA3_TRY(dev_alloc(c, &b.phase, c->n_ch_pad));

@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(256)
 adc_prepare_tc_kernel(const int16_t* __restrict__ adc, uint32_t n8, uint16_t* __restrict__ adc_h, uint8_t* __restrict__ wrap_flag,
                       uint32_t* __restrict__ tile_counter) {
     __shared__ uint32_t s_any[8];
+    UA3_PDL_WAIT();                                 // adc_h / wrap_flag / the tile counter are still read by the previous push's front kernel
+    UA3_PDL_TRIGGER();                              // the front kernel's CTAs may take their SMs and load the NCO table meanwhile
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v == 0) *tile_counter = 0;
     bool hit = false;
@@ -321,6 +323,8 @@ ddc_ciccomp_kernel(const uint64_t* __restrict__ L, uint32_t l_ch_stride, uint32_
     const uint32_t n_rec = 2 * nk + kLHalo;
     // record index (array, halo included) of the tile's first staged record: chunk 2*k0 - 69 -> array index 2*k0
     const uint64_t* src = L + (size_t)ch * l_ch_stride + (size_t)(2 * k0) * kLRec;
+    UA3_PDL_WAIT();                                                  // the front kernel's records
+    UA3_PDL_TRIGGER();
 #if !defined(UA3_HOST_EMU)
     if (tid == 0) {
         mbar_init(&s_bar, 1);
@@ -432,6 +436,8 @@ ddc_hilb_kernel(const int16_t* __restrict__ YI, uint32_t yi_stride, const int16_
     const uint32_t tid = threadIdx.x;
     // VOICE_I of frame k is the Hilbert sum d_i samples back (serial MAC + output register, rx_hilb.vhd:907-947)
     const int16_t* src = YI + (size_t)ch * yi_stride + k0 + (kMaxDI - d_i);
+    UA3_PDL_WAIT();                                        // YI / YQ of ddc_ciccomp_kernel
+    UA3_PDL_TRIGGER();
     for (uint32_t i = tid; i < 512; i += kHbThreads) {     // every warp: 32 consecutive samples -> one word per plane
         const int32_t v = (i < nk + 255u) ? (int32_t)src[i] : 0;
         s_y[i] = v;
@@ -503,6 +509,8 @@ ddc_rotate_kernel(uint64_t* __restrict__ L, uint32_t l_ch_stride,
     constexpr int kLPer = (kLHalo * kLRec + 255) / 256;               // halo words per thread
     static_assert(kYIHalo <= 512 && kYQHalo <= 256, "halo rotation: two YI words and one YQ word per thread");
     uint64_t vl[kLPer]; int16_t vyi = 0, vyi2 = 0, vyq = 0;
+    UA3_PDL_WAIT();                                                   // ddc_hilb_kernel still reads the YI / YQ halos
+    UA3_PDL_TRIGGER();
 #pragma unroll
     for (int q = 0; q < kLPer; ++q) { const uint32_t w = t + 256u * q; vl[q] = (w < kLHalo * kLRec) ? l[(size_t)n_chunks * kLRec + w] : 0; }
     if (t < kYIHalo) vyi = yi[n_frames + t];
@@ -624,6 +632,12 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
     const uint32_t n_chunks = n_samples / kCicR, n_frames = n_samples / kFrameAdc;
     if (n_chunks == 0) return cudaSuccess;
     if (ev && ((ev_mask >> 0) & 1u)) cudaEventRecord(ev[0], st);
+    // programmatic dependent launch between the kernels of the chain (tensor-core path; every kernel of it calls UA3_PDL_WAIT
+    // before it reads or overwrites what an earlier one uses): the launch latencies and the front kernel's 216 KB prologue
+    // run under the predecessor's tail.  A launch that directly follows a recorded profiling event is made the ordinary way
+    // (the event sits between the two kernels): with bench.py's front-kernel bracket that is the front kernel and the one
+    // behind it, the other boundaries keep their overlap inside the timed region.
+    auto pdl_at = [&](int point) { return b.pdl != 0 && !(ev && ((ev_mask >> point) & 1u)); };
     // big-table kernel when a CTA tile (256 channels x 4 chunks) can be filled; the 8 KB-table kernel otherwise
     const bool big = b.front_variant != 1 && b.big_tab && (b.front_variant == 2 || ((b.n_ch_pad >> 5) >= (uint32_t)kBtCG && n_chunks >= (uint32_t)kBtTG));
 #if !defined(UA3_HOST_EMU)
@@ -635,7 +649,7 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
     if (tcore) {
 #if !defined(UA3_HOST_EMU)
         const uint32_t n8 = n_chunks * (uint32_t)kCicR / 8u;
-        UA3_LAUNCH(adc_prepare_tc_kernel, (n8 + 255u) / 256u, 256, 0, st, adc_dev, n8, b.adc_h, b.wrap_flag, b.tile_counter);
+        UA3_LAUNCH_PDL(pdl_at(0) && pdl_at(5), adc_prepare_tc_kernel, (n8 + 255u) / 256u, 256, 0, st, adc_dev, n8, b.adc_h, b.wrap_flag, b.tile_counter);
         if (launches) *launches += 1;
         if (ev && ((ev_mask >> 1) & 1u)) cudaEventRecord(ev[1], st);
         const uint32_t n_tiles = ((b.n_ch_pad + 127u) / 128u) * n_chunks;
@@ -643,7 +657,7 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
         TcFix fix;
         for (int k = 0; k < 5; ++k) fix.c[k] = b.tc_fix[k];
         if (b.tc_adc_stage)
-            UA3_LAUNCH(ddc_front_tc_kernel<true>, grid, kTcThreads, kTcSmemBytes, st, b.adc_h, b.wrap_flag, n_chunks, b.tab_h, b.fcw, b.phase,
+            UA3_LAUNCH_PDL(pdl_at(1), ddc_front_tc_kernel<true>, grid, kTcThreads, kTcSmemBytes, st, b.adc_h, b.wrap_flag, n_chunks, b.tab_h, b.fcw, b.phase,
                        b.n_ch_pad, b.tc_w, b.L, b.l_ch_stride, b.tile_counter, fix);
         else
             UA3_LAUNCH(ddc_front_tc_kernel<false>, grid, kTcThreads, kTcSmemBytes, st, b.adc_h, b.wrap_flag, n_chunks, b.tab_h, b.fcw, b.phase,
@@ -673,13 +687,13 @@ cudaError_t ddc_launch_block(const DdcBuffers& b, const int16_t* adc_dev, uint32
                    b.L, b.l_ch_stride);
     }
     if (ev && ((ev_mask >> 2) & 1u)) cudaEventRecord(ev[2], st);
-    UA3_LAUNCH(ddc_ciccomp_kernel, dim3(b.n_ch, (n_frames + kCcFrames - 1) / kCcFrames), kCcThreads, 0, st, b.L, b.l_ch_stride, n_frames,
+    UA3_LAUNCH_PDL(pdl_at(2), ddc_ciccomp_kernel, dim3(b.n_ch, (n_frames + kCcFrames - 1) / kCcFrames), kCcThreads, 0, st, b.L, b.l_ch_stride, n_frames,
                b.YI, b.yi_stride, b.YQ, b.yq_stride, (uint32_t)b.align_b);
     if (ev && ((ev_mask >> 3) & 1u)) cudaEventRecord(ev[3], st);
-    UA3_LAUNCH(ddc_hilb_kernel, dim3(b.n_ch, (n_frames + kHbFrames - 1) / kHbFrames), kHbThreads, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
+    UA3_LAUNCH_PDL(pdl_at(3), ddc_hilb_kernel, dim3(b.n_ch, (n_frames + kHbFrames - 1) / kHbFrames), kHbThreads, 0, st, b.YI, b.yi_stride, b.YQ, b.yq_stride,
                n_frames, b.frames, b.frame_ch_stride, ring_start, b.ring_mask, (uint32_t)b.d_i, (uint32_t)b.d_q);
     if (ev && ((ev_mask >> 4) & 1u)) cudaEventRecord(ev[4], st);
-    UA3_LAUNCH(ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.YI, b.yi_stride,
+    UA3_LAUNCH_PDL(pdl_at(4), ddc_rotate_kernel, b.n_ch_pad, 256, 0, st, b.L, b.l_ch_stride, b.YI, b.yi_stride,
                b.YQ, b.yq_stride, n_chunks, n_frames, b.phase, b.fcw, b.n_ch_pad);
     if (ev && ((ev_mask >> 5) & 1u)) cudaEventRecord(ev[5], st);
     if (launches) *launches += kDdcKernels - 1;

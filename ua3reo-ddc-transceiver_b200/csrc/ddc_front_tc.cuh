@@ -162,6 +162,7 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     mbar_wait(s_tabbar, 0);                               // table and weights have landed (async proxy writes, visible to the MMA as well)
+    UA3_PDL_WAIT();                                       // everything above ran under adc_prepare_tc_kernel (and its launch); now its outputs
     const uint32_t tmem = s_misc[0];
     const uint32_t n_cg = (n_ch_pad + 127u) / 128u, n_tiles = n_cg * n_chunks;
     const bool issuer = warp >= kTcWg * 4;

@@ -19,6 +19,7 @@ struct DdcBuffers {
     uint64_t tc_fix[5] = {0, 0, 0, 0, 0};   // per-stage offset removed in the recombination (build_tc_weight_planes)
     uint16_t* adc_h = nullptr;     // [max_block] the current ADC block as binary16 (adc_prepare_tc_kernel)
     uint8_t* wrap_flag = nullptr;  // [max_chunks] chunk contains an ADC sample of -2048
+    int pdl = 1;                   // programmatic dependent launch between the chain's kernels (UA3REO_PDL=0 turns it off)
     int tc_adc_stage = 1;          // 1: the chunk's samples are staged in shared memory (cp.async, one tile ahead); 0: broadcast global loads
     uint32_t* fcw = nullptr;       // [n_ch_pad] 22-bit tuning words
     uint32_t* phase = nullptr;     // [n_ch_pad] 22-bit phase at the start of the next block

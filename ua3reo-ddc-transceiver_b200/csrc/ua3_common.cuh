@@ -19,6 +19,37 @@
 #if !defined(UA3_HOST_EMU)
 #define UA3_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #endif
+#if defined(__CUDACC__) && !defined(UA3_HOST_EMU)
+#include <cuda_runtime.h>
+#include <utility>
+namespace ua3 {
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+}  // namespace ua3
+#define UA3_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, ...) (void)ua3::launch_pdl((pdl), kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__)
+#else
+#define UA3_LAUNCH_PDL(pdl, kernel, grid, block, smem, stream, ...) UA3_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__)
+#endif
+
+// Programmatic dependent launch: a kernel launched with the attribute may be scheduled while its predecessor in the stream
+// still runs; it must call pdl_wait() before it touches anything the predecessor (or, transitively, any earlier kernel - every
+// kernel of the chain waits) produced.  pdl_trigger() lets the NEXT kernel's CTAs take their places early.  Both are no-ops
+// in a kernel launched the ordinary way.
+#if defined(__CUDA_ARCH__)
+#define UA3_PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define UA3_PDL_TRIGGER() asm volatile("griddepcontrol.launch_dependents;" ::: "memory")
+#else
+#define UA3_PDL_WAIT() ((void)0)
+#define UA3_PDL_TRIGGER() ((void)0)
+#endif
 
 namespace ua3 {
 
