@@ -131,6 +131,25 @@ def test_full_size_block_properties(pkg, oracle):
     assert np.array_equal(np.concatenate(parts, axis=1), whole)
 
 
+@pytest.mark.parametrize("n_ch", [1024, 8192])
+def test_baseline_size_every_channel_against_golden(pkg, oracle, n_ch):
+    """BASELINE configs[2] / [3] at their full size - 1024 and 8192 channels x 2^20 ADC samples - with EVERY channel's frames
+    compared bit for bit against the golden model (all host cores run it: about 2 s and 16 s of CPU work on 16 cores)."""
+    n = 1 << 20
+    adc = oracle.synth_adc(n, seed=20261018)
+    fcw = pkg.random_fcw(n_ch, seed=20261018 + n_ch)
+    fcw[:4] = [1, (1 << 22) - 1, 1 << 21, 620407]                     # the extremes ride along
+    rx = pkg.Receiver(n_ch, n)
+    rx.set_fcw(fcw)
+    assert rx.push(adc) == n // 1024
+    got = rx.read_frames()
+    rx.close()
+    _, ref = oracle.GoldenBank(fcw).push(adc, os.cpu_count() or 8, want_frames=True)
+    bad = np.flatnonzero((got != ref).reshape(n_ch, -1).any(axis=1))
+    assert bad.size == 0, "channels with differing frames: %s" % bad[:10]
+    assert got.reshape(n_ch, -1).any(axis=1).all()                    # no channel was left silent
+
+
 def test_front_kernel_variants_agree(pkg, oracle, monkeypatch):
     """The 8 KB-table kernel and the 208 KB big-table kernel (TMA-staged, one CTA per SM) are both exact:
     same frames for 300 channels (not a multiple of the 256-channel CTA tile) over ragged pushes."""

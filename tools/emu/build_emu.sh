@@ -6,7 +6,7 @@ CSRC="$HERE/../../ua3reo-ddc-transceiver_b200/csrc"
 mkdir -p "$HERE/_build"
 SRCS=()
 for f in "$CSRC"/*.cu; do
-  case "$(basename "$f")" in peak.cu) continue;; esac
+  case "$(basename "$f")" in peak.cu|fanout.cu) continue;; esac   # device micro-benchmarks / CUDA IPC: nothing to emulate
   SRCS+=("$f")
 done
 g++ -std=c++20 -O1 -g -fPIC -shared -pthread -ffp-contract=off -I"$HERE" -I"$CSRC" -Wno-unknown-pragmas \

@@ -509,16 +509,21 @@ ddc_rotate_kernel(uint64_t* __restrict__ L, uint32_t l_ch_stride,
     constexpr int kLPer = (kLHalo * kLRec + 255) / 256;               // halo words per thread
     static_assert(kYIHalo <= 512 && kYQHalo <= 256, "halo rotation: two YI words and one YQ word per thread");
     uint64_t vl[kLPer]; int16_t vyi = 0, vyi2 = 0, vyq = 0;
-    UA3_PDL_WAIT();                                                   // ddc_hilb_kernel still reads the YI / YQ halos
-    UA3_PDL_TRIGGER();
+    // The chunk records and the phases are used by the front kernel and ddc_ciccomp_kernel only, and those have completed when
+    // a CTA of this kernel runs at all: launched the ordinary way it starts after ddc_hilb_kernel has finished; launched
+    // programmatically it starts after every CTA of ddc_hilb_kernel has passed ITS wait on ddc_ciccomp_kernel (ddc_hilb_kernel
+    // waits before it triggers).  So this part runs beside ddc_hilb_kernel; only the YI / YQ halos wait for it.
 #pragma unroll
     for (int q = 0; q < kLPer; ++q) { const uint32_t w = t + 256u * q; vl[q] = (w < kLHalo * kLRec) ? l[(size_t)n_chunks * kLRec + w] : 0; }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kLPer; ++q) { const uint32_t w = t + 256u * q; if (w < kLHalo * kLRec) l[w] = vl[q]; }
+    UA3_PDL_WAIT();                                                   // ddc_hilb_kernel still reads the YI / YQ halos
+    UA3_PDL_TRIGGER();
     if (t < kYIHalo) vyi = yi[n_frames + t];
     if (t + 256 < kYIHalo) vyi2 = yi[n_frames + t + 256];
     if (t < kYQHalo) vyq = yq[n_frames + t];
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < kLPer; ++q) { const uint32_t w = t + 256u * q; if (w < kLHalo * kLRec) l[w] = vl[q]; }
     if (t < kYIHalo) yi[t] = vyi;
     if (t + 256 < kYIHalo) yi[t + 256] = vyi2;
     if (t < kYQHalo) yq[t] = vyq;

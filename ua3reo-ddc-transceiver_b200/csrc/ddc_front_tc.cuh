@@ -285,6 +285,7 @@ ddc_front_tc_kernel(const uint16_t* __restrict__ adc_h, const uint8_t* __restric
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    UA3_PDL_TRIGGER();                                    // out of tiles: ddc_ciccomp_kernel's CTAs may take this SM (they wait for the whole grid)
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 #endif  // !UA3_HOST_EMU
