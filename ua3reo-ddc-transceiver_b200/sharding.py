@@ -139,10 +139,10 @@ def _ipc_open(lib, kind, create_args, dist, group):
         if rc != 0:
             msg = lib.ua3reo_last_error().decode()
     elif rc == 0:
-        rc, msg = -5, "a peer rank could not create its end"
+        rc, msg = -5, ""                           # a peer could not create its end: its own message names the cause
     oks = [None] * world
     dist.all_gather_object(oks, (rc == 0, msg), group=group)
-    bad = [(r, m) for r, (ok, m) in enumerate(oks) if not ok]
+    bad = sorted(((r, m) for r, (ok, m) in enumerate(oks) if not ok), key=lambda rm: (rm[1] == "", rm[0]))
     if bad:                                        # every rank sees the same verdict: unmap, meet, free
         if handle is not None:
             fn("disconnect")(handle)
