@@ -603,19 +603,25 @@ rx_post_kernel(uint32_t n_blocks, const RxParams* __restrict__ params, RxState* 
 // each) and two consumer warps (rx_post_warp, 32 channels each).  A consumer starts on block b as soon as its two producers
 // have published it, while they are already filtering block b+1: the post stage costs one block of latency instead of a
 // whole push, which is what decides the step time at small channel counts (the chain is per-channel sequential).
-constexpr int kRxFusedProd = 4, kRxFusedCons = 2;
-__global__ void __launch_bounds__(32 * (kRxFusedProd + kRxFusedCons), UA3_RX_FUSED_MINB)
+// G such 64-channel groups share a CTA.  Two of them (384 threads x 168 registers) fill an SM's register file with ONE CTA:
+// the block scheduler places CTAs breadth first over the idle SMs, so 192-thread CTAs end up one per SM - twice the SMs for
+// the same warps - and every SM the stage holds is an SM the next push's front kernel has to wait for.  Twelve warps on
+// an SM run each about a quarter slower than six, though, so the packed form is for banks whose step leaves the stage time
+// (rx_launch_audio: from 2048 channels, where a block takes about 1.3 ms); measured at 4096 channels 2.865 -> 2.799 ms per step, at 1024 0.774 -> 0.812.
+template <int G>
+__global__ void __launch_bounds__(32 * 6 * G, G == 1 ? UA3_RX_FUSED_MINB : 1)
 rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t frame_ch_stride, uint32_t start,
                 uint32_t n_blocks, const RxParams* __restrict__ params, RxState* __restrict__ state, uint32_t n_ch,
                 const uint32_t* __restrict__ order, RxScratch scr, int32_t* __restrict__ audio_out, uint32_t out_ch_stride,
                 float* __restrict__ cw_mag, uint32_t cw_ch_stride) {
+    constexpr int kRxFusedProd = 4 * G, kRxFusedCons = 2 * G;
     __shared__ __align__(8) int2 s_tile[kRxFusedCons][32 * kRxTilePitch];
     __shared__ uint32_t s_ch[kRxFusedCons][32];
     __shared__ uint32_t s_done[kRxFusedProd];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < kRxFusedProd) s_done[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t cta_slot0 = blockIdx.x * 64u;
+    const uint32_t cta_slot0 = blockIdx.x * (64u * G);
     if (warp < kRxFusedProd) {
         const uint32_t slot0 = cta_slot0 + (uint32_t)warp * 16u;
         if (slot0 >= n_ch) return;
@@ -639,9 +645,9 @@ rx_audio_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_
 // channels per warp) instead of on two lanes of a per-channel warp.  Output: fin[frame][rail][sample][slot] floats
 // (512 / zoom samples per frame when zoomed), read back by rx_fft_kernel.
 // ------------------------------------------------------------------------------------------------
-constexpr int kRxFftPreWarps = 4;
+constexpr int kRxFftPreWarps = 16;      // 512 threads x 117 registers: one CTA fills an SM (128-thread CTAs were placed one per SM, see rx_audio_kernel)
 
-__global__ void __launch_bounds__(32 * kRxFftPreWarps, 4)
+__global__ void __launch_bounds__(32 * kRxFftPreWarps, 1)
 rx_fft_pre_kernel(const uint64_t* __restrict__ frames, uint32_t ring_mask, uint32_t frame_ch_stride, uint32_t start,
                   uint32_t n_frames, const RxParams* __restrict__ params, RxState* __restrict__ state, uint32_t n_ch,
                   const uint32_t* __restrict__ order, float* __restrict__ fin, uint32_t n_slot_pad) {
@@ -1143,8 +1149,12 @@ cudaError_t rx_launch_audio(const RxBuffers& b, uint32_t start, uint32_t n_block
                    b.n_ch, b.order, scr, b.audio_out, b.audio_ch_stride, b.cw_mag, b.max_audio_blocks);
         if (launches) *launches += 1;
     } else {
-        UA3_LAUNCH(rx_audio_kernel, (b.n_ch + 63u) / 64u, 32 * (kRxFusedProd + kRxFusedCons), 0, st, b.frames, b.ring_mask, b.frame_ch_stride,
-                   start, n_blocks, b.params, b.state, b.n_ch, b.order, scr, b.audio_out, b.audio_ch_stride, b.cw_mag, b.max_audio_blocks);
+        if (b.n_ch >= 2048u)
+            UA3_LAUNCH(rx_audio_kernel<2>, (b.n_ch + 127u) / 128u, 384, 0, st, b.frames, b.ring_mask, b.frame_ch_stride, start, n_blocks,
+                       b.params, b.state, b.n_ch, b.order, scr, b.audio_out, b.audio_ch_stride, b.cw_mag, b.max_audio_blocks);
+        else
+            UA3_LAUNCH(rx_audio_kernel<1>, (b.n_ch + 63u) / 64u, 192, 0, st, b.frames, b.ring_mask, b.frame_ch_stride, start, n_blocks,
+                       b.params, b.state, b.n_ch, b.order, scr, b.audio_out, b.audio_ch_stride, b.cw_mag, b.max_audio_blocks);
     }
 #endif
     if (launches) *launches += 1;
@@ -1157,9 +1167,8 @@ size_t rx_scratch_floats(uint32_t n_ch, uint32_t max_audio_blocks) {
 }
 
 int rx_audio_sms(uint32_t n_ch) {
-    // whole SMs rx_audio_kernel can fill: two CTAs of 64 channels per SM (register bound)
-    const uint32_t ctas = (n_ch + 63u) / 64u;
-    return (int)((ctas + 1u) / 2u);
+    // whole SMs rx_audio_kernel can fill: 128 channels per SM (register bound; two 64-channel CTAs or one of 128)
+    return (int)((n_ch + 127u) / 128u);
 }
 
 cudaError_t rx_launch_fft(const RxBuffers& b, uint32_t start, uint32_t n_frames, cudaStream_t st, int* launches) {
