@@ -18,9 +18,10 @@
 using namespace ua3;
 #include "rx_host.cpp.inc"
 
-// SMs the front kernel leaves to the STM32 stage (see push_common).  Measured (tools/gpu/sweep_rx_reserve.sh): 1024 channels
-// 1.022 / 1.037 / 1.071 ms per step at 6 / 8 / 12 SMs; 4096 channels 3.707 / 3.739 / 3.768 ms at 4 / 6 / 8.
-static constexpr int kRxReserveSmall = 5, kRxReserveLarge = 4;   // at least; the front kernel hands back every SM its round count does not need
+// SMs the front kernel leaves to the STM32 stage (see push_common): none since the stage's CTAs are packed and its streams have
+// the higher priority.  Earlier sweeps (tools/gpu/sweep_rx_reserve.sh, unpacked CTAs): 1024 channels 1.022 / 1.037 / 1.071 ms per
+// step at 6 / 8 / 12 SMs; 4096 channels 3.707 / 3.739 / 3.768 ms at 4 / 6 / 8.
+static constexpr int kRxReserveSmall = 0, kRxReserveLarge = 0;   // below / from 2048 channels (UA3REO_RX_RESERVE_SMS overrides); the front kernel hands back every SM its round count does not need
 static constexpr int kProfEvents = kDdcKernels + 3;   // 5 DDC kernels, rx_audio, rx_fft: 8 event points per block
 static thread_local std::string g_err;
 
@@ -468,7 +469,13 @@ static int push_common(ua3reo_ctx* c, const int16_t* src, size_t n, size_t* fram
         if (c->rx_on) {
             const char* env = std::getenv("UA3REO_RX_RESERVE_SMS");
             const int want = rx_audio_sms(c->n_ch);
-            const int cap = c->n_ch <= 2048u ? kRxReserveSmall : kRxReserveLarge;   // a longer step leaves the stage more time per SM
+            // From 2048 channels the stage's CTAs are packed onto whole SMs (rx.cu: rx_audio_kernel<2>) and nothing is set aside:
+            // its kernels are launched before the front kernel and take idle SMs, and the FFT kernel that follows them gets the
+            // SMs they vacate ahead of the waiting front CTAs (the rx streams have the higher priority).  Measured
+            // (tools/gpu/sweep_rx_reserve2.sh) at 4096 channels 2.743 / 2.752 / 2.765 / 2.787 / 2.811 ms per step with 0 / 1 / 2 / 4 /
+            // 6 SMs set aside, at 2048 channels 1.406 / 1.412 / 1.417 / 1.423 with 0 / 2 / 4 / 6, at 1024 channels (192-thread CTAs,
+            // sweep_rx_reserve3.sh) 0.783 / 0.796 / 0.794 with 0 / 2 / 5.
+            const int cap = c->n_ch < 2048u ? kRxReserveSmall : kRxReserveLarge;
             const int reserve = env ? std::atoi(env) : (want < cap ? want : cap);
             if (reserve > 0 && reserve < front_sms) front_sms -= reserve;
         }
