@@ -85,6 +85,29 @@ def golden_frames(adc, fcws, clocking=None):
     return np.stack(out)
 
 
+def golden_nco(n, fcw):
+    """(sin14, cos14) of the golden NCO (ua3g_nco: start phase 0, the documented output convention) for n samples"""
+    L = lib()
+    phase = (np.arange(n, dtype=np.int64) * int(fcw)) & 0x3FFFFF
+    uniq, inv = np.unique(phase, return_inverse=True)
+    s14 = np.zeros(uniq.size, np.int64)
+    c14 = np.zeros(uniq.size, np.int64)
+    s = ctypes.c_int32(0)
+    c = ctypes.c_int32(0)
+    for i, ph in enumerate(uniq):
+        L.ua3g_nco(int(ph), ctypes.byref(s), ctypes.byref(c))
+        s14[i], c14[i] = s.value, c.value
+    return s14[inv], c14[inv]
+
+
+def executed_mixer(adc, fcw):
+    """golden_mixer with the restated arithmetic replaced by the reference's own nco_shift.v, mixer.v and rx_mixer_shift.v,
+    executed (oracle/vlog_ref.py); only the NCO in front of them stays the golden model's."""
+    from . import vlog_ref
+    s14, c14 = golden_nco(len(adc), fcw)
+    return vlog_ref.rx_mixer_path(adc, s14), vlog_ref.rx_mixer_path(adc, c14)
+
+
 def golden_mixer(adc, fcw):
     """(x_i, x_q): the s23 words RX_CIC_I/Q.filter_in see for every ADC sample (golden NCO + mixer conventions)"""
     L = lib()

@@ -12,6 +12,8 @@ import ctypes
 import os
 import subprocess
 
+import numpy as np
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(_HERE, "_ref", "libua3_vlog.so")
 REF_FPGA = "/root/reference/FPGA"
@@ -41,6 +43,8 @@ def lib():
         for f in ("vl_field_width", "vl_field_length", "vl_field_signed"):
             getattr(L, f).restype, getattr(L, f).argtypes = ctypes.c_int, [vp, ctypes.c_int]
         L.vl_clock_edge.restype, L.vl_clock_edge.argtypes = ctypes.c_int, [vp, vp, ctypes.c_char_p]
+        L.vl_run.restype = ctypes.c_int
+        L.vl_run.argtypes = [vp, vp, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]
         _lib = L
     return _lib
 
@@ -94,3 +98,34 @@ class VModule:
     def clock(self, name):
         if self._L.vl_clock_edge(self._m, self._buf, name.encode()) != 0:
             raise KeyError("module has no process on posedge %s" % name)
+
+    def run(self, inputs, outputs, clock=None):
+        """Vector form: inputs {name: int array of n}, outputs [names]; per step the inputs are applied, the continuous
+        assignments settle, `clock` rises once (if given).  Returns {name: int64 array}, two's complement for signed signals."""
+        names = list(inputs)
+        n = len(np.asarray(inputs[names[0]]))
+        order = list(self._fields)
+        a = np.ascontiguousarray(np.stack([np.asarray(inputs[k], dtype=np.int64).astype(np.uint64) for k in names]))
+        out = np.zeros((len(outputs), n), np.uint64)
+        ii = np.array([order.index(k) for k in names], np.int32)
+        oi = np.array([order.index(k) for k in outputs], np.int32)
+        rc = self._L.vl_run(self._m, self._buf, clock.encode() if clock else None, n, len(names), ii.ctypes.data, a.ctypes.data,
+                            len(outputs), oi.ctypes.data, out.ctypes.data)
+        if rc != 0:
+            raise KeyError("vl_run failed (%d): unknown clock or a memory used as a scalar" % rc)
+        res = {}
+        for k, row in zip(outputs, out):
+            _, width, _, sgn = self._fields[k]
+            v = row.astype(np.int64)
+            res[k] = np.where(v >> (width - 1) != 0, v - (1 << width), v) if sgn and width < 64 else v
+        return res
+
+
+def rx_mixer_path(adc12, nco14):
+    """nco_shift.v -> mixer.v (lpm_mult, one pipeline register) -> rx_mixer_shift.v for whole streams, executed: the s23 word
+    RX_CIC.filter_in sees for every (ADC sample, NCO output) pair.  The one-clock latency of the multiplier is taken out."""
+    n12 = VModule("nco_shift").run({"in": np.asarray(nco14, np.int64) & 0x3FFF}, ["out"])["out"]
+    res = VModule("mixer").run({"dataa": np.asarray(adc12, np.int64) & 0xFFF, "datab": n12, "clken": np.ones(len(n12), np.int64)},
+                               ["result"], clock="clock")["result"]
+    out = VModule("rx_mixer_shift").run({"in": res & 0xFFFFFF}, ["out"])["out"]
+    return np.where(out >> 22 != 0, out - (1 << 23), out)             # out is declared unsigned [22:0]: read it as the s23 the CIC takes

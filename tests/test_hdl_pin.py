@@ -309,6 +309,11 @@ def test_golden_chain_equals_hdl_chain(oracle, t_rx, tau, cls):
     adc = rng.integers(-2048, 2048, n).astype(np.int16)
     fcw = int(rng.integers(1, 1 << 22))
     x_i, x_q = oracle.golden_mixer(adc, fcw)
+    from oracle import vlog_ref
+    if vlog_ref.available():              # the mixer path from the reference's own Verilog: the HDL chain then runs executed
+        e_i, e_q = oracle.executed_mixer(adc, fcw)                      # sources from the mixer inputs to the frame
+        assert np.array_equal(e_i, x_i) and np.array_equal(e_q, x_q)
+        x_i, x_q = e_i, e_q
     hf = hdl.frames_at(hdl.rx_chain(x_i, x_q, t_rx=t_rx), tau)
     g = oracle.GoldenDDC(fcw, cls).push(adc)
     lags = [lag for lag in range(4) if np.array_equal(hf[lag:lag + 390], g[:390])]

@@ -37,7 +37,9 @@ def main():
     names = []
     for name, kind, seed, fcw, t_rx, tau in CASES:
         adc = make_adc(kind, seed)
-        x_i, x_q = pyoracle.golden_mixer(adc, fcw)
+        x_i, x_q = pyoracle.executed_mixer(adc, fcw)          # nco_shift.v, mixer.v, rx_mixer_shift.v executed; the NCO is the golden model's
+        g_i, g_q = pyoracle.golden_mixer(adc, fcw)
+        assert np.array_equal(x_i, g_i) and np.array_equal(x_q, g_q), name
         ch = hdl_ref.rx_chain(x_i, x_q, t_rx=t_rx)
         hf = hdl_ref.frames_at(ch, tau)
         cls = classify(hf, adc, fcw)

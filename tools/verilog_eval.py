@@ -811,6 +811,28 @@ size_t vl_field_offset(const vl_module *m, int i) { return m->fields[i].offset; 
 int vl_field_width(const vl_module *m, int i) { return m->fields[i].width; }
 int vl_field_length(const vl_module *m, int i) { return m->fields[i].length; }
 int vl_field_signed(const vl_module *m, int i) { return m->fields[i].is_signed; }
+/* n steps of one module: inputs in[j * n + t] -> scalar field in_idx[j], continuous assignments, one rising edge of `clock` (none
+ * if clock is null: a combinational module), then out[k * n + t] = raw bits of scalar field out_idx[k] */
+int vl_run(const vl_module *m, void *s, const char *clock, size_t n, int n_in, const int *in_idx, const uint64_t *in,
+           int n_out, const int *out_idx, uint64_t *out) {
+    void (*edge)(void *) = 0;
+    if (clock) {
+        for (int i = 0; m->clocks[i].name; i++) if (!strcmp(m->clocks[i].name, clock)) edge = m->clocks[i].fn;
+        if (!edge) return -1;
+    }
+    for (int j = 0; j < n_in; j++) if (in_idx[j] < 0 || in_idx[j] >= m->n_fields || m->fields[in_idx[j]].length) return -2;
+    for (int k = 0; k < n_out; k++) if (out_idx[k] < 0 || out_idx[k] >= m->n_fields || m->fields[out_idx[k]].length) return -2;
+    for (size_t t = 0; t < n; t++) {
+        for (int j = 0; j < n_in; j++) {
+            const vl_field *f = &m->fields[in_idx[j]];
+            *(uint64_t *)((char *)s + f->offset) = in[(size_t)j * n + t] & (f->width >= 64 ? ~0ULL : ((1ULL << f->width) - 1ULL));
+        }
+        m->settle(s);
+        if (edge) edge(s);
+        for (int k = 0; k < n_out; k++) out[(size_t)k * n + t] = *(const uint64_t *)((const char *)s + m->fields[out_idx[k]].offset);
+    }
+    return 0;
+}
 int vl_clock_edge(const vl_module *m, void *s, const char *clock) {
     for (int i = 0; m->clocks[i].name; i++) if (!strcmp(m->clocks[i].name, clock)) { m->clocks[i].fn(s); return 0; }
     return -1;
