@@ -328,3 +328,55 @@ def test_committed_bus_vectors_are_current(tmp_path):
     assert sorted(fresh) == sorted(stored.files)
     for k in fresh:
         assert np.array_equal(fresh[k], stored[k]), k
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# two evaluation paths of the evaluator: the compiled C translation and a Python interpreter over the same typed tree
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not have_reference(), reason="needs the reference tree")
+@pytest.mark.parametrize("fname,cname,overrides,clocks,steps", [
+    ("DAC_corrector.v", "DAC_corrector", {}, ["clk_in"], 400),
+    ("data_delay.v", "data_delay", {}, ["clk_in"], 200),
+    ("data_delay.v", "data_delay_q", {"bus_length": 16, "delay_length": 130}, ["clk_in"], 300),
+    ("mixer.v", "mixer", {}, ["clock"], 400),
+    ("tx_summator.v", "tx_summator", {}, ["clock"], 400),
+    ("nco_shift.v", "nco_shift", {}, [], 200),
+    ("stm32_interface.v", "stm32_interface", {}, ["clk_in", "adcclk_in"], 3000)])
+def test_interpreter_equals_c_translation_verilog(fname, cname, overrides, clocks, steps):
+    import verilog_eval as V
+    vl = _vl()
+    mod = V.parse_file(os.path.join(V.REF, fname))
+    it = V.Interp(mod, overrides)
+    cm = vl.VModule(cname)
+    inputs = [s for s in it.e.sigs.values() if s.kind in ("input", "inout") and s.name not in clocks]
+    rng = np.random.default_rng(len(fname) + steps)
+    loop_vars = set()                                 # `for` counters are locals of the C translation (nothing else reads them)
+    for _, body in mod["always"]:
+        loop_vars |= it.e._loopvars_in(body)
+    names = [s.name for s in it.e.sigs.values() if s.name not in loop_vars]
+    for step in range(steps):
+        for s in inputs:
+            if s.name == "DATA_BUS":                                  # mostly commands and small data so that the state machine moves
+                v = int(rng.integers(0, 8)) if rng.random() < 0.5 else int(rng.integers(0, 256))
+                it.ext_in["DATA_BUS"] = v
+                cm["DATA_BUS__ext"] = v
+                continue
+            v = int(rng.integers(0, 1 << s.width)) if s.width < 63 else int(rng.integers(0, 1 << 62))
+            if s.name == "DATA_SYNC":
+                v = int(rng.random() < 0.2)
+            it.v[s.name] = v
+            cm[s.name] = v
+        it.settle()
+        cm.settle()
+        if clocks:
+            ck = clocks[int(rng.integers(0, len(clocks)))]
+            it.clock(ck)
+            cm.clock(ck)
+        for nme in names:
+            s = it.e.sigs[nme]
+            if s.kind == "input" and nme in clocks:
+                continue
+            if s.length:
+                assert [cm[(nme, i)] for i in range(s.length)] == list(it.v[nme]), "%s step %d: %s" % (cname, step, nme)
+            else:
+                assert cm[nme] == it.v[nme], "%s step %d: %s (C %d, interpreter %d)" % (cname, step, nme, cm[nme], it.v[nme])

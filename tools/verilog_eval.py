@@ -25,6 +25,9 @@ Not supported (none of the eight files needs it): case, functions/tasks, generat
 division, X/Z arithmetic, hierarchical names other than defparam.
 
   python tools/verilog_eval.py c <out.c> <file.v>[:param=value,...][@cname] ...     emit C for the listed modules
+
+`Interp` executes the same modules in Python over the same typed tree - a second evaluation path that the tests compare with
+the compiled translation step by step.
 """
 import os
 import re
@@ -783,6 +786,234 @@ class Emitter:
         if st[0] == "for":
             return {st[1][1][1]} | self._loopvars_in(st[4])
         return set()
+
+
+class Interp:
+    """The same module executed by a Python interpreter over the same typed tree - an independent evaluation path for the
+    C emitter above (tests/test_verilog_pin.py drives both with the same stimulus).  Values are Python integers, reduced to
+    the context width after every operation; LPM instances are evaluated from their parameters directly."""
+
+    def __init__(self, mod, overrides=None):
+        self.e = Emitter(mod, overrides)              # elaboration: parameters, widths, typing rules
+        self.m = mod
+        self.v = {}
+        for s in self.e.sigs.values():
+            self.v[s.name] = [0] * s.length if s.length else 0
+            if s.init is not None:
+                self.v[s.name] = const_eval(s.init, self.e.params) & ((1 << s.width) - 1)
+        self.ext_in, self.pipes = {}, {}
+        for lv, ex in mod["assigns"]:
+            if ex[0] == "tern" and ex[3][0] == "num" and ex[3][4]:
+                self.ext_in[lv[1]] = 0
+        for mtype, iname, conns in mod["inst"]:
+            n = int(self._par(iname, "lpm_pipeline", 0))
+            self.pipes[iname] = {"result": [0] * n, "overflow": [0] * n}
+        self.settle()
+
+    # -- values --
+    @staticmethod
+    def _sx(v, w):
+        v &= (1 << w) - 1
+        return v - (1 << w) if v >> (w - 1) else v
+
+    def _ext(self, v, w, W, S):
+        v &= (1 << w) - 1
+        if S and w < W:
+            v = self._sx(v, w)
+        return v & ((1 << W) - 1)
+
+    def _self(self, e):
+        w, s = self.e.size(e), self.e.signed(e)
+        return self.ev(e, w, s), w
+
+    def ev(self, e, W, S):
+        k, M = e[0], (1 << W) - 1
+        E = self.e
+        if k == "num":
+            return self._ext(e[1], e[2] if e[2] else 32, W, S)
+        if k == "id":
+            if e[1] in E.params:
+                return self._ext(E.params[e[1]], 32, W, S)
+            return self._ext(self.v[e[1]], E.size(e), W, S)
+        if k == "idx":
+            s = E.sig(e[1])
+            i, _ = self._self(e[2])
+            if s.length:
+                return self._ext(self.v[s.name][i if i < s.length else 0], s.width, W, S)
+            return (self.v[s.name] >> (i if i < s.width else 0)) & 1
+        if k == "range":
+            msb, lsb = const_eval(e[2], E.params), const_eval(e[3], E.params)
+            return (self.v[e[1]] >> lsb) & ((1 << (msb - lsb + 1)) - 1)
+        if k == "cat":
+            acc = 0
+            for x in e[1]:
+                c, w = self._self(x)
+                acc = (acc << w) | c
+            return acc & M
+        if k == "un":
+            if e[1] == "!":
+                return int(self._self(e[2])[0] == 0)
+            a = self.ev(e[2], W, S)
+            return a if e[1] == "+" else ((-a) & M if e[1] == "-" else (~a) & M)
+        if k == "bin":
+            op = e[1]
+            if op == "&&":
+                return int(self._self(e[2])[0] != 0 and self._self(e[3])[0] != 0)
+            if op == "||":
+                return int(self._self(e[2])[0] != 0 or self._self(e[3])[0] != 0)
+            if op in ("==", "!=", "<", "<=", ">", ">="):
+                w = max(E.size(e[2]), E.size(e[3]))
+                sg = E.signed(e[2]) and E.signed(e[3])
+                a, b = self.ev(e[2], w, sg), self.ev(e[3], w, sg)
+                if sg:
+                    a, b = self._sx(a, w), self._sx(b, w)
+                return int({"==": a == b, "!=": a != b, "<": a < b, "<=": a <= b, ">": a > b, ">=": a >= b}[op])
+            if op in ("<<", "<<<", ">>", ">>>"):
+                a, n = self.ev(e[2], W, S), self._self(e[3])[0]
+                if op in ("<<", "<<<"):
+                    return (a << n) & M if n < 64 else 0
+                if op == ">>>" and S:
+                    return (self._sx(a, W) >> min(n, 63)) & M
+                return a >> n if n < 64 else 0
+            a, b = self.ev(e[2], W, S), self.ev(e[3], W, S)
+            return {"+": a + b, "-": a - b, "*": a * b, "&": a & b, "|": a | b, "^": a ^ b}[op] & M
+        if k == "tern":
+            return self.ev(e[2], W, S) if self._self(e[1])[0] != 0 else self.ev(e[3], W, S)
+        raise VError("cannot interpret %r" % (e,))
+
+    # -- statements --
+    def _store(self, lv, val, target):
+        s = self.e.sig(lv[1])
+        if lv[0] == "id":
+            target[s.name] = val & ((1 << s.width) - 1)
+        elif lv[0] == "idx":
+            i, _ = self._self(lv[2])
+            if s.length:
+                arr = list(target[s.name])
+                arr[i if i < s.length else 0] = val & ((1 << s.width) - 1)
+                target[s.name] = arr
+            else:
+                i = i if i < s.width else 0
+                target[s.name] = (target[s.name] & ~(1 << i)) | ((val & 1) << i)
+        else:
+            msb, lsb = const_eval(lv[2], self.e.params), const_eval(lv[3], self.e.params)
+            m = ((1 << (msb - lsb + 1)) - 1)
+            target[s.name] = (target[s.name] & ~(m << lsb)) | ((val & m) << lsb)
+
+    def _lwidth(self, lv):
+        s = self.e.sig(lv[1])
+        if lv[0] == "id":
+            return s.width
+        if lv[0] == "idx":
+            return s.width if s.length else 1
+        return const_eval(lv[2], self.e.params) - const_eval(lv[3], self.e.params) + 1
+
+    def _assign(self, lv, rhs, target):
+        W = max(self._lwidth(lv), self.e.size(rhs))
+        self._store(lv, self.ev(rhs, W, self.e.signed(rhs)), target)
+
+    def _stmt(self, st, nba):
+        k = st[0]
+        if k == "block":
+            for x in st[1]:
+                self._stmt(x, nba)
+        elif k == "assign":
+            self._assign(st[1], st[2], nba if st[3] else self.v)
+        elif k == "if":
+            if self._self(st[1])[0] != 0:
+                self._stmt(st[2], nba)
+            elif st[3] is not None:
+                self._stmt(st[3], nba)
+        elif k == "for":
+            self._assign(st[1][1], st[1][2], self.v)
+            while self._self(st[2])[0] != 0:
+                self._stmt(st[4], nba)
+                self._assign(st[3][1], st[3][2], self.v)
+        else:
+            raise VError("statement %r" % (st,))
+
+    # -- LPM --
+    def _par(self, iname, name, default=None):
+        p = self.m["defparam"].get(iname, {})
+        if name not in p:
+            return default
+        ex = p[name]
+        return ex[1] if ex[0] in ("num", "str") else const_eval(ex, self.e.params)
+
+    def _lpm_now(self, mtype, iname, conns):
+        sgn = str(self._par(iname, "lpm_representation", "UNSIGNED")).upper() == "SIGNED"
+
+        def operand(port, w):
+            c, _ = self._self(conns[port])
+            return self._sx(c, w) if sgn else c
+        if mtype == "lpm_mult":
+            wa, wb, wp = (int(self._par(iname, k)) for k in ("lpm_widtha", "lpm_widthb", "lpm_widthp"))
+            prod = (operand("dataa", wa) * operand("datab", wb)) & ((1 << (wa + wb)) - 1)
+            return {"result": (prod >> max(0, wa + wb - wp)) & ((1 << wp) - 1)}
+        w = int(self._par(iname, "lpm_width"))
+        a, b = operand("dataa", w), operand("datab", w)
+        full = a + b if str(self._par(iname, "lpm_direction", "ADD")).upper() == "ADD" else a - b
+        res = full & ((1 << w) - 1)
+        ov = int(self._sx(res, w) != full) if sgn else (full >> w) & 1
+        return {"result": res, "overflow": ov}
+
+    # -- module --
+    def settle(self):
+        for _ in range(4):                            # a few passes reach the fixed point of these small netlists
+            for mtype, iname, conns in self.m["inst"]:
+                now = self._lpm_now(mtype, iname, conns)
+                for port, val in now.items():
+                    wire = conns.get(port)
+                    if wire is not None:
+                        pipe = self.pipes[iname][port]
+                        self.v[wire[1]] = (pipe[-1] if pipe else val) & ((1 << self.e.sig(wire[1]).width) - 1)
+            for lv, ex in self.m["assigns"]:
+                if lv[1] in self.ext_in and ex[0] == "tern" and ex[3][0] == "num" and ex[3][4]:
+                    s = self.e.sig(lv[1])
+                    oe = self._self(ex[1])[0] != 0
+                    self.v[lv[1] + "__oe"] = int(oe)
+                    val = self.ev(ex[2], max(s.width, self.e.size(ex[2])), self.e.signed(ex[2])) if oe else self.ext_in[lv[1]]
+                    self.v[lv[1]] = val & ((1 << s.width) - 1)
+                else:
+                    self._assign(lv, ex, self.v)
+
+    def clock(self, clk):
+        hit = False
+        for mtype, iname, conns in self.m["inst"]:
+            ck = conns.get("clock")
+            if ck is not None and ck[1] == clk and int(self._par(iname, "lpm_pipeline", 0)):
+                hit = True
+                if conns.get("clken") is None or self._self(conns["clken"])[0] != 0:
+                    now = self._lpm_now(mtype, iname, conns)
+                    for port, val in now.items():
+                        pipe = self.pipes[iname][port]
+                        pipe.insert(0, val)
+                        pipe.pop()
+        for c, body in self.m["always"]:
+            if c == clk:
+                hit = True
+                nba = {}
+                shadow = _NbaView(self.v, nba)
+                self._stmt(body, shadow)
+                for name, val in nba.items():
+                    self.v[name] = val
+        if not hit:
+            raise KeyError("no process on posedge %s" % clk)
+        self.settle()
+
+
+class _NbaView(dict):
+    """target of non-blocking assignments: reads of a not yet written name see the CURRENT value, writes go to the side"""
+
+    def __init__(self, cur, side):
+        super().__init__()
+        self.cur, self.side = cur, side
+
+    def __getitem__(self, k):
+        return self.side[k] if k in self.side else self.cur[k]
+
+    def __setitem__(self, k, v):
+        self.side[k] = v
 
 
 PRELUDE = r"""/* generated by tools/verilog_eval.py - the reference's Verilog translated to C.  TEST INFRASTRUCTURE ONLY. */
