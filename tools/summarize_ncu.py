@@ -47,6 +47,25 @@ def launches(path):
     print("| kernel | launches | total us | share | avg us |\n|---|---|---|---|---|")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("| %s | %d | %.1f | %.3f | %.1f |" % (k, v[0], v[1] / 1e3, v[1] / tot, v[1] / v[0] / 1e3))
+    # the front kernel's share of ONE DDC step (what bench.py reports as roofline.kernel_share_of_step): the launch list holds
+    # both workloads and the peak microbenchmarks, so the share is taken over the steps of the 1024-channel DDC workload -
+    # consecutive prepare / front / ciccomp / hilb / rotate launches with the shorter front kernel
+    seq, order = [], ("adc_prepare", "ddc_front_tc", "ddc_ciccomp", "ddc_hilb", "ddc_rotate")
+    named = []
+    for r in rows[1:]:
+        try:
+            named.append((r[ki].split('(')[0].replace('void ', ''), float(r[vi].replace(',', '')) / 1e3))
+        except ValueError:
+            pass
+    for i in range(len(named) - 4):
+        if all(named[i + j][0].startswith(order[j]) for j in range(5)):
+            seq.append([named[i + j][1] for j in range(5)])
+    if seq:
+        short = min(s[1] for s in seq) * 1.5
+        seq = [s for s in seq if s[1] < short]
+        m = [sum(s[j] for s in seq) / len(seq) for j in range(5)]
+        print("\nDDC workload, %d steps: prepare %.1f + front %.1f + ciccomp %.1f + hilb %.1f + rotate %.1f = %.1f us per step; "
+              "front kernel share %.3f" % ((len(seq),) + tuple(m) + (sum(m), m[1] / sum(m))))
 
 
 def full(rep, out):
