@@ -142,3 +142,23 @@ def frames_at(ch, tau, n_frames=None):
     out[:, 0::2] = words >> 8
     out[:, 1::2] = words & 0xFF
     return out if n_frames is None else out[:n_frames]
+
+
+def tx_chain(words, t_tx=0, tau=0):
+    """The transmit interpolators across their two clock domains, for one rail: TX_I / TX_Q as stm32_interface holds it (a new
+    word every 1024 clk_sys ticks, written `tau` ticks after the 48 kHz grid) -> tx_ciccomp on MAIN_PLL c3 = clk_sys x 23 / 512
+    (46 clocks per word, MAIN_PLL.v:117-119) -> tx_cic on clk_sys; both leave reset `t_tx` ticks after an instant at which
+    all clocks rise together (TX_N, UA3REO.bdf via tools/bdf_netlist.py).  Same [convention] as rx_chain: ideal PLL, a
+    register clocked at the same instant as its producer sees the producer's previous value.  Returns tx_cic.filter_out
+    (14 bits) after every clk_sys edge."""
+    words = np.asarray(words, np.int64)
+    n = words.size * 1024
+    j = np.arange(int(np.ceil(t_tx * 23 / 512.0)), int((t_tx + n) * 23 / 512.0))
+    t_c3 = j * 512.0 / 23.0 - t_tx                                      # c3 edges, in clk_sys ticks after the release
+    k = np.floor((t_c3 + t_tx - tau) / 1024.0).astype(np.int64)
+    w = np.where((k >= 0) & (k < words.size), words[np.clip(k, 0, words.size - 1)], 0)
+    comp = _sx(run("tx_ciccomp", w & 0xFFFF), 16)                       # after every c3 edge
+    e = np.arange(n, dtype=np.float64)
+    idx = np.searchsorted(t_c3, e, side="left") - 1                     # the last c3 edge strictly before the clk_sys edge
+    xin = np.where(idx >= 0, comp[np.clip(idx, 0, comp.size - 1)], 0)
+    return _sx(run("tx_cic", xin & 0xFFFF), 14)
