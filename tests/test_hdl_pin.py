@@ -402,3 +402,54 @@ def test_cuda_ddc_equals_hdl_vectors(pkg):
             got = np.concatenate(got, axis=1)
             assert np.array_equal(got[0, : frames.shape[0]], frames), name
             assert np.array_equal(got[2], got[0])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# committed TRANSMIT vectors: every stage but the NCO executed from the reference's HDL (tools/gen_golden_hdl_tx.py)
+# ------------------------------------------------------------------------------------------------------------------
+TX_GOLDEN = os.path.join(ROOT, "tests", "golden", "hdl_tx_cases.npz")
+
+
+def _tx_cases():
+    z = np.load(TX_GOLDEN)
+    for name in sorted(k[:-3] for k in z.files if k.endswith("_iq")):
+        yield name, z[name + "_iq"], int(z[name + "_meta"][0]), z[name + "_dac"], z[name + "_otr"]
+
+
+def test_golden_duc_equals_hdl_tx_vectors(oracle):
+    n_cases = 0
+    for name, iq, fcw, dac, otr in _tx_cases():
+        g_dac, g_otr = oracle.GoldenDUC(fcw).push(iq[:, 0], iq[:, 1])
+        assert np.array_equal(g_dac[:dac.size], dac), name
+        assert np.array_equal(g_otr[:otr.size], otr), name
+        assert dac.size == (iq.shape[0] - 2) * 1024 and dac.max() < (1 << 14)
+        n_cases += 1
+    assert n_cases == 6
+
+
+@needs_ref
+def test_committed_hdl_tx_vectors_are_current():
+    import gen_golden_hdl_tx
+    if not _hdl():
+        pytest.skip("no HDL library")
+    fresh = gen_golden_hdl_tx.generate()
+    stored = np.load(TX_GOLDEN)
+    assert sorted(fresh) == sorted(stored.files)
+    for k in fresh:
+        assert np.array_equal(fresh[k], stored[k]), k
+
+
+@pytest.mark.gpu
+def test_cuda_duc_equals_hdl_tx_vectors(pkg):
+    """The CUDA DUC against DAC words produced by the reference's own HDL (tx_ciccomp.vhd, tx_cic.vhd across their clock domains,
+    tx_mixer.v, tx_summator.v, DAC_corrector.v executed; NCO = the golden convention), through the C ABI, bit for bit."""
+    cases = list(_tx_cases())
+    n = cases[0][1].shape[0]
+    rx = pkg.Receiver(len(cases), 1 << 14)
+    rx.set_fcw(np.array([c[2] for c in cases], np.uint32))
+    rx.duc_enable(n)
+    rx.duc_push(np.stack([c[1] for c in cases]))
+    got = rx.duc_read_dac()
+    rx.close()
+    for ch, (name, iq, fcw, dac, otr) in enumerate(cases):
+        assert np.array_equal(got[ch, :dac.size], dac), name
