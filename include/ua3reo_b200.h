@@ -384,7 +384,9 @@ int ua3reo_bank_sync(ua3reo_bank *bank);
  *                   ua3reo_ddc_push_device(ctx, blk, n, &frames)     consumed in place (DEVICE PUSH CONTRACT above)
  *                   ua3reo_fanout_release(f, stream)                 the slot's credit goes back behind the push's kernels
  * Nothing here orders the processes' HOST threads: the waits are executed by the streams.  Sends run `n_buffers` - 1 blocks
- * ahead of the slowest consumer.  The reference has one board = one ADC = one channel (fpga.c:286-401 reads it frame by
+ * ahead of the slowest consumer.  One object is driven by one host thread at a time (like a context); acquire and release
+ * alternate; every rank makes the same sequence of calls (a rank that stops consuming stalls the ingest rank's copy stream
+ * once its credits are used up, nothing is dropped or overwritten).  The reference has one board = one ADC = one channel (fpga.c:286-401 reads it frame by
  * frame); this is the path's only exchange when its channels are spread over devices.
  * ------------------------------------------------------------------------------------------- */
 typedef struct ua3reo_fanout ua3reo_fanout;
